@@ -1,0 +1,147 @@
+/* kmc_b200 — C ABI of the B200 (sm_100a) implementation of KMC's per-bin stage 2.
+ *
+ * This is the drop-in boundary: a KMC build binds these entry points where its own CPU code does the
+ * per-bin work today.  File:line references are to refresh-bio/KMC 3.2.4.
+ *
+ *   seam #2 (the drop-in)  kmcb200_process_bin / kmcb200_submit_bin + kmcb200_wait_bin
+ *        replaces the body of CKmerBinSorter<SIZE>::ProcessBins  (kmc_core/kb_sorter.h:210-237):
+ *        Expand (:728-752) -> Sort (:757-780) -> Compact (:1287-1293) for one bin, i.e. everything
+ *        between sorters_manager->GetNext()/bd->read() and kq->push().
+ *   seam #1 (sort only)    kmcb200_sort_records
+ *        replaces SortFunction<CKmer<SIZE>> (kmc_core/raduls.h:19-20), i.e. RadulsSort::RadixSortMSD_*
+ *        (raduls_impl.h:769-776) / RadixSort::RadixSortMSD (radix.h:845-855), as called at kb_sorter.h:775.
+ *   device-level twins     kmcb200_dev_*  — same operations on buffers that already live in HBM
+ *        (used by bench.py for the kernel-only numbers and by hosts that keep bins resident).
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative kmcb200_status;
+ * kmcb200_last_error() gives the message.  A context is bound to one GPU and may be used by one host
+ * thread at a time (KMC runs one sorter thread per context).  There is NO CPU fallback: without a usable
+ * sm_100 device kmcb200_create fails with KMCB200_ERR_NO_DEVICE.
+ */
+#ifndef KMC_B200_H
+#define KMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMCB200_VERSION 1
+#define KMCB200_MAX_KMER_LEN 128          /* records of up to 4 x 64 bit */
+#define KMCB200_MAX_SLOTS 4
+
+typedef enum {
+	KMCB200_OK = 0,
+	KMCB200_ERR_INVALID = -1,             /* bad argument */
+	KMCB200_ERR_NO_DEVICE = -2,           /* no CUDA device / not sm_100 */
+	KMCB200_ERR_CUDA = -3,                /* CUDA runtime error (message in last_error) */
+	KMCB200_ERR_BIN_FORMAT = -4,          /* packs do not end on record boundaries / n_rec mismatch */
+	KMCB200_ERR_CAPACITY = -5,            /* out_capacity too small */
+	KMCB200_ERR_BUSY = -6                 /* slot already holds a submitted bin */
+} kmcb200_status;
+
+typedef struct kmcb200_ctx kmcb200_ctx;
+
+/* Per-run parameters: the fields CKmerBinSorter's constructor takes from CKMCParams (kb_sorter.h:165-200). */
+typedef struct {
+	uint32_t kmer_len;                    /* Params.kmer_len, 1..KMCB200_MAX_KMER_LEN */
+	uint32_t both_strands;                /* Params.both_strands: 1 = canonical k-mers */
+	uint32_t cutoff_min;                  /* Params.cutoff_min */
+	uint32_t cutoff_max;                  /* (uint32)Params.cutoff_max   (kb_sorter.h:186) */
+	uint32_t counter_max;                 /* (uint32)Params.counter_max  (kb_sorter.h:187) */
+	uint32_t lut_prefix_len;              /* Params.lut_prefix_len, >= 1, (kmer_len - lut_prefix_len) % 4 == 0 */
+	int32_t device;                       /* CUDA ordinal */
+	uint32_t n_slots;                     /* bins in flight per context (1..KMCB200_MAX_SLOTS); 2 overlaps copies with kernels */
+} kmcb200_params;
+
+int kmcb200_create(const kmcb200_params* params, kmcb200_ctx** out_ctx);
+void kmcb200_destroy(kmcb200_ctx* ctx);
+/* message of the last failure on this context (or of the last failed kmcb200_create when ctx == NULL) */
+const char* kmcb200_last_error(const kmcb200_ctx* ctx);
+
+/* bytes of one emitted database record: (k-p)/4 suffix bytes + counter bytes (kb_sorter.h:1132-1142, defs.h:154-159) */
+uint32_t kmcb200_out_rec_bytes(const kmcb200_ctx* ctx);
+/* size in bytes of the out buffer the reference reserves for a bin of n_rec k-mers (kb_reader.h:141-150) */
+uint64_t kmcb200_out_capacity(const kmcb200_ctx* ctx, uint64_t n_rec);
+/* entries of the per-bin LUT: 4^lut_prefix_len */
+uint64_t kmcb200_lut_entries(const kmcb200_ctx* ctx);
+
+/* Pinned host memory for bin / result buffers (cudaHostAlloc).  A host may instead cudaHostRegister its own arena. */
+int kmcb200_host_alloc(kmcb200_ctx* ctx, uint64_t bytes, void** out_ptr);
+int kmcb200_host_free(kmcb200_ctx* ctx, void* ptr);
+
+/* ---- seam #2: one bin, host buffers --------------------------------------------------------------
+ * Inputs  = what CKmerBinSorter::ProcessBins gets from sorters_manager->GetNext / bd->read / epd->pop:
+ *   superkmers/size : the bin byte stream (CMemoryBins::mba_input_file)        kb_sorter.h:216
+ *   n_rec           : number of k-mers in the bin (CBinDesc)                   kb_sorter.h:219
+ *   n_plus_x_recs   : (k+x)-mer estimate; accepted for signature parity, unused (we never build (k,x)-mers)
+ *   pack_bytes[n_packs] : byte length of every expander pack (CExpanderPackDesc, first of each pair,
+ *                     queues.h:376-396); packs start on record boundaries.  pack_recs may be NULL (unused).
+ * Outputs = what is handed to kq->push (kb_sorter.h:1273, queues.h:826):
+ *   out_suffix[0, *out_bytes) : the emitted records (one data pack (0, out_pos))
+ *   lut[4^p]                  : raw per-prefix counts (the completer does the prefix sum)
+ *   stats[4]                  : n_unique, n_cutoff_min, n_cutoff_max, n_total
+ * An empty bin (size == 0) is legal and yields zero output and a zero LUT (kb_reader.h:198-205).
+ */
+int kmcb200_process_bin(kmcb200_ctx* ctx, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, uint64_t n_plus_x_recs,
+	const uint64_t* pack_bytes, const uint64_t* pack_recs, uint32_t n_packs,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* out_bytes,
+	uint64_t* lut, uint64_t stats[4]);
+
+/* Asynchronous form: submit returns once the work is queued on the slot's stream; wait blocks until the
+ * bin's outputs are in the host buffers given to submit.  Host buffers should be pinned for real overlap. */
+int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, uint64_t n_plus_x_recs,
+	const uint64_t* pack_bytes, const uint64_t* pack_recs, uint32_t n_packs,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut);
+int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint64_t stats[4]);
+
+/* ---- seam #1: sort host records ------------------------------------------------------------------
+ * Contract of SortFunction (raduls.h:19-20, kb_sorter.h:775-779): n records of rec_bytes (multiple of 8,
+ * CKmer<SIZE> images) sorted ascending on bytes key_bytes-1..0; the result is left in `tmp` when key_bytes
+ * is odd and in `recs` when it is even.  Returns 1 / 0 for tmp / recs, negative on error. */
+int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, uint32_t rec_bytes, uint32_t key_bytes);
+
+/* ---- device-level entry points (pointers are DEVICE pointers, `stream` is a cudaStream_t or NULL) ---
+ * All work is enqueued on `stream` (NULL = slot 0's stream) and is asynchronous with respect to the host. */
+
+/* Expand + sort + count one bin that already lives in HBM.  d_superkmers must be 8-byte aligned and readable
+ * up to the next multiple of 8 past size.  pack_bytes is a HOST array.  d_result receives 8 x uint64:
+ * [0..3] stats, [4] emitted records, [5] capacity error flag, [6] bin-format error bits, [7] reserved. */
+int kmcb200_dev_process_bin(kmcb200_ctx* ctx, uint32_t slot,
+	const uint8_t* d_superkmers, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs,
+	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, void* stream);
+
+/* Individual stages, for per-kernel measurement.  d_recs/d_tmp hold n records of 8*ceil(k/32) bytes.
+ * kmcb200_dev_expand also leaves the histogram of the first radix digit in the slot's workspace, which
+ * kmcb200_dev_sort(..., hist_ready=1) consumes; with hist_ready=0 the sort counts the first digit itself.
+ * kmcb200_dev_sort returns 1 when the sorted records are in d_tmp, 0 when they are in d_recs. */
+int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkmers, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, uint64_t* d_result, void* stream);
+int kmcb200_dev_sort(kmcb200_ctx* ctx, uint32_t slot, void* d_recs, void* d_tmp, uint64_t n, uint32_t key_bytes,
+	int hist_ready, void* stream);
+int kmcb200_dev_count(kmcb200_ctx* ctx, uint32_t slot, const void* d_sorted, uint64_t n,
+	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, void* stream);
+
+/* Number of kernels this library has launched on the context so far (bench.py reports the delta). */
+uint64_t kmcb200_kernel_launches(const kmcb200_ctx* ctx);
+/* Duration in ms of the last-run stages of a slot, measured with CUDA events on the launching stream:
+ * ms[0] index+expand, ms[1] sort (all passes), ms[2] count/emit, ms[3..3+n_passes) the radix passes.
+ * Blocks until the slot's work has finished.  Returns the number of radix passes, negative on error. */
+int kmcb200_stage_times(kmcb200_ctx* ctx, uint32_t slot, float* ms, uint32_t capacity);
+
+/* Synthetic bin in stage 1's output format (kb_collector.cpp:34-90) for tests and benchmarks: super-k-mers are
+ * substrings (random strand, `err_ppm` substitutions per million symbols) of a random genome of genome_len
+ * symbols, with `a` ~ geometric(mean mean_extra), capped at 255, until exactly n_rec k-mers exist.
+ * Two-call protocol: with data == NULL it only returns the sizes.  pack_bytes holds one entry per <= 64 KiB pack. */
+int kmcb200_synth_bin(uint64_t seed, uint32_t kmer_len, uint64_t n_rec, uint64_t genome_len, double mean_extra,
+	uint32_t err_ppm, uint8_t* data, uint64_t data_capacity, uint64_t* size,
+	uint64_t* pack_bytes, uint32_t pack_capacity, uint32_t* n_packs, uint64_t* n_super_kmers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

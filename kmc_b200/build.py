@@ -1,0 +1,34 @@
+"""Builds kmc_b200/libkmc_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "kmc_b200.cu")
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("kmc_b200.cu", "common.cuh", "expand.cuh", "radix_sort.cuh", "count.cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", "kmc_b200.h")]
+OUT = os.path.join(HERE, "libkmc_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
+         "-Xcompiler", "-fvisibility=default"]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    if not os.path.exists(NVCC):
+        raise RuntimeError("nvcc not found at %s and %s is missing or stale" % (NVCC, OUT))
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

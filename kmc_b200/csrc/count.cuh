@@ -1,0 +1,275 @@
+// kmc_b200 — sorted-run counting and compaction (replaces CKmerBinSorter::CompactKmers,
+// kmc_core/kb_sorter.h:1128-1281, and for k % 32 != 0 the (k,x)-mer merge CompactKxmers :937-1122 +
+// kxmer_set.h, whose output is the same function of the sorted k-mer multiset).
+//
+// One pass over the sorted records, one CTA per tile, chained scan (decoupled look-back) for the output
+// offsets, so the kernel reads N*W bytes once and writes only the emitted database records:
+//   * run tails are found with one neighbour compare per record; ballots give a bitmap of tails, the
+//     previous set bit gives the run head -> run length, no scan needed; a run that started in an earlier
+//     tile is measured by a short backward probe of the (sorted) input followed, for giant runs, by a
+//     lower_bound binary search;
+//   * cutoffs and clamping exactly as kb_sorter.h:1174-1191: count < cutoff_min -> n_cutoff_min,
+//     else count > cutoff_max -> n_cutoff_max, else emit min(count, counter_max);
+//   * emitted record = (k-p)/4 suffix bytes, most significant first, + counter bytes, least significant
+//     first (:1198-1201); lut[prefix]++ (:1203) is aggregated per warp (match.any) and per tile (shared
+//     window) before it touches global memory.
+#pragma once
+#include "common.cuh"
+
+namespace kmcb {
+
+struct CountArgs {
+	const void* recs;        // sorted records
+	uint64_t n;
+	uint32_t n_tiles;
+	uint32_t k;
+	uint32_t lut_prefix_len;
+	uint32_t cutoff_min, cutoff_max, counter_max;
+	uint32_t counter_bytes;
+	uint32_t suffix_bytes;   // (k - p) / 4
+	uint8_t* out;            // emitted records
+	uint64_t out_capacity;   // bytes
+	uint64_t* lut;           // [4^p], zero-initialised
+	uint64_t* result;        // [0..3] n_unique, n_cutoff_min, n_cutoff_max, n_total; [4] emitted records; [5] error (capacity)
+	uint64_t* desc;          // [n_tiles] look-back chain
+	uint32_t epoch;
+	uint32_t* tile_counter;  // zero-initialised
+};
+
+template <int WORDS> struct CountCfg { static constexpr int kThreads = 512, kIpt = (WORDS == 1 ? 8 : WORDS == 2 ? 4 : 2); };
+
+constexpr int kLutWindow = 1024;
+
+template <int WORDS>
+__host__ __device__ constexpr int count_tile() { return CountCfg<WORDS>::kThreads * CountCfg<WORDS>::kIpt; }
+
+// dynamic shared memory: max(record tile + 1 lookahead, staging of emitted bytes + 32)
+template <int WORDS>
+inline size_t count_smem_bytes(uint32_t out_rec_bytes)
+{
+	const size_t a = (size_t)(count_tile<WORDS>() + 1) * 8 * WORDS;
+	const size_t b = (size_t)count_tile<WORDS>() * out_rec_bytes + 32;
+	return (a > b ? a : b) + 16;
+}
+
+// the p leading symbols of a k-mer (kmer.h:294-303 remove_suffix(2*(k-p)))
+template <int WORDS>
+__device__ __forceinline__ uint32_t rec_prefix(const Rec<WORDS>& r, uint32_t nbits)
+{
+	const uint32_t q = nbits >> 6, s = nbits & 63u;
+	uint64_t lo = r.w[0], hi = 0;
+#pragma unroll
+	for (int i = 1; i < WORDS; ++i) {
+		if (q == (uint32_t)i) lo = r.w[i];
+		if (q + 1 == (uint32_t)i) hi = r.w[i];
+	}
+	if (WORDS == 1) return (uint32_t)(lo >> s);
+	if (q + 1 >= (uint32_t)WORDS || s == 0) return (uint32_t)(lo >> s);
+	return (uint32_t)((hi << (64u - s)) | (lo >> s));
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(const CountArgs a)
+{
+	using R = Rec<WORDS>;
+	constexpr int THREADS = CountCfg<WORDS>::kThreads, IPT = CountCfg<WORDS>::kIpt, TILE = THREADS * IPT;
+	constexpr int WARPS = THREADS / 32, NW = TILE / 32;
+	extern __shared__ __align__(16) uint8_t dsm[];
+	R* srec = reinterpret_cast<R*>(dsm);
+	__shared__ uint32_t tailmask[NW], emitmask[NW], wordpre[NW];
+	__shared__ uint32_t lutwin[kLutWindow];
+	__shared__ uint32_t s_tile, s_warp[WARPS], s_emit_total;
+	__shared__ uint64_t s_run_head0, s_base;
+	__shared__ unsigned long long s_stats[3];
+
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const R* __restrict__ g = reinterpret_cast<const R*>(a.recs);
+
+	if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
+	if (tid < 3) s_stats[tid] = 0;
+	for (int i = tid; i < kLutWindow; i += THREADS) lutwin[i] = 0;
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint64_t first = (uint64_t)tile * TILE;
+	const uint64_t rem = a.n - first;
+	const uint32_t cnt = rem < (uint64_t)TILE ? (uint32_t)rem : (uint32_t)TILE;
+
+	R rec[IPT];
+#pragma unroll
+	for (int r = 0; r < IPT; ++r) {
+		const uint32_t i = r * THREADS + tid;
+		if (i < cnt) {
+			rec[r] = g[first + i];
+			srec[i] = rec[r];
+		}
+	}
+	if (tid == 0 && first + cnt < a.n) srec[cnt] = g[first + cnt];
+	__syncthreads();
+
+	// ---- head of the run that contains the first record of the tile (warp 0)
+	if (warp == 0) {
+		uint64_t h = first;
+		if (first != 0) {
+			const R key0 = srec[0];
+			uint64_t pos = first;
+			bool found = false;
+			for (int c = 0; c < 4 && !found; ++c) {
+				const bool valid = pos >= (uint64_t)lane + 1;
+				bool neq = true;
+				if (valid) neq = !rec_equal<WORDS>(g[pos - 1 - lane], key0);
+				const uint32_t m = __ballot_sync(0xffffffffu, neq);
+				if (m) {
+					h = pos - (uint32_t)(__ffs(m) - 1);
+					found = true;
+				} else
+					pos -= 32;
+			}
+			if (!found) {   // giant run: lower_bound of key0 in g[0, pos)
+				uint64_t lo = 0, hi = pos;
+				while (lo < hi) {
+					const uint64_t mid = (lo + hi) >> 1;
+					if (rec_less<WORDS>(g[mid], key0)) lo = mid + 1;
+					else hi = mid;
+				}
+				h = lo;
+			}
+		}
+		if (lane == 0) s_run_head0 = h;
+	}
+
+	// ---- run tails
+	uint32_t tailbits = 0;
+#pragma unroll
+	for (int r = 0; r < IPT; ++r) {
+		const uint32_t i = r * THREADS + tid;
+		bool tail = false;
+		if (i < cnt) tail = (first + i == a.n - 1) || !rec_equal<WORDS>(rec[r], srec[i + 1]);
+		const uint32_t w = __ballot_sync(0xffffffffu, tail);
+		if (lane == 0) tailmask[r * WARPS + warp] = w;
+		tailbits |= (uint32_t)tail << r;
+	}
+	__syncthreads();
+
+	// ---- run lengths, cutoffs
+	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
+	const uint32_t pfx0 = rec_prefix<WORDS>(srec[0], prefix_shift);
+	uint32_t emitbits = 0;
+	uint32_t value[IPT];
+	uint32_t n_unique = 0, n_min = 0, n_max = 0;
+#pragma unroll
+	for (int r = 0; r < IPT; ++r) {
+		const uint32_t i = r * THREADS + tid;
+		bool emit = false;
+		value[r] = 0;
+		if ((tailbits >> r) & 1u) {
+			// previous tail inside the tile
+			int wi = (int)(i >> 5);
+			uint32_t m = tailmask[wi] & ((1u << (i & 31u)) - 1u);
+			while (m == 0 && wi > 0) m = tailmask[--wi];
+			const uint64_t head = m ? first + (uint64_t)wi * 32 + (31 - __clz(m)) + 1 : s_run_head0;
+			const uint32_t count = (uint32_t)(first + i - head + 1);       // uint32 like kb_sorter.h:1153
+			++n_unique;
+			if (count < a.cutoff_min) ++n_min;
+			else if (count > a.cutoff_max) ++n_max;
+			else {
+				emit = true;
+				value[r] = count > a.counter_max ? a.counter_max : count;
+			}
+		}
+		const uint32_t w = __ballot_sync(0xffffffffu, emit);
+		if (lane == 0) emitmask[r * WARPS + warp] = w;
+		emitbits |= (uint32_t)emit << r;
+	}
+	// block-reduce the three counters
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		n_unique += __shfl_down_sync(0xffffffffu, n_unique, o);
+		n_min += __shfl_down_sync(0xffffffffu, n_min, o);
+		n_max += __shfl_down_sync(0xffffffffu, n_max, o);
+	}
+	if (lane == 0) {
+		atomicAdd(&s_stats[0], (unsigned long long)n_unique);
+		atomicAdd(&s_stats[1], (unsigned long long)n_min);
+		atomicAdd(&s_stats[2], (unsigned long long)n_max);
+	}
+	__syncthreads();
+
+	// ---- ranks of the emitted records: exclusive scan over the popcounts of the NW bitmap words
+	{
+		uint32_t c = tid < NW ? __popc(emitmask[tid]) : 0;
+		uint32_t inc = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc += x;
+		}
+		if (lane == 31) s_warp[warp] = inc;
+		__syncthreads();
+		uint32_t base = 0;
+		for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+		if (tid < NW) wordpre[tid] = base + inc - c;
+		if (tid == NW - 1) s_emit_total = base + inc;
+	}
+	__syncthreads();
+	const uint32_t emit_total = s_emit_total;
+	if (tid == 0) {
+		const uint64_t base = lookback_exclusive(a.desc, 1, tile, (uint64_t)emit_total, a.epoch);
+		s_base = base;
+		if (tile == a.n_tiles - 1) a.result[4] = base + emit_total;
+	}
+	// srec is dead from here on (every thread holds its records in registers): reuse it as the staging area
+	__syncthreads();
+
+	const uint32_t ob = a.suffix_bytes + a.counter_bytes;
+	const uint64_t base = s_base;
+	uint8_t* dst = a.out + base * ob;
+	const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);     // staging keeps the destination's 16-byte phase
+	uint8_t* stage = dsm + mis;
+	const bool fits = (base + emit_total) * (uint64_t)ob <= a.out_capacity;
+
+#pragma unroll
+	for (int r = 0; r < IPT; ++r) {
+		const uint32_t i = r * THREADS + tid;
+		const bool emit = (emitbits >> r) & 1u;
+		uint32_t pfx = 0xffffffffu;
+		if (emit) {
+			const uint32_t wi = i >> 5;
+			const uint32_t rnk = wordpre[wi] + __popc(emitmask[wi] & ((1u << (i & 31u)) - 1u));
+			uint8_t* o = stage + (size_t)rnk * ob;
+			for (uint32_t j = 0; j < a.suffix_bytes; ++j) o[j] = (uint8_t)rec_byte<WORDS>(rec[r], a.suffix_bytes - 1 - j);
+			for (uint32_t j = 0; j < a.counter_bytes; ++j) o[a.suffix_bytes + j] = (uint8_t)(value[r] >> (8 * j));
+			pfx = rec_prefix<WORDS>(rec[r], prefix_shift);
+		}
+		// lut[prefix]++ aggregated per warp
+		const uint32_t peers = __match_any_sync(0xffffffffu, pfx);
+		if (emit && (int)lane == __ffs(peers) - 1) {
+			const uint32_t c = __popc(peers);
+			const uint32_t d = pfx - pfx0;
+			if (d < (uint32_t)kLutWindow) atomicAdd(&lutwin[d], c);
+			else atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + pfx, (unsigned long long)c);
+		}
+	}
+	__syncthreads();
+
+	// ---- copy the staged bytes out: head bytes up to 16-byte alignment, 16-byte vectors, tail bytes
+	if (fits) {
+		const uint32_t total = emit_total * ob;
+		const uint32_t headb = min(total, (16u - mis) & 15u);
+		if (tid < headb) dst[tid] = stage[tid];
+		const uint32_t nvec = (total - headb) >> 4;
+		const uint4* sv = reinterpret_cast<const uint4*>(stage + headb);
+		uint4* dv = reinterpret_cast<uint4*>(dst + headb);
+		for (uint32_t v = tid; v < nvec; v += THREADS) dv[v] = sv[v];
+		const uint32_t done = headb + (nvec << 4);
+		if (tid < total - done) dst[done + tid] = stage[done + tid];
+	} else if (tid == 0)
+		a.result[5] = 1;
+
+	for (int i = tid; i < kLutWindow; i += THREADS) {
+		const uint32_t c = lutwin[i];
+		if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + pfx0 + i, (unsigned long long)c);
+	}
+	if (tid < 3 && s_stats[tid]) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + tid, s_stats[tid]);
+}
+
+}  // namespace kmcb

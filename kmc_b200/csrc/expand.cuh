@@ -1,0 +1,263 @@
+// kmc_b200 — super-k-mer expansion (replaces CKmerBinSorter::ExpandKmersBoth / ExpandKmersAll,
+// kmc_core/kb_sorter.h:251-362; for k % 32 != 0 also ExpandKxmersBoth/All :371-724 — we always expand to
+// plain k-mers, the emitted database depends only on the multiset of canonical k-mers).
+//
+// Input : the bin byte stream written by stage 1 (kb_collector.cpp:34-90): records
+//         [u8 a][ceil((k+a)/4) bytes], 2 bits per symbol, first symbol in bits 7-6 of the first byte.
+// Output: n_rec records Rec<WORDS>, byte image identical to CKmer<SIZE> (kmer.h:22-67).
+//
+// The stream is self-delimiting, so record starts need a walk.  Packs (one per <=64 KiB collector flush,
+// CExpanderPackDesc, queues.h:376-396) start on record boundaries and give the parallelism:
+//   1. walk_packs_kernel  : one thread per pack walks its records and writes, per super-k-mer, its byte offset
+//                           and the number of k-mers before it in the pack (both in a gap-free-per-pack region
+//                           addressed by pack_start / min_rec_bytes, so no allocation scan is needed);
+//   2. scan_packs_kernel  : exclusive scans over packs (k-mer base, output-tile base) + tile->pack map;
+//   3. expand_kernel      : one CTA per 2048 consecutive OUTPUT k-mers (perfect load balance whatever the
+//                           super-k-mer lengths): head flags + max-scan map every output slot to its
+//                           super-k-mer, then each thread extracts its k-mer straight from the packed bytes
+//                           with funnel shifts, reverse-complements it with brev, takes the canonical one and
+//                           stores it coalesced.  The histogram of the first radix digit is counted on the
+//                           way out, so the sort never re-reads the records just to count.
+#pragma once
+#include "common.cuh"
+
+namespace kmcb {
+
+constexpr int kExpandTile = 2048;
+constexpr int kExpandThreads = 256;
+
+struct ExpandArgs {
+	const uint8_t* bin;          // bin byte stream (device)
+	uint64_t size;
+	const uint64_t* pack_start;  // [n_packs + 1] byte offsets (device)
+	uint32_t n_packs;
+	uint32_t k;
+	uint32_t min_rec_bytes;      // 1 + ceil(k/4)
+	uint32_t both_strands;
+	uint64_t n_rec;              // expected number of k-mers (CBinDesc::n_rec)
+	// index produced by walk/scan
+	uint32_t* sk_off;            // [size / min_rec_bytes + 1]
+	uint32_t* sk_kpre;           // same
+	uint32_t* tile_first;        // [4 * size / kExpandTile + n_packs + 1] first super-k-mer of every output tile of a pack
+	uint32_t* pack_nsk;          // [n_packs]
+	uint32_t* pack_nk;           // [n_packs]
+	uint64_t* pack_kbase;        // [n_packs + 1]
+	uint32_t* pack_tbase;        // [n_packs + 1]
+	uint32_t* tile_pack;         // [n_rec / kExpandTile + n_packs + 1]
+	uint32_t* status;            // [0] error bits, [1] total tiles
+	// output
+	void* recs;
+	uint64_t* hist0;             // [256] histogram of record byte 0 (zero-initialised)
+};
+
+enum : uint32_t { kErrPackWalk = 1, kErrRecCount = 2 };
+
+__device__ __forceinline__ uint64_t tile_first_base(uint64_t pack_start, uint32_t p) { return pack_start * 4 / kExpandTile + p; }
+
+__global__ void __launch_bounds__(128) walk_packs_kernel(const ExpandArgs a)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= a.n_packs) return;
+	uint64_t pos = a.pack_start[p];
+	const uint64_t end = a.pack_start[p + 1];
+	const uint64_t slot = pos / a.min_rec_bytes;
+	const uint64_t tfb = tile_first_base(pos, p);
+	uint32_t j = 0, nk = 0, next_tile = 0;
+	while (pos < end) {
+		const uint32_t x = a.bin[pos];
+		a.sk_off[slot + j] = (uint32_t)pos;
+		a.sk_kpre[slot + j] = nk;
+		if (nk + x + 1 > next_tile * (uint32_t)kExpandTile) {   // this super-k-mer holds k-mer number next_tile * tile of the pack
+			a.tile_first[tfb + next_tile] = j;
+			++next_tile;
+		}
+		nk += x + 1;
+		pos += 1 + ((x + a.k + 3) >> 2);
+		++j;
+	}
+	if (pos != end) atomicOr(a.status, kErrPackWalk);
+	a.pack_nsk[p] = j;
+	a.pack_nk[p] = nk;
+}
+
+// single CTA: exclusive scans over packs
+__global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
+{
+	__shared__ uint64_t s_k[32];
+	__shared__ uint32_t s_t[32];
+	__shared__ uint64_t carry_k;
+	__shared__ uint32_t carry_t;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) { carry_k = 0; carry_t = 0; }
+	__syncthreads();
+	for (uint32_t base = 0; base < a.n_packs; base += 1024) {
+		const uint32_t p = base + tid;
+		const uint32_t nk = p < a.n_packs ? a.pack_nk[p] : 0;
+		const uint32_t nt = (nk + kExpandTile - 1) / kExpandTile;
+		uint64_t ik = nk;
+		uint32_t it = nt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			uint64_t tk = __shfl_up_sync(0xffffffffu, ik, o);
+			uint32_t tt = __shfl_up_sync(0xffffffffu, it, o);
+			if (lane >= (uint32_t)o) { ik += tk; it += tt; }
+		}
+		if (lane == 31) { s_k[warp] = ik; s_t[warp] = it; }
+		__syncthreads();
+		uint64_t bk = carry_k;
+		uint32_t bt = carry_t;
+		for (uint32_t w = 0; w < warp; ++w) { bk += s_k[w]; bt += s_t[w]; }
+		const uint64_t ek = bk + ik - nk;
+		const uint32_t et = bt + it - nt;
+		if (p < a.n_packs) {
+			a.pack_kbase[p] = ek;
+			a.pack_tbase[p] = et;
+			for (uint32_t t = 0; t < nt; ++t) a.tile_pack[et + t] = p;
+		}
+		__syncthreads();
+		if (tid == 1023) { carry_k = ek + nk; carry_t = et + nt; }
+		__syncthreads();
+	}
+	if (tid == 0) {
+		a.pack_kbase[a.n_packs] = carry_k;
+		a.pack_tbase[a.n_packs] = carry_t;
+		a.status[1] = carry_t;
+		if (carry_k != a.n_rec) atomicOr(a.status, kErrRecCount);
+	}
+}
+
+__device__ __forceinline__ uint64_t bswap64(uint64_t x)
+{
+	const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+	return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
+}
+// reverse the order of the 32 two-bit symbols of a word
+__device__ __forceinline__ uint64_t rev_symbols64(uint64_t x)
+{
+	const uint64_t y = __brevll(x);
+	return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+
+// k-mer number `s` of the super-k-mer whose packed symbols start at global byte address `payload`
+template <int WORDS>
+__device__ __forceinline__ Rec<WORDS> extract_kmer(const uint8_t* payload, uint32_t s, uint32_t k, bool canonical)
+{
+	const uint8_t* A = payload + (s >> 2);
+	const uint32_t sh = (s & 3u) * 2u;
+	const uintptr_t a0 = reinterpret_cast<uintptr_t>(A) & ~(uintptr_t)7;
+	const uint32_t bo = (uint32_t)(reinterpret_cast<uintptr_t>(A) - a0) * 8u + sh;    // 0..62: bit offset inside b[0]
+	const uintptr_t need_end = reinterpret_cast<uintptr_t>(A) + ((sh + 2u * k + 7u) >> 3);
+	uint64_t b[WORDS + 1];
+#pragma unroll
+	for (int i = 0; i <= WORDS; ++i) {
+		const uintptr_t wa = a0 + 8u * i;
+		b[i] = wa < need_end ? bswap64(__ldg(reinterpret_cast<const unsigned long long*>(wa))) : 0ull;
+	}
+	// t = the WORDS-word big number (t[0] most significant) holding bits [bo, bo + 64*WORDS)
+	uint64_t t[WORDS];
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i) t[i] = bo ? ((b[i] << bo) | (b[i + 1] >> (64u - bo))) : b[i];
+	// right-align the top 2k bits
+	const uint32_t rs = 64u * WORDS - 2u * k;     // 0..63
+	Rec<WORDS> f;
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i) {
+		// word i counted from the most significant end after the shift
+		uint64_t v = t[i] >> rs;
+		if (i > 0 && rs) v |= t[i - 1] << (64u - rs);
+		f.w[WORDS - 1 - i] = v;
+	}
+	if (!canonical) return f;
+	// reverse complement: reverse all symbols of the 64*WORDS-bit number (puts the k-mer top-aligned), complement, right-align
+	uint64_t u[WORDS];      // u[0] most significant
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i) u[i] = ~rev_symbols64(f.w[i]);      // f.w[i] (i-th least significant) becomes i-th most significant
+	Rec<WORDS> r;
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i) {
+		uint64_t v = u[i] >> rs;
+		if (i > 0 && rs) v |= u[i - 1] << (64u - rs);
+		r.w[WORDS - 1 - i] = v;
+	}
+	return rec_less<WORDS>(f, r) ? f : r;       // kmer < rev ? kmer : rev  (kb_sorter.h:340,356)
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandArgs a)
+{
+	constexpr int IPT = kExpandTile / kExpandThreads;    // 8
+	__shared__ uint16_t head[kExpandTile];
+	__shared__ uint32_t warp_max[kExpandThreads / 32];
+	__shared__ uint32_t hist[256];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	hist[tid] = 0;
+	const uint32_t total_tiles = a.status[1];
+	Rec<WORDS>* __restrict__ out = reinterpret_cast<Rec<WORDS>*>(a.recs);
+
+	for (uint32_t g = blockIdx.x; g < total_tiles; g += gridDim.x) {
+		const uint32_t p = a.tile_pack[g];
+		const uint32_t t = g - a.pack_tbase[p];
+		const uint64_t pstart = a.pack_start[p];
+		const uint64_t slot0 = pstart / a.min_rec_bytes;
+		const uint32_t nsk = a.pack_nsk[p];
+		const uint32_t nk = a.pack_nk[p];
+		const uint32_t tile_start = t * kExpandTile;
+		const uint32_t cnt = min((uint32_t)kExpandTile, nk - tile_start);
+		const uint32_t j_lo = a.tile_first[tile_first_base(pstart, p) + t];
+		const uint32_t* __restrict__ kpre = a.sk_kpre + slot0;
+		const uint32_t* __restrict__ off = a.sk_off + slot0;
+
+		__syncthreads();      // previous tile is done with head[]
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) head[i * kExpandThreads + tid] = 0;
+		__syncthreads();
+		// head flags: super-k-mer j_lo + r starts at output slot kpre - tile_start
+		for (uint32_t j = j_lo + 1 + tid; j < nsk; j += kExpandThreads) {
+			const uint32_t kp = kpre[j];
+			if (kp >= tile_start + cnt) break;
+			head[kp - tile_start] = (uint16_t)(j - j_lo);
+		}
+		__syncthreads();
+		// inclusive max-scan (blocked: 8 consecutive slots per thread)
+		uint32_t v[IPT];
+		uint32_t m = 0;
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			m = max(m, (uint32_t)head[tid * IPT + i]);
+			v[i] = m;
+		}
+		uint32_t inc = m;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc = max(inc, x);
+		}
+		if (lane == 31) warp_max[warp] = inc;
+		uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+		if (lane == 0) excl = 0;
+		__syncthreads();
+		for (uint32_t w = 0; w < warp; ++w) excl = max(excl, warp_max[w]);
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) head[tid * IPT + i] = (uint16_t)max(v[i], excl);
+		__syncthreads();
+
+		// striped extraction: consecutive lanes <-> consecutive output k-mers
+		const uint64_t obase = a.pack_kbase[p] + tile_start;
+#pragma unroll 2
+		for (int i = 0; i < IPT; ++i) {
+			const uint32_t slot = i * kExpandThreads + tid;
+			if (slot < cnt) {
+				const uint32_t j = j_lo + head[slot];
+				const uint32_t s = tile_start + slot - kpre[j];
+				const Rec<WORDS> r = extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0);
+				out[obase + slot] = r;
+				atomicAdd(&hist[(uint32_t)r.w[0] & 0xFFu], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	const uint32_t c = hist[tid];
+	if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.hist0) + tid, (unsigned long long)c);
+}
+
+}  // namespace kmcb

@@ -1,0 +1,655 @@
+// kmc_b200 — host side of the C ABI (include/kmc_b200.h): context, HBM workspace, launch sequences.
+// The per-bin sequence mirrors CKmerBinSorter<SIZE>::ProcessBins (kmc_core/kb_sorter.h:210-237):
+//   Expand (index + expand kernels) -> Sort (one radix_pass_kernel per key byte) -> Compact (count_emit_kernel).
+#include "../../include/kmc_b200.h"
+#include "common.cuh"
+#include "expand.cuh"
+#include "radix_sort.cuh"
+#include "count.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace kmcb;
+
+namespace {
+
+constexpr int kMaxPasses = 4 * 8;                 // key bytes of a 4-word record
+constexpr int kHistRows = kMaxPasses + 1;
+constexpr int kCounterSlots = kMaxPasses + 8;     // tile counters: one per pass + [kMaxPasses] for count_emit
+constexpr uint32_t kEpochLimit = (1u << 22) - 2;
+constexpr int kStageRing = 4;
+
+thread_local std::string g_create_error;
+
+struct ZeroBlock {                                // zeroed with one memset at the start of every bin
+	uint64_t hist[kHistRows][256];
+	uint32_t counters[kCounterSlots];
+	uint32_t status[2];                           // expand: [0] error bits, [1] total tiles
+	uint32_t pad[6];
+};
+
+struct Slot {
+	cudaStream_t stream = nullptr;
+	// records
+	uint8_t* recs_a = nullptr; size_t recs_a_cap = 0;
+	uint8_t* recs_b = nullptr; size_t recs_b_cap = 0;
+	// bin + index
+	uint8_t* d_bin = nullptr; size_t bin_cap = 0;
+	uint64_t* d_pack_start = nullptr; size_t packs_cap = 0;
+	uint64_t* h_pack_start[kStageRing] = {}; cudaEvent_t ev_pack[kStageRing] = {}; int ring = 0;   // pinned staging of the pack offsets
+	uint32_t* pack_nsk = nullptr; uint32_t* pack_nk = nullptr; uint32_t* pack_tbase = nullptr; uint64_t* pack_kbase = nullptr;
+	uint32_t* sk_off = nullptr; size_t sk_off_cap = 0;
+	uint32_t* sk_kpre = nullptr; size_t sk_kpre_cap = 0;
+	uint32_t* tile_first = nullptr; size_t tile_first_cap = 0;
+	uint32_t* tile_pack = nullptr; size_t tile_pack_cap = 0;
+	ZeroBlock* zero = nullptr;
+	uint64_t* desc = nullptr; size_t desc_cap = 0;          // radix look-back descriptors
+	uint64_t* cdesc = nullptr; size_t cdesc_cap = 0;        // count look-back descriptors
+	// outputs of the host-buffer path
+	uint8_t* d_out = nullptr; size_t out_cap = 0;
+	uint64_t* d_lut = nullptr;
+	uint64_t* d_result = nullptr; uint64_t* h_result = nullptr;
+	// events
+	cudaEvent_t ev_begin = nullptr, ev_expand = nullptr, ev_sort = nullptr, ev_count = nullptr, ev_result = nullptr;
+	cudaEvent_t ev_pass[kMaxPasses + 1] = {};
+	int n_passes_run = 0;
+	bool ran_expand = false, ran_sort = false, ran_count = false;
+	// pending host-buffer bin
+	bool busy = false;
+	uint8_t* host_out = nullptr; uint64_t host_out_cap = 0; uint64_t* host_lut = nullptr; uint64_t pending_n_rec = 0;
+};
+
+}  // namespace
+
+struct kmcb200_ctx {
+	kmcb200_params prm{};
+	int words = 1;
+	uint32_t key_bytes = 0, suffix_bytes = 0, counter_bytes = 0;
+	uint64_t lut_entries = 0;
+	int sm_count = 0;
+	int occ_radix = 1, occ_expand = 1;
+	uint32_t epoch = 1;
+	uint64_t launches = 0;
+	std::vector<Slot> slots;
+	std::string err;
+};
+
+namespace {
+
+int fail(kmcb200_ctx* c, int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (c) c->err = buf;
+	else g_create_error = buf;
+	return code;
+}
+
+#define CU(call)                                                                                             \
+	do {                                                                                                     \
+		cudaError_t e_ = (call);                                                                             \
+		if (e_ != cudaSuccess) return fail(ctx, KMCB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+uint32_t byte_log(uint64_t x) { return x < (1u << 8) ? 1 : x < (1u << 16) ? 2 : x < (1u << 24) ? 3 : 4; }   // defs.h:121
+
+template <typename T>
+int ensure(kmcb200_ctx* ctx, T*& p, size_t& cap, size_t need_elems, bool zero = false)
+{
+	if (need_elems <= cap && p) return 0;
+	size_t n = std::max<size_t>(need_elems + need_elems / 8, 1024);
+	if (p) CU(cudaFree(p));
+	p = nullptr; cap = 0;
+	CU(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T) + 256));
+	if (zero) { CU(cudaMemset(p, 0, n * sizeof(T) + 256)); CU(cudaDeviceSynchronize()); }   // the slot streams are non-blocking
+	cap = n;
+	return 0;
+}
+
+uint32_t next_epoch(kmcb200_ctx* ctx)
+{
+	if (ctx->epoch >= kEpochLimit) {           // wrap: forget every descriptor ever written
+		for (auto& s : ctx->slots) {
+			if (s.desc) cudaMemset(s.desc, 0, s.desc_cap * sizeof(uint64_t));
+			if (s.cdesc) cudaMemset(s.cdesc, 0, s.cdesc_cap * sizeof(uint64_t));
+		}
+		cudaDeviceSynchronize();
+		ctx->epoch = 1;
+	}
+	return ctx->epoch++;
+}
+
+// --------------------------------------------------------------------------------------------- per-WORDS launchers
+template <int WORDS>
+int setup_kernels(kmcb200_ctx* ctx)
+{
+	CU(cudaFuncSetAttribute(radix_pass_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortSmem<WORDS>::kBytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_radix, radix_pass_kernel<WORDS>, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_expand, expand_kernel<WORDS>, kExpandThreads, 0));
+	const size_t cs = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
+	CU(cudaFuncSetAttribute(count_emit_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
+	if (ctx->occ_radix < 1) ctx->occ_radix = 1;
+	if (ctx->occ_expand < 1) ctx->occ_expand = 1;
+	return 0;
+}
+
+template <int WORDS>
+int launch_expand(kmcb200_ctx* ctx, const ExpandArgs& a, cudaStream_t st)
+{
+	const uint32_t max_tiles = (uint32_t)(a.n_rec / kExpandTile) + a.n_packs + 1;
+	const uint32_t grid = std::min<uint32_t>(max_tiles, (uint32_t)(ctx->sm_count * ctx->occ_expand));
+	expand_kernel<WORDS><<<grid, kExpandThreads, 0, st>>>(a);
+	ctx->launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+template <int WORDS>
+int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, bool hist_ready, cudaStream_t st)
+{
+	constexpr int TILE = SortSmem<WORDS>::kTile;
+	const uint64_t n_tiles64 = (n + TILE - 1) / TILE;
+	if (n_tiles64 > 0x7fffffffull) return fail(ctx, KMCB200_ERR_INVALID, "bin too large: %llu records", (unsigned long long)n);
+	const uint32_t n_tiles = (uint32_t)n_tiles64;
+	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
+	if (!hist_ready) {
+		CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
+		const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 511) / 512, (uint64_t)ctx->sm_count * 4);
+		digit_histogram_kernel<WORDS><<<grid, 512, 0, st>>>(a, n, 0, s.zero->hist[0]);
+		ctx->launches++;
+	}
+	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix));
+	void* in = a; void* out = b;
+	CU(cudaEventRecord(s.ev_pass[0], st));
+	for (uint32_t pass = 0; pass < key_bytes; ++pass) {
+		SortPass p;
+		p.in = in; p.out = out; p.n = n; p.n_tiles = n_tiles; p.byte = pass;
+		p.next_byte = pass + 1 < key_bytes ? (int32_t)(pass + 1) : -1;
+		p.hist = s.zero->hist[pass];
+		p.hist_next = s.zero->hist[pass + 1];
+		p.desc = s.desc;
+		p.epoch = next_epoch(ctx);
+		p.tile_counter = &s.zero->counters[pass];
+		radix_pass_kernel<WORDS><<<grid, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes, st>>>(p);
+		ctx->launches++;
+		CU(cudaEventRecord(s.ev_pass[pass + 1], st));
+		std::swap(in, out);
+	}
+	CU(cudaGetLastError());
+	s.n_passes_run = (int)key_bytes;
+	return 0;
+}
+
+template <int WORDS>
+int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
+	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+{
+	constexpr int TILE = count_tile<WORDS>();
+	const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
+	if (int rc = ensure(ctx, s.cdesc, s.cdesc_cap, (size_t)n_tiles, true)) return rc;
+	CountArgs a;
+	a.recs = sorted; a.n = n; a.n_tiles = n_tiles; a.k = ctx->prm.kmer_len; a.lut_prefix_len = ctx->prm.lut_prefix_len;
+	a.cutoff_min = ctx->prm.cutoff_min; a.cutoff_max = ctx->prm.cutoff_max; a.counter_max = ctx->prm.counter_max;
+	a.counter_bytes = ctx->counter_bytes; a.suffix_bytes = ctx->suffix_bytes;
+	a.out = d_out; a.out_capacity = out_capacity; a.lut = d_lut; a.result = d_result;
+	a.desc = s.cdesc; a.epoch = next_epoch(ctx); a.tile_counter = &s.zero->counters[kMaxPasses];
+	const size_t smem = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
+	count_emit_kernel<WORDS><<<n_tiles, CountCfg<WORDS>::kThreads, smem, st>>>(a);
+	ctx->launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+#define DISPATCH_WORDS(ctx, fn, ...)                                   \
+	((ctx)->words == 1 ? fn<1>(__VA_ARGS__) : (ctx)->words == 2 ? fn<2>(__VA_ARGS__) \
+	 : (ctx)->words == 3 ? fn<3>(__VA_ARGS__) : fn<4>(__VA_ARGS__))
+
+// --------------------------------------------------------------------------------------------- stages
+int set_device(kmcb200_ctx* ctx) { CU(cudaSetDevice(ctx->prm.device)); return 0; }
+
+int check_slot(kmcb200_ctx* ctx, uint32_t slot)
+{
+	if (!ctx) return KMCB200_ERR_INVALID;
+	if (slot >= ctx->slots.size()) return fail(ctx, KMCB200_ERR_INVALID, "slot %u out of range (n_slots=%zu)", slot, ctx->slots.size());
+	return 0;
+}
+
+// index + expand; pack_bytes is a host array (may be null / empty: the whole bin is one pack)
+int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st)
+{
+	if (size >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin of %llu bytes: bins of 4 GiB or more are not supported", (unsigned long long)size);
+	const uint32_t k = ctx->prm.kmer_len;
+	const uint32_t min_rec = 1 + (k + 3) / 4;
+	const uint32_t np = (n_packs && pack_bytes) ? n_packs : 1;
+	// host prefix sum of the pack sizes -> device
+	if (np + 1 > s.packs_cap) {
+		const size_t cap = np + np / 4 + 64;
+		CU(cudaStreamSynchronize(st));
+		for (int i = 0; i < kStageRing; ++i) {
+			if (s.h_pack_start[i]) CU(cudaFreeHost(s.h_pack_start[i]));
+			s.h_pack_start[i] = nullptr;
+		}
+		for (void* p : {(void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase, (void*)s.pack_kbase})
+			if (p) CU(cudaFree(p));
+		s.packs_cap = 0;
+		for (int i = 0; i < kStageRing; ++i) CU(cudaHostAlloc(reinterpret_cast<void**>(&s.h_pack_start[i]), cap * 8, cudaHostAllocDefault));
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.d_pack_start), cap * 8));
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_nsk), cap * 4));
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_nk), cap * 4));
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_tbase), cap * 4));
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_kbase), cap * 8));
+		s.packs_cap = cap;
+	}
+	// host prefix sum of the pack sizes into a pinned staging buffer (ring: the copy of an earlier bin may still be queued)
+	s.ring = (s.ring + 1) % kStageRing;
+	CU(cudaEventSynchronize(s.ev_pack[s.ring]));
+	uint64_t* hps = s.h_pack_start[s.ring];
+	uint64_t acc = 0;
+	if (n_packs && pack_bytes) {
+		for (uint32_t i = 0; i < np; ++i) { hps[i] = acc; acc += pack_bytes[i]; }
+	}
+	else acc = size;
+	hps[0] = 0;
+	hps[np] = acc;
+	if (acc != size) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander packs cover %llu bytes but the bin has %llu", (unsigned long long)acc, (unsigned long long)size);
+	CU(cudaMemcpyAsync(s.d_pack_start, hps, (np + 1) * 8, cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(s.ev_pack[s.ring], st));
+
+	if (int rc = ensure(ctx, s.sk_off, s.sk_off_cap, size / min_rec + 2)) return rc;
+	if (int rc = ensure(ctx, s.sk_kpre, s.sk_kpre_cap, size / min_rec + 2)) return rc;
+	if (int rc = ensure(ctx, s.tile_first, s.tile_first_cap, size * 4 / kExpandTile + np + 2)) return rc;
+	if (int rc = ensure(ctx, s.tile_pack, s.tile_pack_cap, n_rec / kExpandTile + np + 2)) return rc;
+
+	ExpandArgs a;
+	a.bin = d_bin; a.size = size; a.pack_start = s.d_pack_start; a.n_packs = np; a.k = k; a.min_rec_bytes = min_rec;
+	a.both_strands = ctx->prm.both_strands; a.n_rec = n_rec;
+	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
+	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.status = s.zero->status;
+	a.recs = d_recs; a.hist0 = s.zero->hist[0];
+
+	CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
+	walk_packs_kernel<<<(np + 127) / 128, 128, 0, st>>>(a);
+	scan_packs_kernel<<<1, 1024, 0, st>>>(a);
+	ctx->launches += 2;
+	CU(cudaGetLastError());
+	return DISPATCH_WORDS(ctx, launch_expand, ctx, a, st);
+}
+
+int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
+	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+{
+	CU(cudaMemsetAsync(d_lut, 0, ctx->lut_entries * 8, st));
+	CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
+	CU(cudaMemsetAsync(&s.zero->counters[kMaxPasses], 0, sizeof(uint32_t), st));
+	if (n == 0) return 0;
+	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, st);
+}
+
+__global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uint32_t* status)
+{
+	result[3] = n_rec;              // n_total = n_rec (kb_sorter.h:1166)
+	result[6] = status ? status[0] : 0;
+}
+
+// Expand -> Sort -> Compact on device buffers; records live in the slot workspace
+int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
+	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+{
+	const size_t rec_bytes = (size_t)ctx->words * 8;
+	s.ran_expand = s.ran_sort = s.ran_count = false;
+	CU(cudaEventRecord(s.ev_begin, st));
+	if (n_rec == 0 || size == 0) {
+		if (n_rec != 0 || size != 0) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin with size=%llu but n_rec=%llu", (unsigned long long)size, (unsigned long long)n_rec);
+		if (int rc = stage_count(ctx, s, nullptr, 0, d_out, out_capacity, d_lut, d_result, st)) return rc;
+		CU(cudaEventRecord(s.ev_expand, st)); CU(cudaEventRecord(s.ev_sort, st)); CU(cudaEventRecord(s.ev_count, st));
+		s.n_passes_run = 0;
+		return 0;
+	}
+	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, n_rec * rec_bytes)) return rc;
+	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n_rec * rec_bytes)) return rc;
+	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st)) return rc;
+	CU(cudaEventRecord(s.ev_expand, st));
+	s.ran_expand = true;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, true, st)) return rc;
+	CU(cudaEventRecord(s.ev_sort, st));
+	s.ran_sort = true;
+	const void* sorted = (ctx->key_bytes & 1) ? s.recs_b : s.recs_a;
+	if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
+	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status);
+	ctx->launches++;
+	CU(cudaEventRecord(s.ev_count, st));
+	s.ran_count = true;
+	return 0;
+}
+
+}  // namespace
+
+// ================================================================================================= C ABI
+extern "C" {
+
+int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
+{
+	kmcb200_ctx* ctx = nullptr;     // fail() then records into the thread-local create error
+	if (!prm || !out_ctx) return fail(ctx, KMCB200_ERR_INVALID, "null argument");
+	*out_ctx = nullptr;
+	if (prm->kmer_len < 1 || prm->kmer_len > KMCB200_MAX_KMER_LEN)
+		return fail(ctx, KMCB200_ERR_INVALID, "kmer_len %u outside 1..%d", prm->kmer_len, KMCB200_MAX_KMER_LEN);
+	if (prm->lut_prefix_len < 1 || prm->lut_prefix_len >= prm->kmer_len || prm->lut_prefix_len > 15 || (prm->kmer_len - prm->lut_prefix_len) % 4 != 0)
+		return fail(ctx, KMCB200_ERR_INVALID, "lut_prefix_len %u illegal for k=%u: need 1 <= p <= 15, p < k, (k-p) %% 4 == 0 (kmc.h:1434-1469)", prm->lut_prefix_len, prm->kmer_len);
+	if (prm->n_slots < 1 || prm->n_slots > KMCB200_MAX_SLOTS) return fail(ctx, KMCB200_ERR_INVALID, "n_slots %u outside 1..%d", prm->n_slots, KMCB200_MAX_SLOTS);
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+		return fail(ctx, KMCB200_ERR_NO_DEVICE, "no CUDA device visible: kmc_b200 has no CPU fallback");
+	if (prm->device < 0 || prm->device >= n_dev) return fail(ctx, KMCB200_ERR_NO_DEVICE, "device %d not present (%d visible)", prm->device, n_dev);
+	cudaDeviceProp dp;
+	if (cudaGetDeviceProperties(&dp, prm->device) != cudaSuccess) return fail(ctx, KMCB200_ERR_CUDA, "cudaGetDeviceProperties failed");
+	if (dp.major != 10) return fail(ctx, KMCB200_ERR_NO_DEVICE, "device %d is sm_%d%d; kmc_b200 is built for sm_100a only", prm->device, dp.major, dp.minor);
+
+	ctx = new kmcb200_ctx();
+	ctx->prm = *prm;
+	ctx->words = (int)((prm->kmer_len + 31) / 32);
+	ctx->key_bytes = (prm->kmer_len + 3) / 4;                                  // rec_len, kb_sorter.h:769
+	ctx->suffix_bytes = (prm->kmer_len - prm->lut_prefix_len) / 4;             // kb_sorter.h:1132-1133
+	ctx->counter_bytes = prm->counter_max == 1 ? 0 : std::min(byte_log(prm->cutoff_max), byte_log(prm->counter_max));   // defs.h:154-159
+	ctx->lut_entries = 1ull << (2 * prm->lut_prefix_len);
+	ctx->sm_count = dp.multiProcessorCount;
+	ctx->slots.resize(prm->n_slots);
+	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };
+	if (cudaSetDevice(prm->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(KMCB200_ERR_CUDA); }
+	if (int rc = DISPATCH_WORDS(ctx, setup_kernels, ctx)) return bail(rc);
+	for (auto& s : ctx->slots) {
+		bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.zero), sizeof(ZeroBlock)) == cudaSuccess;
+		ok = ok && cudaMemset(s.zero, 0, sizeof(ZeroBlock)) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_lut), ctx->lut_entries * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_result), 64) == cudaSuccess;
+		ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_result), 64, cudaHostAllocDefault) == cudaSuccess;
+		for (cudaEvent_t* e : {&s.ev_begin, &s.ev_expand, &s.ev_sort, &s.ev_count, &s.ev_result}) ok = ok && cudaEventCreate(e) == cudaSuccess;
+		for (auto& e : s.ev_pass) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+		for (auto& e : s.ev_pack) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+		if (!ok) { ctx->err = std::string("slot allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return bail(KMCB200_ERR_CUDA); }
+	}
+	*out_ctx = ctx;
+	return KMCB200_OK;
+}
+
+void kmcb200_destroy(kmcb200_ctx* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->prm.device);
+	cudaDeviceSynchronize();
+	for (auto& s : ctx->slots) {
+		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
+				 (void*)s.pack_kbase, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
+				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result})
+			if (p) cudaFree(p);
+		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
+		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
+		if (s.h_result) cudaFreeHost(s.h_result);
+		for (cudaEvent_t e : {s.ev_begin, s.ev_expand, s.ev_sort, s.ev_count, s.ev_result}) if (e) cudaEventDestroy(e);
+		for (auto e : s.ev_pass) if (e) cudaEventDestroy(e);
+		if (s.stream) cudaStreamDestroy(s.stream);
+	}
+	delete ctx;
+}
+
+const char* kmcb200_last_error(const kmcb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint32_t kmcb200_out_rec_bytes(const kmcb200_ctx* ctx) { return ctx ? ctx->suffix_bytes + ctx->counter_bytes : 0; }
+uint64_t kmcb200_out_capacity(const kmcb200_ctx* ctx, uint64_t n_rec)
+{
+	if (!ctx) return 0;
+	return ((n_rec + 1) / std::max(ctx->prm.cutoff_min, 1u)) * (uint64_t)(ctx->suffix_bytes + ctx->counter_bytes);   // kb_reader.h:141-150
+}
+uint64_t kmcb200_lut_entries(const kmcb200_ctx* ctx) { return ctx ? ctx->lut_entries : 0; }
+uint64_t kmcb200_kernel_launches(const kmcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int kmcb200_host_alloc(kmcb200_ctx* ctx, uint64_t bytes, void** out_ptr)
+{
+	if (!ctx || !out_ptr) return KMCB200_ERR_INVALID;
+	if (int rc = set_device(ctx)) return rc;
+	CU(cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+	return 0;
+}
+int kmcb200_host_free(kmcb200_ctx* ctx, void* ptr)
+{
+	if (!ctx) return KMCB200_ERR_INVALID;
+	if (ptr) CU(cudaFreeHost(ptr));
+	return 0;
+}
+
+int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, uint64_t n_plus_x_recs,
+	const uint64_t* pack_bytes, const uint64_t* pack_recs, uint32_t n_packs,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut)
+{
+	(void)bin_id; (void)n_plus_x_recs; (void)pack_recs;
+	if (int rc = check_slot(ctx, slot)) return rc;
+	Slot& s = ctx->slots[slot];
+	if (s.busy) return fail(ctx, KMCB200_ERR_BUSY, "slot %u already holds a submitted bin", slot);
+	if ((size && !superkmers) || !lut || (!out_suffix && out_capacity)) return fail(ctx, KMCB200_ERR_INVALID, "null buffer");
+	if (int rc = set_device(ctx)) return rc;
+	cudaStream_t st = s.stream;
+	if (int rc = ensure(ctx, s.d_bin, s.bin_cap, size + 64)) return rc;
+	if (int rc = ensure(ctx, s.d_out, s.out_cap, out_capacity + 64)) return rc;
+	if (size) CU(cudaMemcpyAsync(s.d_bin, superkmers, size, cudaMemcpyHostToDevice, st));
+	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, st)) return rc;
+	CU(cudaMemcpyAsync(s.h_result, s.d_result, 64, cudaMemcpyDeviceToHost, st));
+	CU(cudaEventRecord(s.ev_result, st));
+	CU(cudaMemcpyAsync(lut, s.d_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, st));
+	s.busy = true;
+	s.host_out = out_suffix; s.host_out_cap = out_capacity; s.host_lut = lut; s.pending_n_rec = n_rec;
+	return 0;
+}
+
+int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint64_t stats[4])
+{
+	if (int rc = check_slot(ctx, slot)) return rc;
+	Slot& s = ctx->slots[slot];
+	if (!s.busy) return fail(ctx, KMCB200_ERR_INVALID, "slot %u has no submitted bin", slot);
+	if (int rc = set_device(ctx)) return rc;
+	s.busy = false;
+	CU(cudaEventSynchronize(s.ev_result));
+	const uint64_t* r = s.h_result;
+	if (r[6] & (kErrPackWalk | kErrRecCount)) {
+		cudaStreamSynchronize(s.stream);
+		return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error (bits %llu): %s", (unsigned long long)r[6],
+			(r[6] & kErrPackWalk) ? "an expander pack does not end on a record boundary" : "the bin does not hold n_rec k-mers");
+	}
+	const uint64_t bytes = r[4] * (uint64_t)(ctx->suffix_bytes + ctx->counter_bytes);
+	if (r[5] || bytes > s.host_out_cap) {
+		cudaStreamSynchronize(s.stream);
+		return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small for %llu bytes", (unsigned long long)s.host_out_cap, (unsigned long long)bytes);
+	}
+	if (bytes) CU(cudaMemcpyAsync(s.host_out, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+	CU(cudaStreamSynchronize(s.stream));
+	if (out_bytes) *out_bytes = bytes;
+	if (stats) for (int i = 0; i < 4; ++i) stats[i] = r[i];
+	return 0;
+}
+
+int kmcb200_process_bin(kmcb200_ctx* ctx, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, uint64_t n_plus_x_recs,
+	const uint64_t* pack_bytes, const uint64_t* pack_recs, uint32_t n_packs,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* out_bytes, uint64_t* lut, uint64_t stats[4])
+{
+	if (int rc = kmcb200_submit_bin(ctx, 0, bin_id, superkmers, size, n_rec, n_plus_x_recs, pack_bytes, pack_recs, n_packs, out_suffix, out_capacity, lut)) return rc;
+	return kmcb200_wait_bin(ctx, 0, out_bytes, stats);
+}
+
+int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, uint32_t rec_bytes, uint32_t key_bytes)
+{
+	if (int rc = check_slot(ctx, 0)) return rc;
+	if (rec_bytes != (uint32_t)ctx->words * 8) return fail(ctx, KMCB200_ERR_INVALID, "rec_bytes %u does not match the context (k=%u -> %d bytes)", rec_bytes, ctx->prm.kmer_len, ctx->words * 8);
+	if (key_bytes < 1 || key_bytes > rec_bytes || !recs || !tmp) return fail(ctx, KMCB200_ERR_INVALID, "bad key_bytes / buffers");
+	if (int rc = set_device(ctx)) return rc;
+	Slot& s = ctx->slots[0];
+	if (s.busy) return fail(ctx, KMCB200_ERR_BUSY, "slot 0 busy");
+	const int where = (key_bytes & 1) ? 1 : 0;      // kb_sorter.h:776-779
+	if (n == 0) return where;
+	cudaStream_t st = s.stream;
+	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, n * rec_bytes)) return rc;
+	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n * rec_bytes)) return rc;
+	CU(cudaMemcpyAsync(s.recs_a, recs, n * rec_bytes, cudaMemcpyHostToDevice, st));
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, false, st)) return rc;
+	CU(cudaMemcpyAsync(where ? tmp : recs, where ? s.recs_b : s.recs_a, n * rec_bytes, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return where;
+}
+
+// ---- device-level entry points
+int kmcb200_dev_process_bin(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkmers, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, void* stream)
+{
+	if (int rc = check_slot(ctx, slot)) return rc;
+	if (int rc = set_device(ctx)) return rc;
+	Slot& s = ctx->slots[slot];
+	return run_bin(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_out, out_capacity, d_lut, d_result, stream ? (cudaStream_t)stream : s.stream);
+}
+
+int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkmers, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, uint64_t* d_result, void* stream)
+{
+	if (int rc = check_slot(ctx, slot)) return rc;
+	if (int rc = set_device(ctx)) return rc;
+	Slot& s = ctx->slots[slot];
+	cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+	if (n_rec == 0) return 0;
+	CU(cudaEventRecord(s.ev_begin, st));
+	if (int rc = stage_expand(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_recs, st)) return rc;
+	if (d_result) {
+		CU(cudaMemsetAsync(d_result, 0, 64, st));
+		finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status);
+		ctx->launches++;
+	}
+	CU(cudaEventRecord(s.ev_expand, st));
+	s.ran_expand = true; s.ran_sort = s.ran_count = false;
+	return 0;
+}
+
+int kmcb200_dev_sort(kmcb200_ctx* ctx, uint32_t slot, void* d_recs, void* d_tmp, uint64_t n, uint32_t key_bytes, int hist_ready, void* stream)
+{
+	if (int rc = check_slot(ctx, slot)) return rc;
+	if (key_bytes < 1 || key_bytes > (uint32_t)ctx->words * 8) return fail(ctx, KMCB200_ERR_INVALID, "key_bytes %u", key_bytes);
+	if (int rc = set_device(ctx)) return rc;
+	Slot& s = ctx->slots[slot];
+	cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+	const int where = (key_bytes & 1) ? 1 : 0;
+	if (n == 0) return where;
+	if (!hist_ready) CU(cudaEventRecord(s.ev_expand, st));
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready != 0, st)) return rc;
+	CU(cudaEventRecord(s.ev_sort, st));
+	s.ran_sort = true; s.ran_count = false;
+	if (!hist_ready) s.ran_expand = false;
+	return where;
+}
+
+int kmcb200_dev_count(kmcb200_ctx* ctx, uint32_t slot, const void* d_sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
+	uint64_t* d_lut, uint64_t* d_result, void* stream)
+{
+	if (int rc = check_slot(ctx, slot)) return rc;
+	if (int rc = set_device(ctx)) return rc;
+	Slot& s = ctx->slots[slot];
+	cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+	CU(cudaEventRecord(s.ev_sort, st));
+	if (int rc = stage_count(ctx, s, d_sorted, n, d_out, out_capacity, d_lut, d_result, st)) return rc;
+	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n, nullptr);
+	ctx->launches++;
+	CU(cudaEventRecord(s.ev_count, st));
+	s.ran_count = true; s.ran_expand = false; s.ran_sort = false;
+	return 0;
+}
+
+int kmcb200_stage_times(kmcb200_ctx* ctx, uint32_t slot, float* ms, uint32_t capacity)
+{
+	if (int rc = check_slot(ctx, slot)) return rc;
+	if (!ms || capacity < 3) return fail(ctx, KMCB200_ERR_INVALID, "ms capacity");
+	if (int rc = set_device(ctx)) return rc;
+	Slot& s = ctx->slots[slot];
+	for (uint32_t i = 0; i < capacity; ++i) ms[i] = 0.f;
+	if (s.ran_count) CU(cudaEventSynchronize(s.ev_count));
+	else if (s.ran_sort) CU(cudaEventSynchronize(s.ev_sort));
+	else if (s.ran_expand) CU(cudaEventSynchronize(s.ev_expand));
+	if (s.ran_expand) CU(cudaEventElapsedTime(&ms[0], s.ev_begin, s.ev_expand));
+	if (s.ran_sort) {
+		CU(cudaEventElapsedTime(&ms[1], s.ev_expand, s.ev_sort));
+		for (int p = 0; p < s.n_passes_run && 3 + p < (int)capacity; ++p) CU(cudaEventElapsedTime(&ms[3 + p], s.ev_pass[p], s.ev_pass[p + 1]));
+	}
+	if (s.ran_count) CU(cudaEventElapsedTime(&ms[2], s.ev_sort, s.ev_count));
+	return s.ran_sort ? s.n_passes_run : 0;
+}
+
+// ---- synthetic bins (host only; mirrors the byte format of CKmerBinCollector::PutExtendedKmer, kb_collector.cpp:34-90)
+static inline uint64_t splitmix64(uint64_t& x)
+{
+	uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+int kmcb200_synth_bin(uint64_t seed, uint32_t k, uint64_t n_rec, uint64_t genome_len, double mean_extra, uint32_t err_ppm,
+	uint8_t* data, uint64_t data_capacity, uint64_t* size, uint64_t* pack_bytes, uint32_t pack_capacity, uint32_t* n_packs, uint64_t* n_super_kmers)
+{
+	if (k < 1 || k > 256 || !size || !n_packs) return KMCB200_ERR_INVALID;
+	if (genome_len < (uint64_t)k + 256) genome_len = (uint64_t)k + 256;
+	uint64_t rs = seed * 0x2545F4914F6CDD1Dull + 0x1234567;
+	std::vector<uint8_t> genome(genome_len);
+	for (uint64_t i = 0; i < genome_len; i += 32) {
+		uint64_t r = splitmix64(rs);
+		for (uint64_t j = i; j < std::min(genome_len, i + 32); ++j) { genome[j] = r & 3; r >>= 2; }
+	}
+	const double pgeo = 1.0 / (mean_extra + 1.0);
+	const double log1mp = std::log(1.0 - std::min(pgeo, 0.999999));
+	const uint64_t err_thr = (uint64_t)((double)err_ppm * 1e-6 * 18446744073709551615.0);
+	uint64_t pos_out = 0, made = 0, n_sk = 0;
+	uint32_t np = 0;
+	uint64_t pack_fill = 0;
+	uint8_t symbuf[256 + 256 + 8];
+	while (made < n_rec) {
+		double u = (double)(splitmix64(rs) >> 11) * (1.0 / 9007199254740992.0);
+		uint64_t a = pgeo >= 0.999999 ? 0 : (uint64_t)(std::log(1.0 - u) / log1mp);
+		if (a > 255) a = 255;
+		if (a + 1 > n_rec - made) a = n_rec - made - 1;
+		const uint32_t n = k + (uint32_t)a;
+		const uint64_t p = splitmix64(rs) % (genome_len - n + 1);
+		const bool rc = splitmix64(rs) & 1;
+		for (uint32_t i = 0; i < n; ++i) {
+			uint8_t s = rc ? (uint8_t)(3 - genome[p + n - 1 - i]) : genome[p + i];
+			if (err_thr && splitmix64(rs) < err_thr) s = (uint8_t)((s + 1 + splitmix64(rs) % 3) & 3);
+			symbuf[i] = s;
+		}
+		const uint32_t bytes = 1 + (n + 3) / 4;
+		if (pack_fill + bytes > (1u << 16)) {               // collector flush (kb_collector.cpp:44-55)
+			if (pack_bytes && np < pack_capacity) pack_bytes[np] = pack_fill;
+			++np;
+			pack_fill = 0;
+		}
+		if (data) {
+			if (pos_out + bytes > data_capacity) return KMCB200_ERR_CAPACITY;
+			data[pos_out] = (uint8_t)a;
+			for (uint32_t i = 0; i < (n + 3) / 4; ++i) {
+				uint8_t b = 0;
+				for (uint32_t j = 0; j < 4; ++j) { const uint32_t q = 4 * i + j; b = (uint8_t)((b << 2) | (q < n ? symbuf[q] : 0)); }
+				data[pos_out + 1 + i] = b;
+			}
+		}
+		pos_out += bytes; pack_fill += bytes; made += a + 1; ++n_sk;
+	}
+	if (pack_fill) { if (pack_bytes && np < pack_capacity) pack_bytes[np] = pack_fill; ++np; }
+	*size = pos_out; *n_packs = np;
+	if (n_super_kmers) *n_super_kmers = n_sk;
+	if (pack_bytes && np > pack_capacity) return KMCB200_ERR_CAPACITY;
+	return 0;
+}
+
+}  // extern "C"

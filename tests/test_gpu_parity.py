@@ -1,0 +1,211 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle (bit-exact)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from kmc_testlib import Params, Bin, synth_bin, pack_superkmers, choose_lut_prefix_len, bin_from_reads
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(p: Params, n_slots=1):
+    import kmc_b200
+    return kmc_b200.Stage2Context(kmc_b200.Stage2Params(p.k, p.both_strands, p.cutoff_min, p.cutoff_max, p.counter_max, p.lut_prefix_len), device=0, n_slots=n_slots)
+
+
+def _to_skb(b: Bin):
+    import kmc_b200
+    return kmc_b200.SuperKmerBin(data=b.data, n_rec=b.n_rec, pack_bytes=b.pack_bytes, n_super_kmers=b.n_super_kmers, kmer_len=b.k)
+
+
+def _check_bin(oracle, b: Bin, p: Params, ctx=None):
+    own = ctx is None
+    ctx = ctx or _ctx(p)
+    r = ctx.process_bin(_to_skb(b))
+    e = oracle.process_bin(b, p)
+    assert r.stats == e.stats
+    assert np.array_equal(r.lut, e.lut)
+    assert r.payload.tobytes() == e.payload
+    if own:
+        ctx.close()
+
+
+@pytest.mark.parametrize("k,both,cmin", [(31, True, 2), (31, False, 1), (28, True, 1), (17, True, 1), (32, True, 2), (15, True, 1), (5, True, 1)])
+def test_bin_parity_one_word(oracle, k, both, cmin):
+    p = Params(k=k, both_strands=both, cutoff_min=cmin, lut_prefix_len=choose_lut_prefix_len(k))
+    _check_bin(oracle, synth_bin(7, k, 20000, genome_len=30000, err=0.02), p)
+
+
+@pytest.mark.parametrize("k,both,cmin", [(55, True, 2), (55, False, 1), (33, True, 1), (64, True, 2), (70, True, 1), (96, True, 2), (127, False, 1), (128, True, 1)])
+def test_bin_parity_multi_word(oracle, k, both, cmin):
+    p = Params(k=k, both_strands=both, cutoff_min=cmin, lut_prefix_len=choose_lut_prefix_len(k))
+    _check_bin(oracle, synth_bin(11, k, 8000, genome_len=12000, err=0.02), p)
+
+
+def test_expand_matches_oracle(oracle):
+    import torch
+    for k, both in [(31, True), (31, False), (55, True), (100, True), (9, True)]:
+        p = Params(k=k, both_strands=both, lut_prefix_len=choose_lut_prefix_len(k))
+        b = synth_bin(3, k, 5000, genome_len=4000, pad_garbage=True)
+        ctx = _ctx(p)
+        d_bin = torch.zeros(b.size + 64, dtype=torch.uint8, device="cuda")
+        d_bin[:b.size] = torch.from_numpy(b.data).cuda()
+        d_recs = torch.zeros((b.n_rec + 8) * p.words, dtype=torch.int64, device="cuda")
+        d_res = torch.zeros(8, dtype=torch.int64, device="cuda")
+        ctx.dev_expand(0, d_bin.data_ptr(), b.size, b.n_rec, b.pack_bytes, d_recs.data_ptr(), d_res.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = d_recs.cpu().numpy().view(np.uint64)[:b.n_rec * p.words].reshape(b.n_rec, p.words)
+        exp = oracle.expand(b, p)
+        assert int(d_res[6]) == 0
+        assert np.array_equal(got, exp), "k=%d both=%s" % (k, both)
+        ctx.close()
+
+
+@pytest.mark.parametrize("words,key_bytes,n", [(1, 8, 100000), (1, 8, 4096), (1, 8, 4097), (1, 5, 33333), (1, 1, 1000), (2, 14, 50001), (2, 16, 2048), (3, 20, 30000), (4, 32, 20000), (1, 8, 1), (1, 8, 3)])
+def test_sort_records_matches_oracle(oracle, words, key_bytes, n):
+    rng = np.random.default_rng(n + words)
+    recs = rng.integers(0, 1 << 63, size=(n, words), dtype=np.uint64)
+    # duplicate-rich + masked to the key bytes (bytes above key_bytes are zero in KMC records)
+    recs[n // 2:] = recs[rng.integers(0, max(n // 2, 1), n - n // 2)]
+    full = np.zeros((n, words * 8), dtype=np.uint8)
+    full[:, :key_bytes] = recs.view(np.uint8).reshape(n, words * 8)[:, :key_bytes]
+    recs = full.view(np.uint64).reshape(n, words)
+    k = {1: 31, 2: 55, 3: 90, 4: 128}[words]
+    p = Params(k=k, lut_prefix_len=choose_lut_prefix_len(k))
+    ctx = _ctx(p)
+    got = ctx.sort_records(recs, key_bytes)
+    exp = oracle.sort(recs, key_bytes)
+    assert np.array_equal(got, exp)
+    ctx.close()
+
+
+def test_count_matches_oracle_runs_across_tiles(oracle):
+    """Runs longer than a tile (giant runs need the backward probe + binary search), cutoffs and clamping."""
+    import torch
+    rng = np.random.default_rng(5)
+    for cmin, cmax, cntmax in [(1, 10 ** 9, 255), (2, 10 ** 9, 255), (3, 50, 7), (1, 20000, 65535), (2, 10 ** 9, 1)]:
+        p = Params(k=31, cutoff_min=cmin, cutoff_max=cmax, counter_max=cntmax, lut_prefix_len=7)
+        keys = np.sort(rng.integers(0, 1 << 62, 3000, dtype=np.uint64))
+        reps = rng.integers(1, 6, keys.size)
+        reps[100] = 9000
+        reps[101] = 4096
+        reps[2000] = 70000
+        reps[2999] = 5000
+        recs = np.repeat(keys, reps).reshape(-1, 1)
+        n = recs.shape[0]
+        exp = oracle.compact(recs, p)
+        ctx = _ctx(p)
+        d = torch.from_numpy(recs.view(np.int64)).cuda()
+        cap = ctx.out_capacity(n) + 64
+        d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_lut = torch.zeros(ctx.lut_entries, dtype=torch.int64, device="cuda")
+        d_res = torch.zeros(8, dtype=torch.int64, device="cuda")
+        ctx.dev_count(0, d.data_ptr(), n, d_out.data_ptr(), cap, d_lut.data_ptr(), d_res.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        res = d_res.cpu().numpy()
+        assert tuple(int(x) for x in res[:4]) == exp.stats
+        nb = int(res[4]) * ctx.out_rec_bytes
+        assert d_out[:nb].cpu().numpy().tobytes() == exp.payload
+        assert np.array_equal(d_lut.cpu().numpy().view(np.uint64), exp.lut)
+        ctx.close()
+
+
+def test_edge_bins(oracle):
+    p = Params(k=31, cutoff_min=1, lut_prefix_len=7)
+    ctx = _ctx(p)
+    rng = np.random.default_rng(0)
+    # empty bin (kb_reader.h:198-205)
+    _check_bin(oracle, synth_bin(1, 31, 0), p, ctx)
+    # a single k-mer; maximum-length super-k-mers (k+255 symbols); poly-A (one giant run, palindromic ties AT)
+    _check_bin(oracle, pack_superkmers(31, [rng.integers(0, 4, 31)]), p, ctx)
+    _check_bin(oracle, pack_superkmers(31, [rng.integers(0, 4, 31 + 255) for _ in range(300)]), p, ctx)
+    _check_bin(oracle, pack_superkmers(31, [np.zeros(31 + 255, dtype=np.uint8) for _ in range(200)]), p, ctx)
+    _check_bin(oracle, pack_superkmers(31, [np.tile(np.array([0, 3], dtype=np.uint8), 100)[:31 + 150] for _ in range(50)]), p, ctx)
+    # ragged: many a=0 records
+    _check_bin(oracle, pack_superkmers(31, [rng.integers(0, 4, 31) for _ in range(5000)]), p, ctx)
+    ctx.close()
+
+
+def test_reference_kats_through_gpu(oracle):
+    """The reference's own CLI known-answers (tests/golden/kats.json, made from .github/workflows/main.yml:35-52)."""
+    import json, os
+    from kmc_testlib import decode_payload
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kats.json")))
+    for kat in kats:
+        p = Params(k=kat["k"], cutoff_min=kat["cutoff_min"], lut_prefix_len=kat["lut_prefix_len"])
+        b = bin_from_reads(kat["k"], kat["reads"])
+        ctx = _ctx(p)
+        r = ctx.process_bin(_to_skb(b))
+        assert r.n_total == kat["n_total"]
+        if "dump" in kat:
+            assert decode_payload(r.payload.tobytes(), r.lut, p) == [tuple(x) for x in kat["dump"]]
+        ctx.close()
+
+
+def test_pipelined_slots_and_reuse(oracle):
+    """Several bins of different sizes through 2 slots (submit/wait), buffers reused and regrown."""
+    import kmc_b200
+    p = Params(k=31, cutoff_min=2, lut_prefix_len=7)
+    ctx = _ctx(p, n_slots=2)
+    bins = [synth_bin(100 + i, 31, n, genome_len=max(2000, n), err=0.01) for i, n in enumerate([3000, 50, 12000, 0, 7000, 1])]
+    outs = [np.zeros(ctx.out_capacity(b.n_rec) + 64, dtype=np.uint8) for b in bins]
+    luts = [np.zeros(ctx.lut_entries, dtype=np.uint64) for _ in bins]
+    res = [None] * len(bins)
+    for i, b in enumerate(bins):
+        slot = i % 2
+        if i >= 2:
+            res[i - 2] = ctx.wait_bin(slot)
+        d = np.ascontiguousarray(b.data)
+        ctx.submit_bin(slot, d.ctypes.data, d.size, b.n_rec, np.ascontiguousarray(b.pack_bytes), outs[i].ctypes.data, outs[i].size, luts[i].ctypes.data)
+        bins[i].data = d
+    for i in range(len(bins) - 2, len(bins)):
+        res[i] = ctx.wait_bin(i % 2)
+    for i, b in enumerate(bins):
+        e = oracle.process_bin(b, p)
+        nb, stats = res[i]
+        assert stats == e.stats and outs[i][:nb].tobytes() == e.payload and np.array_equal(luts[i], e.lut)
+    ctx.close()
+
+
+def test_bad_packs_are_reported():
+    import kmc_b200
+    p = Params(k=31, lut_prefix_len=7)
+    b = synth_bin(1, 31, 500)
+    ctx = _ctx(p)
+    skb = _to_skb(b)
+    bad = skb.pack_bytes.copy()
+    if bad.size == 1:
+        bad = np.array([bad[0] - 3, 3], dtype=np.uint64)      # second pack starts in the middle of a record
+    skb.pack_bytes = bad
+    with pytest.raises(kmc_b200.KmcB200Error) as ei:
+        ctx.process_bin(skb)
+    assert ei.value.code == kmc_b200.ERR_BIN_FORMAT
+    ctx.close()
+
+
+def test_large_bin_properties_and_parity(oracle):
+    """2^22 k-mers (oracle finishes in seconds) bit-exact; then 2^26 (BASELINE config 2) through size-independent
+    properties: n_total, sum of LUT == emitted records, emitted records strictly increasing, counters within cutoffs."""
+    import kmc_b200
+    p = Params(k=31, cutoff_min=2, lut_prefix_len=7)
+    ctx = _ctx(p)
+    sk = kmc_b200.synth_bin(12345, 31, 1 << 22)
+    b = Bin(data=sk.data, n_rec=sk.n_rec, n_super_kmers=sk.n_super_kmers, pack_bytes=sk.pack_bytes, pack_recs=sk.pack_bytes, k=31)
+    _check_bin(oracle, b, p, ctx)
+    sk = kmc_b200.synth_bin(999, 31, 1 << 26)
+    r = ctx.process_bin(sk)
+    assert r.n_total == 1 << 26
+    n_emit = r.payload.size // ctx.out_rec_bytes
+    assert int(r.lut.sum()) == n_emit == r.n_unique - r.n_cutoff_min - r.n_cutoff_max
+    rec = r.payload.reshape(n_emit, ctx.out_rec_bytes)
+    cnt = rec[:, -1]
+    assert cnt.min() >= 2
+    # full k-mer = (prefix from the LUT, suffix bytes): strictly increasing
+    prefix = np.repeat(np.arange(ctx.lut_entries, dtype=np.uint64), r.lut.astype(np.int64))
+    suf = np.zeros(n_emit, dtype=np.uint64)
+    for j in range(6):
+        suf = (suf << np.uint64(8)) | rec[:, j].astype(np.uint64)
+    full = (prefix << np.uint64(48)) | suf
+    assert np.all(full[1:] > full[:-1])
+    ctx.close()
