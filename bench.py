@@ -214,7 +214,10 @@ def main_ours(args, rank, world, local_rank):
     d_out = torch.zeros(cap, dtype=torch.uint8, device=dev)
     d_lut = torch.zeros(ctx.lut_entries, dtype=torch.int64, device=dev)
     d_res = torch.zeros(8, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: the library enqueues on it, torch events time it
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_dev(i):
         hb = host_bins[i % 2]
