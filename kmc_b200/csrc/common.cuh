@@ -153,4 +153,24 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint64_t 
 	return excl;
 }
 
+
+// Second half of the chained scan when the aggregate has already been published (radix passes publish it early):
+// returns the exclusive prefix over all earlier tiles and upgrades this tile's descriptor to an inclusive prefix.
+__device__ __forceinline__ uint64_t lookback_resolve(uint64_t* desc, uint64_t stride, uint32_t tile, uint64_t aggregate, uint32_t epoch)
+{
+	uint64_t excl = 0;
+	for (int64_t t = (int64_t)tile - 1;; --t) {
+		uint64_t v;
+		uint32_t st;
+		do {
+			v = ld_relaxed(desc + (uint64_t)t * stride);
+			st = desc_state(v, epoch);
+		} while (st == 0);
+		excl += v & kDescValueMask;
+		if (st == kDescPrefix) break;
+	}
+	st_relaxed(desc + (uint64_t)tile * stride, desc_pack(kDescPrefix, epoch, excl + aggregate));
+	return excl;
+}
+
 }  // namespace kmcb

@@ -36,21 +36,27 @@ struct CountArgs {
 	uint32_t* tile_counter;  // zero-initialised
 };
 
-template <int WORDS> struct CountCfg { static constexpr int kThreads = 512, kIpt = (WORDS == 1 ? 8 : WORDS == 2 ? 4 : 2); };
+template <int WORDS> struct CountCfg { static constexpr int kThreads = 256, kIpt = (WORDS == 1 ? 8 : WORDS == 2 ? 4 : 2); };
 
-constexpr int kLutWindow = 1024;
+constexpr int kLutWindow = 512;
 
 template <int WORDS>
 __host__ __device__ constexpr int count_tile() { return CountCfg<WORDS>::kThreads * CountCfg<WORDS>::kIpt; }
 
-// dynamic shared memory: max(record tile + 1 lookahead, staging of emitted bytes + 32)
+// dynamic shared memory layout: [records + 1 lookahead | staging of the emitted bytes | tail positions | emitted positions | emitted values]
 template <int WORDS>
-inline size_t count_smem_bytes(uint32_t out_rec_bytes)
-{
-	const size_t a = (size_t)(count_tile<WORDS>() + 1) * 8 * WORDS;
-	const size_t b = (size_t)count_tile<WORDS>() * out_rec_bytes + 32;
-	return (a > b ? a : b) + 16;
-}
+struct CountSmem {
+	static constexpr int kTile = CountCfg<WORDS>::kThreads * CountCfg<WORDS>::kIpt;
+	static constexpr size_t oRec = 0;
+	static constexpr size_t oStage = ((size_t)(kTile + 1) * 8 * WORDS + 15) & ~(size_t)15;
+	__host__ __device__ static size_t stage_bytes(uint32_t ob) { return ((size_t)kTile * ob + 32 + 15) & ~(size_t)15; }
+	__host__ __device__ static size_t oTails(uint32_t ob) { return oStage + stage_bytes(ob); }
+	__host__ __device__ static size_t oEmPos(uint32_t ob) { return oTails(ob) + (size_t)kTile * 2; }
+	__host__ __device__ static size_t oEmVal(uint32_t ob) { return oEmPos(ob) + (size_t)kTile * 2; }
+	__host__ __device__ static size_t bytes(uint32_t ob) { return oEmVal(ob) + (size_t)kTile * 4; }
+};
+template <int WORDS>
+inline size_t count_smem_bytes(uint32_t out_rec_bytes) { return CountSmem<WORDS>::bytes(out_rec_bytes); }
 
 // the p leading symbols of a k-mer (kmer.h:294-303 remove_suffix(2*(k-p)))
 template <int WORDS>
@@ -68,25 +74,33 @@ __device__ __forceinline__ uint32_t rec_prefix(const Rec<WORDS>& r, uint32_t nbi
 	return (uint32_t)((hi << (64u - s)) | (lo >> s));
 }
 
+// Sparse events (run tails, emitted records) are first compacted into dense lists, then handled one per thread:
+// with 30x coverage only ~3 % of the records end a run, and a warp that carried the whole emit path for one
+// active lane per round would spend ~30x the instructions.
 template <int WORDS>
 __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(const CountArgs a)
 {
 	using R = Rec<WORDS>;
+	using SM = CountSmem<WORDS>;
 	constexpr int THREADS = CountCfg<WORDS>::kThreads, IPT = CountCfg<WORDS>::kIpt, TILE = THREADS * IPT;
 	constexpr int WARPS = THREADS / 32, NW = TILE / 32;
+	static_assert(NW <= THREADS, "one thread per bitmap word");
 	extern __shared__ __align__(16) uint8_t dsm[];
-	R* srec = reinterpret_cast<R*>(dsm);
-	__shared__ uint32_t tailmask[NW], emitmask[NW], wordpre[NW];
+	const uint32_t ob = a.suffix_bytes + a.counter_bytes;
+	R* srec = reinterpret_cast<R*>(dsm + SM::oRec);
+	uint8_t* stage0 = dsm + SM::oStage;
+	uint16_t* tails_pos = reinterpret_cast<uint16_t*>(dsm + SM::oTails(ob));
+	uint16_t* em_pos = reinterpret_cast<uint16_t*>(dsm + SM::oEmPos(ob));
+	uint32_t* em_val = reinterpret_cast<uint32_t*>(dsm + SM::oEmVal(ob));
+	__shared__ uint32_t tailmask[NW], wordpre[NW];
 	__shared__ uint32_t lutwin[kLutWindow];
-	__shared__ uint32_t s_tile, s_warp[WARPS], s_emit_total;
+	__shared__ uint32_t s_tile, s_warp[WARPS], s_total;
 	__shared__ uint64_t s_run_head0, s_base;
-	__shared__ unsigned long long s_stats[3];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const R* __restrict__ g = reinterpret_cast<const R*>(a.recs);
 
 	if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
-	if (tid < 3) s_stats[tid] = 0;
 	for (int i = tid; i < kLutWindow; i += THREADS) lutwin[i] = 0;
 	__syncthreads();
 	const uint32_t tile = s_tile;
@@ -94,19 +108,25 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 	const uint64_t rem = a.n - first;
 	const uint32_t cnt = rem < (uint64_t)TILE ? (uint32_t)rem : (uint32_t)TILE;
 
+	// ---- load the tile (+ the records just before it for the run-head probe, + one lookahead record)
 	R rec[IPT];
 #pragma unroll
 	for (int r = 0; r < IPT; ++r) {
 		const uint32_t i = r * THREADS + tid;
-		if (i < cnt) {
-			rec[r] = g[first + i];
-			srec[i] = rec[r];
-		}
+		if (i < cnt) rec[r] = g[first + i];
+	}
+	R probe;
+	const bool probe_valid = warp == 0 && first >= (uint64_t)lane + 1;
+	if (probe_valid) probe = g[first - 1 - lane];
+#pragma unroll
+	for (int r = 0; r < IPT; ++r) {
+		const uint32_t i = r * THREADS + tid;
+		if (i < cnt) srec[i] = rec[r];
 	}
 	if (tid == 0 && first + cnt < a.n) srec[cnt] = g[first + cnt];
 	__syncthreads();
 
-	// ---- head of the run that contains the first record of the tile (warp 0)
+	// ---- head of the run that contains the first record of the tile (warp 0): backward probe, then lower_bound for giant runs
 	if (warp == 0) {
 		uint64_t h = first;
 		if (first != 0) {
@@ -114,9 +134,9 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 			uint64_t pos = first;
 			bool found = false;
 			for (int c = 0; c < 4 && !found; ++c) {
-				const bool valid = pos >= (uint64_t)lane + 1;
 				bool neq = true;
-				if (valid) neq = !rec_equal<WORDS>(g[pos - 1 - lane], key0);
+				if (c == 0) { if (probe_valid) neq = !rec_equal<WORDS>(probe, key0); }
+				else if (pos >= (uint64_t)lane + 1) neq = !rec_equal<WORDS>(g[pos - 1 - lane], key0);
 				const uint32_t m = __ballot_sync(0xffffffffu, neq);
 				if (m) {
 					h = pos - (uint32_t)(__ffs(m) - 1);
@@ -124,7 +144,7 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 				} else
 					pos -= 32;
 			}
-			if (!found) {   // giant run: lower_bound of key0 in g[0, pos)
+			if (!found) {
 				uint64_t lo = 0, hi = pos;
 				while (lo < hi) {
 					const uint64_t mid = (lo + hi) >> 1;
@@ -137,7 +157,7 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 		if (lane == 0) s_run_head0 = h;
 	}
 
-	// ---- run tails
+	// ---- run tails: one neighbour compare per record, a bitmap word per warp round
 	uint32_t tailbits = 0;
 #pragma unroll
 	for (int r = 0; r < IPT; ++r) {
@@ -150,53 +170,9 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 	}
 	__syncthreads();
 
-	// ---- run lengths, cutoffs
-	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
-	const uint32_t pfx0 = rec_prefix<WORDS>(srec[0], prefix_shift);
-	uint32_t emitbits = 0;
-	uint32_t value[IPT];
-	uint32_t n_unique = 0, n_min = 0, n_max = 0;
-#pragma unroll
-	for (int r = 0; r < IPT; ++r) {
-		const uint32_t i = r * THREADS + tid;
-		bool emit = false;
-		value[r] = 0;
-		if ((tailbits >> r) & 1u) {
-			// previous tail inside the tile
-			int wi = (int)(i >> 5);
-			uint32_t m = tailmask[wi] & ((1u << (i & 31u)) - 1u);
-			while (m == 0 && wi > 0) m = tailmask[--wi];
-			const uint64_t head = m ? first + (uint64_t)wi * 32 + (31 - __clz(m)) + 1 : s_run_head0;
-			const uint32_t count = (uint32_t)(first + i - head + 1);       // uint32 like kb_sorter.h:1153
-			++n_unique;
-			if (count < a.cutoff_min) ++n_min;
-			else if (count > a.cutoff_max) ++n_max;
-			else {
-				emit = true;
-				value[r] = count > a.counter_max ? a.counter_max : count;
-			}
-		}
-		const uint32_t w = __ballot_sync(0xffffffffu, emit);
-		if (lane == 0) emitmask[r * WARPS + warp] = w;
-		emitbits |= (uint32_t)emit << r;
-	}
-	// block-reduce the three counters
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		n_unique += __shfl_down_sync(0xffffffffu, n_unique, o);
-		n_min += __shfl_down_sync(0xffffffffu, n_min, o);
-		n_max += __shfl_down_sync(0xffffffffu, n_max, o);
-	}
-	if (lane == 0) {
-		atomicAdd(&s_stats[0], (unsigned long long)n_unique);
-		atomicAdd(&s_stats[1], (unsigned long long)n_min);
-		atomicAdd(&s_stats[2], (unsigned long long)n_max);
-	}
-	__syncthreads();
-
-	// ---- ranks of the emitted records: exclusive scan over the popcounts of the NW bitmap words
+	// ---- exclusive scan of the bitmap popcounts -> dense list of tail positions
 	{
-		uint32_t c = tid < NW ? __popc(emitmask[tid]) : 0;
+		const uint32_t c = tid < NW ? __popc(tailmask[tid]) : 0;
 		uint32_t inc = c;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -208,41 +184,93 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 		uint32_t base = 0;
 		for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
 		if (tid < NW) wordpre[tid] = base + inc - c;
-		if (tid == NW - 1) s_emit_total = base + inc;
+		if (tid == NW - 1) s_total = base + inc;
 	}
 	__syncthreads();
-	const uint32_t emit_total = s_emit_total;
+	const uint32_t n_tails = s_total;
+#pragma unroll
+	for (int r = 0; r < IPT; ++r) {
+		if ((tailbits >> r) & 1u) {
+			const uint32_t i = r * THREADS + tid;
+			const uint32_t wi = r * WARPS + warp;
+			tails_pos[wordpre[wi] + __popc(tailmask[wi] & lanemask_lt())] = (uint16_t)i;
+		}
+	}
+	__syncthreads();
+
+	// ---- one thread per run: length, cutoffs (kb_sorter.h:1174-1191), dense list of the emitted ones
+	uint32_t n_min = 0, n_max = 0, n_emit = 0;
+	for (uint32_t j0 = 0; j0 < n_tails; j0 += THREADS) {
+		const uint32_t j = j0 + tid;
+		bool emit = false;
+		uint32_t value = 0, pos = 0;
+		bool is_min = false, is_max = false;
+		if (j < n_tails) {
+			pos = tails_pos[j];
+			const uint64_t head = j ? first + tails_pos[j - 1] + 1 : s_run_head0;
+			const uint32_t count = (uint32_t)(first + pos - head + 1);       // uint32 like kb_sorter.h:1153
+			if (count < a.cutoff_min) is_min = true;
+			else if (count > a.cutoff_max) is_max = true;
+			else {
+				emit = true;
+				value = count > a.counter_max ? a.counter_max : count;
+			}
+		}
+		const uint32_t be = __ballot_sync(0xffffffffu, emit);
+		n_min += __popc(__ballot_sync(0xffffffffu, is_min));
+		n_max += __popc(__ballot_sync(0xffffffffu, is_max));
+		if (lane == 0) s_warp[warp] = __popc(be);
+		__syncthreads();
+		uint32_t base = n_emit, tot = 0;
+#pragma unroll
+		for (int w = 0; w < WARPS; ++w) {
+			const uint32_t c = s_warp[w];
+			if ((uint32_t)w < warp) base += c;
+			tot += c;
+		}
+		if (emit) {
+			const uint32_t e = base + __popc(be & lanemask_lt());
+			em_pos[e] = (uint16_t)pos;
+			em_val[e] = value;
+		}
+		n_emit += tot;
+		__syncthreads();
+	}
+	const uint32_t emit_total = n_emit;
 	if (tid == 0) {
 		const uint64_t base = lookback_exclusive(a.desc, 1, tile, (uint64_t)emit_total, a.epoch);
 		s_base = base;
 		if (tile == a.n_tiles - 1) a.result[4] = base + emit_total;
 	}
-	// srec is dead from here on (every thread holds its records in registers): reuse it as the staging area
+	if (lane == 0 && (n_min | n_max)) {      // every warp saw the same ballots only for its own lanes: per-warp partial sums
+		if (n_min) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 1, (unsigned long long)n_min);
+		if (n_max) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 2, (unsigned long long)n_max);
+	}
+	if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.result), (unsigned long long)n_tails);      // n_unique
 	__syncthreads();
 
-	const uint32_t ob = a.suffix_bytes + a.counter_bytes;
+	// ---- one thread per emitted record: (k-p)/4 suffix bytes, most significant first, then the counter, least significant first
 	const uint64_t base = s_base;
 	uint8_t* dst = a.out + base * ob;
 	const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);     // staging keeps the destination's 16-byte phase
-	uint8_t* stage = dsm + mis;
+	uint8_t* stage = stage0 + mis;
 	const bool fits = (base + emit_total) * (uint64_t)ob <= a.out_capacity;
-
-#pragma unroll
-	for (int r = 0; r < IPT; ++r) {
-		const uint32_t i = r * THREADS + tid;
-		const bool emit = (emitbits >> r) & 1u;
+	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
+	const uint32_t pfx0 = rec_prefix<WORDS>(srec[0], prefix_shift);
+	for (uint32_t e0 = 0; e0 < emit_total; e0 += THREADS) {
+		const uint32_t e = e0 + tid;
 		uint32_t pfx = 0xffffffffu;
-		if (emit) {
-			const uint32_t wi = i >> 5;
-			const uint32_t rnk = wordpre[wi] + __popc(emitmask[wi] & ((1u << (i & 31u)) - 1u));
-			uint8_t* o = stage + (size_t)rnk * ob;
-			for (uint32_t j = 0; j < a.suffix_bytes; ++j) o[j] = (uint8_t)rec_byte<WORDS>(rec[r], a.suffix_bytes - 1 - j);
-			for (uint32_t j = 0; j < a.counter_bytes; ++j) o[a.suffix_bytes + j] = (uint8_t)(value[r] >> (8 * j));
-			pfx = rec_prefix<WORDS>(rec[r], prefix_shift);
+		if (e < emit_total) {
+			const R rr = srec[em_pos[e]];
+			const uint32_t value = em_val[e];
+			uint8_t* o = stage + (size_t)e * ob;
+			for (uint32_t j = 0; j < a.suffix_bytes; ++j) o[j] = (uint8_t)rec_byte<WORDS>(rr, a.suffix_bytes - 1 - j);
+			for (uint32_t j = 0; j < a.counter_bytes; ++j) o[a.suffix_bytes + j] = (uint8_t)(value >> (8 * j));
+			pfx = rec_prefix<WORDS>(rr, prefix_shift);
 		}
-		// lut[prefix]++ aggregated per warp
+		// lut[prefix]++ (kb_sorter.h:1203) aggregated per warp, then per tile in a shared window
 		const uint32_t peers = __match_any_sync(0xffffffffu, pfx);
-		if (emit && (int)lane == __ffs(peers) - 1) {
+		if (e < emit_total && (int)lane == __ffs(peers) - 1) {
 			const uint32_t c = __popc(peers);
 			const uint32_t d = pfx - pfx0;
 			if (d < (uint32_t)kLutWindow) atomicAdd(&lutwin[d], c);
@@ -269,7 +297,6 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 		const uint32_t c = lutwin[i];
 		if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + pfx0 + i, (unsigned long long)c);
 	}
-	if (tid < 3 && s_stats[tid]) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + tid, s_stats[tid]);
 }
 
 }  // namespace kmcb

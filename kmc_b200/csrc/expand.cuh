@@ -8,7 +8,7 @@
 //
 // The stream is self-delimiting, so record starts need a walk.  Packs (one per <=64 KiB collector flush,
 // CExpanderPackDesc, queues.h:376-396) start on record boundaries and give the parallelism:
-//   1. walk_packs_kernel  : one thread per pack walks its records and writes, per super-k-mer, its byte offset
+//   1. walk_packs_kernel  : one warp per pack walks its records and writes, per super-k-mer, its byte offset
 //                           and the number of k-mers before it in the pack (both in a gap-free-per-pack region
 //                           addressed by pack_start / min_rec_bytes, so no allocation scan is needed);
 //   2. scan_packs_kernel  : exclusive scans over packs (k-mer base, output-tile base) + tile->pack map;
@@ -54,30 +54,72 @@ enum : uint32_t { kErrPackWalk = 1, kErrRecCount = 2 };
 
 __device__ __forceinline__ uint64_t tile_first_base(uint64_t pack_start, uint32_t p) { return pack_start * 4 / kExpandTile + p; }
 
-__global__ void __launch_bounds__(128) walk_packs_kernel(const ExpandArgs a)
+// One WARP per pack.  The walk itself is a serial chain (the length byte of a record tells where the next one
+// starts), so the only thing that matters is the latency of one step.  The warp keeps a 512-byte window of the stream
+// in registers (one uint4 per lane, the next window already in flight), a step is one shuffle + a few integer ops
+// (~40 cycles) and never waits for DRAM; the per-super-k-mer index leaves with coalesced 128-byte stores.
+constexpr int kWalkWarpsPerBlock = 4;
+
+__device__ __forceinline__ uint4 walk_load_window(const uint8_t* bin_aligned, uint64_t wbase, uint64_t limit, uint32_t lane)
 {
-	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t o = wbase + 16ull * lane;
+	return o < limit ? __ldg(reinterpret_cast<const uint4*>(bin_aligned + o)) : make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(32 * kWalkWarpsPerBlock) walk_packs_kernel(const ExpandArgs a)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t p = blockIdx.x * kWalkWarpsPerBlock + (threadIdx.x >> 5);
 	if (p >= a.n_packs) return;
 	uint64_t pos = a.pack_start[p];
 	const uint64_t end = a.pack_start[p + 1];
 	const uint64_t slot = pos / a.min_rec_bytes;
 	const uint64_t tfb = tile_first_base(pos, p);
+	// 16-byte aligned view of the stream (the bin pointer is at least 8-byte aligned; the window grid is aligned on absolute addresses)
+	const uintptr_t base_addr = reinterpret_cast<uintptr_t>(a.bin);
+	const uint8_t* bin_aligned = reinterpret_cast<const uint8_t*>(base_addr & ~(uintptr_t)15);
+	const uint64_t shift = base_addr & 15u;                 // stream offset x lives at aligned offset x + shift
+	const uint64_t limit = ((a.size + shift + 15) & ~15ull);  // readable bytes of the aligned view
+	uint64_t wbase = (pos + shift) & ~511ull;
+	uint4 cur = walk_load_window(bin_aligned, wbase, limit, lane);
+	uint4 nxt = walk_load_window(bin_aligned, wbase + 512, limit, lane);
 	uint32_t j = 0, nk = 0, next_tile = 0;
+	uint32_t my_off = 0, my_kpre = 0;
 	while (pos < end) {
-		const uint32_t x = a.bin[pos];
-		a.sk_off[slot + j] = (uint32_t)pos;
-		a.sk_kpre[slot + j] = nk;
+		uint64_t rel = pos + shift - wbase;
+		if (rel >= 512) {            // a record is at most 1 + (k + 255 + 3) / 4 <= 97 bytes: one window shift is enough
+			cur = nxt;
+			wbase += 512;
+			nxt = walk_load_window(bin_aligned, wbase + 512, limit, lane);
+			rel -= 512;
+		}
+		const uint32_t r = (uint32_t)rel;
+		const uint32_t comp = (r >> 2) & 3u;
+		uint32_t w = comp == 0 ? cur.x : comp == 1 ? cur.y : comp == 2 ? cur.z : cur.w;
+		w = __shfl_sync(0xffffffffu, w, r >> 4);
+		const uint32_t x = (w >> ((r & 3u) * 8u)) & 0xFFu;
+		if (lane == (j & 31u)) { my_off = (uint32_t)pos; my_kpre = nk; }
+		if ((j & 31u) == 31u) {      // 32 super-k-mers collected: one coalesced store each
+			a.sk_off[slot + j - 31 + lane] = my_off;
+			a.sk_kpre[slot + j - 31 + lane] = my_kpre;
+		}
 		if (nk + x + 1 > next_tile * (uint32_t)kExpandTile) {   // this super-k-mer holds k-mer number next_tile * tile of the pack
-			a.tile_first[tfb + next_tile] = j;
+			if (lane == 0) a.tile_first[tfb + next_tile] = j;
 			++next_tile;
 		}
 		nk += x + 1;
 		pos += 1 + ((x + a.k + 3) >> 2);
 		++j;
 	}
-	if (pos != end) atomicOr(a.status, kErrPackWalk);
-	a.pack_nsk[p] = j;
-	a.pack_nk[p] = nk;
+	if (lane < (j & 31u)) {          // the unfinished group
+		a.sk_off[slot + (j & ~31u) + lane] = my_off;
+		a.sk_kpre[slot + (j & ~31u) + lane] = my_kpre;
+	}
+	if (lane == 0) {
+		if (pos != end) atomicOr(a.status, kErrPackWalk);
+		a.pack_nsk[p] = j;
+		a.pack_nk[p] = nk;
+	}
 }
 
 // single CTA: exclusive scans over packs

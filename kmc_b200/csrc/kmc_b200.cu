@@ -278,7 +278,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.recs = d_recs; a.hist0 = s.zero->hist[0];
 
 	CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
-	walk_packs_kernel<<<(np + 127) / 128, 128, 0, st>>>(a);
+	walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a);
 	scan_packs_kernel<<<1, 1024, 0, st>>>(a);
 	ctx->launches += 2;
 	CU(cudaGetLastError());

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 	}
 	__syncthreads();
 
-	uint32_t phase0 = 0, phase1 = 0;
+	uint32_t phase0 = 0, phase1 = 0, cnt_real = 0;
 	int cur = 0;
 	while (true) {
 		const uint32_t tile = s_tile[cur];
@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 		}
 		__syncthreads();
 
-		// ---- rank: warp w owns records [w*32*KPT, (w+1)*32*KPT) of the tile, round r covers 32 consecutive ones
+		// ---- phase 1: every record into registers + warp-private digit counts (shared-memory atomics, conflicts only inside a warp).
+		// Warp w owns records [w*32*KPT, (w+1)*32*KPT) of the tile, round r covers 32 consecutive ones.
 		R key[KPT];
-		uint16_t rank[KPT];
 		uint32_t* wh = whist + warp * 256;
 #pragma unroll
 		for (int r = 0; r < KPT; ++r) {
@@ -173,6 +173,33 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 #pragma unroll
 				for (int j = 0; j < WORDS; ++j) key[r].w[j] = ~0ull;     // padding sorts to the very end of digit 255
 			}
+			atomicAdd(&wh[rec_byte<WORDS>(key[r], p.byte)], 1u);
+		}
+		__syncthreads();
+
+		// ---- phase 2, digit d (thread d): offsets of every warp inside the digit's run, tile count; the aggregate is
+		// published BEFORE the expensive ranking so that later tiles almost never wait in their look-back
+		uint32_t cnt = 0;
+		if (tid < 256) {
+#pragma unroll
+			for (int w = 0; w < WARPS; ++w) {
+				uint32_t t = whist[w * 256 + tid];
+				whist[w * 256 + tid] = cnt;
+				cnt += t;
+			}
+			uint32_t real = cnt;
+			if (tid == 255) real -= (TILE - valid);       // padding records are not published
+			st_relaxed(desc + (uint64_t)tile * 256 + tid, desc_pack(tile == 0 ? kDescPrefix : kDescAggregate, p.epoch, real));
+			cnt_real = real;
+		}
+		const uint64_t texcl = block_excl_scan_256(cnt, warp_tot, nullptr);
+		if (tid < 256) tile_excl[tid] = (uint32_t)texcl;
+		__syncthreads();
+
+		// ---- phase 3: stable ranks from match.any + the warp's running bucket cursor; regroup by digit in shared memory
+		// (the tile buffer is dead: every record is in registers)
+#pragma unroll
+		for (int r = 0; r < KPT; ++r) {
 			const uint32_t d = rec_byte<WORDS>(key[r], p.byte);
 			const uint32_t m = __match_any_sync(0xffffffffu, d);
 			const uint32_t below = __popc(m & lanemask_lt());
@@ -183,41 +210,18 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 				wh[d] = old + __popc(m);
 			}
 			old = __shfl_sync(0xffffffffu, old, leader);
-			rank[r] = (uint16_t)(old + below);
+			buf[tile_excl[d] + old + below] = key[r];
 			__syncwarp();
 		}
-		__syncthreads();
 
-		// ---- digit d (thread d): offsets of every warp inside the digit's run, tile count, chained scan
-		uint32_t cnt = 0;
+		// ---- phase 4: chained scan over tiles (decoupled look-back), one digit per thread
 		if (tid < 256) {
-#pragma unroll
-			for (int w = 0; w < WARPS; ++w) {
-				uint32_t t = whist[w * 256 + tid];
-				whist[w * 256 + tid] = cnt;
-				cnt += t;
-			}
-		}
-		uint64_t texcl = block_excl_scan_256(cnt, warp_tot, nullptr);
-		if (tid < 256) {
-			tile_excl[tid] = (uint32_t)texcl;
-			uint32_t real = cnt;
-			if (tid == 255) real -= (TILE - valid);       // padding records are not published
-			const uint64_t excl = lookback_exclusive(desc + tid, 256, tile, (uint64_t)real, p.epoch);
+			const uint64_t excl = tile == 0 ? 0 : lookback_resolve(desc + tid, 256, tile, (uint64_t)cnt_real, p.epoch);
 			goff[tid] = bucket_base + excl - texcl;    // global index of tile-sorted position q is goff[d] + q
 		}
 		__syncthreads();
 
-		// ---- regroup by digit in shared memory (the tile buffer is dead: every record is in registers)
-#pragma unroll
-		for (int r = 0; r < KPT; ++r) {
-			const uint32_t d = rec_byte<WORDS>(key[r], p.byte);
-			const uint32_t q = tile_excl[d] + wh[d] + rank[r];
-			buf[q] = key[r];
-		}
-		__syncthreads();
-
-		// ---- digit-contiguous runs leave with coalesced stores; count the next digit on the way out
+		// ---- phase 5: digit-contiguous runs leave with coalesced stores; count the next digit on the way out
 #pragma unroll
 		for (int i = 0; i < KPT; ++i) {
 			const uint32_t q = i * THREADS + tid;
