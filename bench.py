@@ -116,16 +116,19 @@ def to_testbin(sk):
 
 
 def cpu_sample_plan(R, prm, n_rec, cores, seconds_per_step):
-    """Pick the bounded sample of a reference step: whole bins of n_rec k-mers when the budget allows, else one smaller bin."""
+    """Bounded sample of a reference step.  The reference parallelises over bins (n_sorters threads, kmc.h:1576-1584) and,
+    for k=31, expands/compacts a bin on ONE thread (kb_sorter.h:299-362,1128-1281), so it is given what it is best at:
+    cores/8 bins (capped at 16) of the workload's bin size side by side, ~8 threads each, shrunk only if the time budget
+    of a step requires it."""
     import kmc_b200
+    nb = int(min(max(cores // 8, 1), 16))
     probe = to_testbin(kmc_b200.synth_bin(777, K, 1 << 22))
+    R.process_bins([probe] * nb, prm, n_sorters=cores)          # also faults the arena in
     t0 = time.perf_counter()
-    R.process_bins([probe], prm, n_sorters=cores)
-    rate = probe.n_rec / (time.perf_counter() - t0)            # pessimistic: a small bin does not scale over all cores
-    budget = rate * seconds_per_step
-    if budget >= n_rec:
-        return int(min(max(budget // n_rec, 1), 16)), n_rec
-    return 1, int(max(1 << 22, min(n_rec, budget)))
+    R.process_bins([probe] * nb, prm, n_sorters=cores)
+    rate = nb * probe.n_rec / (time.perf_counter() - t0)
+    per = int(min(n_rec, max(1 << 22, rate * seconds_per_step / nb)))
+    return nb, per
 
 
 def run_reference_steps(R, prm, bins, cores, steps, warmup):
@@ -149,9 +152,8 @@ def cpu_baseline_block(n_rec, seconds=12.0):
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref not available on this box"}
     prm = Params(k=K, cutoff_min=CUTOFF_MIN, cutoff_max=CUTOFF_MAX, counter_max=COUNTER_MAX, lut_prefix_len=LUT_P)
     nb, per = cpu_sample_plan(R, prm, n_rec, cores, seconds / 2)
-    nb = min(nb, 8)
     b = to_testbin(kmc_b200.synth_bin(4242, K, per))
-    total, times, st = run_reference_steps(R, prm, [b] * nb, cores, 1, 0)
+    total, times, st = run_reference_steps(R, prm, [b] * nb, cores, 1, 1)
     return {"value": total / times[0], "unit": UNIT, "cores": cores, "kind": "reference",
             "sample": "%d bin(s) x %d k-mers through the unmodified CKmerBinSorter<1>::ProcessBins + RADULS AVX2 (oracle/_ref), n_sorters=%d, wall %.2f s (sort_func %.2f thread-s)" % (nb, per, cores, times[0], st[0])}
 

@@ -105,7 +105,7 @@ int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint6
 int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, uint32_t rec_bytes, uint32_t key_bytes);
 
 /* ---- device-level entry points (pointers are DEVICE pointers, `stream` is a cudaStream_t or NULL) ---
- * All work is enqueued on `stream` (NULL = slot 0's stream) and is asynchronous with respect to the host. */
+ * All work is enqueued on `stream` (NULL = the context's compute stream) and is asynchronous with respect to the host. */
 
 /* Expand + sort + count one bin that already lives in HBM.  d_superkmers must be 8-byte aligned and readable
  * up to the next multiple of 8 past size.  pack_bytes is a HOST array.  d_result receives 8 x uint64:

@@ -57,6 +57,7 @@ struct Slot {
 	uint64_t* d_result = nullptr; uint64_t* h_result = nullptr;
 	// events
 	cudaEvent_t ev_begin = nullptr, ev_expand = nullptr, ev_sort = nullptr, ev_count = nullptr, ev_result = nullptr;
+	cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;           // copy stream <-> compute stream hand-over
 	cudaEvent_t ev_pass[kMaxPasses + 1] = {};
 	int n_passes_run = 0;
 	bool ran_expand = false, ran_sort = false, ran_count = false;
@@ -76,6 +77,10 @@ struct kmcb200_ctx {
 	int occ_radix = 1, occ_expand = 1;
 	uint32_t epoch = 1;
 	uint64_t launches = 0;
+	// All kernels of a context run on ONE stream: the persistent radix passes size their grids to fill the GPU and two of
+	// them side by side only steal SMs from each other (measured: 2.5x slower).  The slots' own streams carry the
+	// host<->device copies, so the copies of one bin overlap the kernels of another.
+	cudaStream_t compute = nullptr;
 	std::vector<Slot> slots;
 	std::string err;
 };
@@ -367,8 +372,10 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };
 	if (cudaSetDevice(prm->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(KMCB200_ERR_CUDA); }
 	if (int rc = DISPATCH_WORDS(ctx, setup_kernels, ctx)) return bail(rc);
+	if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(KMCB200_ERR_CUDA); }
 	for (auto& s : ctx->slots) {
 		bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+		for (cudaEvent_t* e : {&s.ev_h2d, &s.ev_done}) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.zero), sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMemset(s.zero, 0, sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_lut), ctx->lut_entries * 8) == cudaSuccess;
@@ -396,10 +403,11 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
 		if (s.h_result) cudaFreeHost(s.h_result);
-		for (cudaEvent_t e : {s.ev_begin, s.ev_expand, s.ev_sort, s.ev_count, s.ev_result}) if (e) cudaEventDestroy(e);
+		for (cudaEvent_t e : {s.ev_begin, s.ev_expand, s.ev_sort, s.ev_count, s.ev_result, s.ev_h2d, s.ev_done}) if (e) cudaEventDestroy(e);
 		for (auto e : s.ev_pass) if (e) cudaEventDestroy(e);
 		if (s.stream) cudaStreamDestroy(s.stream);
 	}
+	if (ctx->compute) cudaStreamDestroy(ctx->compute);
 	delete ctx;
 }
 
@@ -438,11 +446,15 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	if (s.busy) return fail(ctx, KMCB200_ERR_BUSY, "slot %u already holds a submitted bin", slot);
 	if ((size && !superkmers) || !lut || (!out_suffix && out_capacity)) return fail(ctx, KMCB200_ERR_INVALID, "null buffer");
 	if (int rc = set_device(ctx)) return rc;
-	cudaStream_t st = s.stream;
+	cudaStream_t st = s.stream;       // copies
 	if (int rc = ensure(ctx, s.d_bin, s.bin_cap, size + 64)) return rc;
 	if (int rc = ensure(ctx, s.d_out, s.out_cap, out_capacity + 64)) return rc;
 	if (size) CU(cudaMemcpyAsync(s.d_bin, superkmers, size, cudaMemcpyHostToDevice, st));
-	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, st)) return rc;
+	CU(cudaEventRecord(s.ev_h2d, st));
+	CU(cudaStreamWaitEvent(ctx->compute, s.ev_h2d, 0));
+	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute)) return rc;
+	CU(cudaEventRecord(s.ev_done, ctx->compute));
+	CU(cudaStreamWaitEvent(st, s.ev_done, 0));
 	CU(cudaMemcpyAsync(s.h_result, s.d_result, 64, cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(s.ev_result, st));
 	CU(cudaMemcpyAsync(lut, s.d_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, st));
@@ -496,7 +508,7 @@ int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, ui
 	if (s.busy) return fail(ctx, KMCB200_ERR_BUSY, "slot 0 busy");
 	const int where = (key_bytes & 1) ? 1 : 0;      // kb_sorter.h:776-779
 	if (n == 0) return where;
-	cudaStream_t st = s.stream;
+	cudaStream_t st = ctx->compute;
 	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, n * rec_bytes)) return rc;
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n * rec_bytes)) return rc;
 	CU(cudaMemcpyAsync(s.recs_a, recs, n * rec_bytes, cudaMemcpyHostToDevice, st));
@@ -513,7 +525,7 @@ int kmcb200_dev_process_bin(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_su
 	if (int rc = check_slot(ctx, slot)) return rc;
 	if (int rc = set_device(ctx)) return rc;
 	Slot& s = ctx->slots[slot];
-	return run_bin(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_out, out_capacity, d_lut, d_result, stream ? (cudaStream_t)stream : s.stream);
+	return run_bin(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_out, out_capacity, d_lut, d_result, stream ? (cudaStream_t)stream : ctx->compute);
 }
 
 int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkmers, uint64_t size, uint64_t n_rec,
@@ -522,7 +534,7 @@ int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkm
 	if (int rc = check_slot(ctx, slot)) return rc;
 	if (int rc = set_device(ctx)) return rc;
 	Slot& s = ctx->slots[slot];
-	cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
 	if (n_rec == 0) return 0;
 	CU(cudaEventRecord(s.ev_begin, st));
 	if (int rc = stage_expand(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_recs, st)) return rc;
@@ -542,7 +554,7 @@ int kmcb200_dev_sort(kmcb200_ctx* ctx, uint32_t slot, void* d_recs, void* d_tmp,
 	if (key_bytes < 1 || key_bytes > (uint32_t)ctx->words * 8) return fail(ctx, KMCB200_ERR_INVALID, "key_bytes %u", key_bytes);
 	if (int rc = set_device(ctx)) return rc;
 	Slot& s = ctx->slots[slot];
-	cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
 	const int where = (key_bytes & 1) ? 1 : 0;
 	if (n == 0) return where;
 	if (!hist_ready) CU(cudaEventRecord(s.ev_expand, st));
@@ -559,7 +571,7 @@ int kmcb200_dev_count(kmcb200_ctx* ctx, uint32_t slot, const void* d_sorted, uin
 	if (int rc = check_slot(ctx, slot)) return rc;
 	if (int rc = set_device(ctx)) return rc;
 	Slot& s = ctx->slots[slot];
-	cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
 	CU(cudaEventRecord(s.ev_sort, st));
 	if (int rc = stage_count(ctx, s, d_sorted, n, d_out, out_capacity, d_lut, d_result, st)) return rc;
 	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n, nullptr);

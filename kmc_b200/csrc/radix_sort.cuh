@@ -197,11 +197,15 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 		__syncthreads();
 
 		// ---- phase 3: stable ranks from match.any + the warp's running bucket cursor; regroup by digit in shared memory
-		// (the tile buffer is dead: every record is in registers)
+		// (the tile buffer is dead: every record is in registers).  All match.any are issued first (independent, their
+		// latency overlaps); only the short cursor update is a serial chain over the rounds.
+		uint32_t peers[KPT];
+#pragma unroll
+		for (int r = 0; r < KPT; ++r) peers[r] = __match_any_sync(0xffffffffu, rec_byte<WORDS>(key[r], p.byte));
 #pragma unroll
 		for (int r = 0; r < KPT; ++r) {
 			const uint32_t d = rec_byte<WORDS>(key[r], p.byte);
-			const uint32_t m = __match_any_sync(0xffffffffu, d);
+			const uint32_t m = peers[r];
 			const uint32_t below = __popc(m & lanemask_lt());
 			const int leader = __ffs(m) - 1;
 			uint32_t old = 0;
