@@ -20,6 +20,10 @@
 #include "kmc_core/raduls.h"
 #include "kmc_core/radix.h"
 #include "kmc_core/kb_sorter.h"
+#ifdef KMCREF_WITH_B200
+// drop-in test: the product's host shim compiled inside the reference tree, in place of CKmerBinSorter
+#include "kb_sorter_b200.h"
+#endif
 
 #include <chrono>
 #include <cstring>
@@ -47,6 +51,7 @@ template <unsigned SIZE>
 int run_bins(int k, int both_strands, uint32_t cutoff_min, uint32_t cutoff_max, uint32_t counter_max,
 	uint32_t lut_prefix_len, int n_sorters, int sort_kind, std::vector<BinIO>& bins, double* times)
 {
+	// sort_kind: 0 RADULS, 1 radix.h, 2 = the B200 drop-in (CKmerBinSorterB200 instead of CKmerBinSorter)
 	const int n_bins = (int)bins.size();
 	CKMCParams P{};
 	P.kmer_len = k;
@@ -123,10 +128,22 @@ int run_bins(int k, int both_strands, uint32_t cutoff_min, uint32_t cutoff_max, 
 	// sorter threads (kmc.h:1576-1584)
 	std::vector<std::unique_ptr<CKmerBinSorter<SIZE>>> sorters;
 	std::vector<std::thread> sorter_threads;
-	for (int i = 0; i < n_sorters; ++i)
-		sorters.emplace_back(std::make_unique<CKmerBinSorter<SIZE>>(P, Q, sort_func));
-	for (int i = 0; i < n_sorters; ++i)
-		sorter_threads.emplace_back([&, i] { sorters[i]->ProcessBins(); });
+#ifdef KMCREF_WITH_B200
+	std::vector<std::unique_ptr<CKmerBinSorterB200<SIZE>>> gpu_sorters;
+	if (sort_kind == 2) {
+		for (int i = 0; i < n_sorters; ++i)
+			gpu_sorters.emplace_back(std::make_unique<CKmerBinSorterB200<SIZE>>(P, Q, 0));
+		for (int i = 0; i < n_sorters; ++i)
+			sorter_threads.emplace_back([&, i] { gpu_sorters[i]->ProcessBins(); });
+	} else
+#endif
+	{
+		if (sort_kind == 2) return -4;
+		for (int i = 0; i < n_sorters; ++i)
+			sorters.emplace_back(std::make_unique<CKmerBinSorter<SIZE>>(P, Q, sort_func));
+		for (int i = 0; i < n_sorters; ++i)
+			sorter_threads.emplace_back([&, i] { sorters[i]->ProcessBins(); });
+	}
 
 	// completer stand-in (kb_completer.cpp:131-205): copy the packs, free suffix + lut
 	std::atomic<int> rc{0};

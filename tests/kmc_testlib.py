@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libkmc_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libkmc_ref.so")
+REF_B200_SO = os.path.join(ORACLE_DIR, "_ref", "libkmc_ref_b200.so")    # same harness, CKmerBinSorterB200 in place of CKmerBinSorter
 PACK_BYTES = 1 << 16          # bin_part_size, kmc_core/kmc.h:151
 
 
@@ -362,12 +363,14 @@ class Oracle:
 
 class Reference:
     """The unmodified reference stage 2 (oracle/ref/ref_harness.cpp)."""
-    RADULS, RADIX_H = 0, 1
+    RADULS, RADIX_H, B200_DROPIN = 0, 1, 2
 
-    def __init__(self):
+    def __init__(self, with_b200=False):
         if not ensure_reference_built():
             raise RuntimeError("oracle/_ref/libkmc_ref.so is not built and /root/reference is absent")
-        self.lib = C.CDLL(REF_SO)
+        if with_b200 and not os.path.exists(REF_B200_SO):
+            raise RuntimeError("oracle/_ref/libkmc_ref_b200.so is not built")
+        self.lib = C.CDLL(REF_B200_SO if with_b200 else REF_SO)
         self.lib.kmcref_process_bins.restype = C.c_int
         self.lib.kmcref_sort.restype = C.c_int
         self.lib.kmcref_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double)]

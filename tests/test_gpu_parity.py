@@ -209,3 +209,22 @@ def test_large_bin_properties_and_parity(oracle):
     full = (prefix << np.uint64(48)) | suf
     assert np.all(full[1:] > full[:-1])
     ctx.close()
+
+
+def test_dropin_inside_reference_pipeline(oracle):
+    """The host shim (kmc_b200/host/kb_sorter_b200.h) compiled INSIDE the reference tree: the reference's own reader stand-in,
+    CMemoryBins arena, CBinQueue, CSortersManager and CKmerQueue drive CKmerBinSorterB200 instead of CKmerBinSorter
+    (oracle/ref/ref_harness.cpp, sort_kind=2); what the completer stand-in pops must equal the CPU reference's output."""
+    import os
+    from kmc_testlib import Reference, REF_B200_SO
+    if not os.path.exists(REF_B200_SO):
+        pytest.skip("oracle/_ref/libkmc_ref_b200.so not built")
+    Rg = Reference(with_b200=True)
+    for k, both, cmin in [(31, True, 2), (55, True, 1), (28, False, 1)]:
+        p = Params(k=k, both_strands=both, cutoff_min=cmin, lut_prefix_len=choose_lut_prefix_len(k))
+        bins = [synth_bin(300 + i, k, n, genome_len=max(n, 500)) for i, n in enumerate([4000, 0, 900, 15000, 1])]
+        got, _ = Rg.process_bins(bins, p, n_sorters=2, sort_kind=Reference.B200_DROPIN)
+        cpu, _ = Rg.process_bins(bins, p, n_sorters=2, sort_kind=Reference.RADULS)
+        for b, g, c in zip(bins, got, cpu):
+            assert g.same_as(c)
+            assert g.same_as(oracle.process_bin(b, p))
