@@ -48,7 +48,7 @@ def hbm_peak():
 def workload_config(n_rec, n_gpus):
     return {
         "workload": "k=31 canonical, one bin of %d k-mers per GPU per step (BASELINE configs[1]), ci=2 cx=1e9 cs=255 p=7" % n_rec,
-        "n_rec_per_bin": n_rec, "record_bytes": REC_BYTES, "radix_passes": KEY_BYTES,
+        "n_rec_per_bin": n_rec, "record_bytes": REC_BYTES, "key_bytes": KEY_BYTES,
         "bin": "synthetic super-k-mers (kb_collector format), ~12 k-mers/super-k-mer, 30x duplicate-rich, 1% substitutions",
         "bins_per_step": n_gpus,
         "l2": "per-step working set ~%.1f GB (2 record buffers) >> 126 MB L2; two input bins alternate between steps" % (2 * n_rec * REC_BYTES / 1e9),
@@ -291,7 +291,15 @@ def main_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        pass_ms = [x for x in st["pass_ms"] if x > 0]
+        names = st.get("pass_names") or ["radix_pass"] * len(st["pass_ms"])
+        intervals = dict()
+        for nm, x in zip(names, st["pass_ms"]):
+            intervals.setdefault(nm, []).append(x)
+        part = [x for nm, v in intervals.items() if nm.startswith("msd_partition") for x in v]
+        if part:        # hybrid MSD sort: the two partition passes are the radix passes (1 read + 1 write of every record each)
+            pass_ms, kernel_name = part, "msd_partition_kernel<1> (one 8-bit MSD partition pass over %d 8-byte records)" % n_rec
+        else:
+            pass_ms, kernel_name = [x for x in st["pass_ms"] if x > 0], "radix_pass_kernel<1> (one 8-bit LSD pass over %d 8-byte records)" % n_rec
         avg_pass = sum(pass_ms) / len(pass_ms)
         alg_bytes = 2.0 * n_rec * REC_BYTES                # one read + one write of every record
         achieved = alg_bytes / (avg_pass * 1e-3) / 1e9
@@ -306,10 +314,11 @@ def main_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": workload_config(n_rec, world),
-            "roofline": {"bound": "hbm", "kernel": "radix_pass_kernel<1> (one 8-bit pass over %d 8-byte records)" % n_rec,
+            "roofline": {"bound": "hbm", "kernel": kernel_name,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass,
-                         "pass_ms": pass_ms, "stage_ms": {"expand": st["expand_ms"], "sort": st["sort_ms"], "count": st["count_ms"]}},
+                         "pass_ms": pass_ms, "sort_intervals_ms": {k: v for k, v in intervals.items()},
+                         "stage_ms": {"expand": st["expand_ms"], "sort": st["sort_ms"], "count": st["count_ms"]}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "ms_per_step": 1e3 * t_e2e / args.steps, "api": "kmcb200_submit_bin/kmcb200_wait_bin, 2 slots, pinned host buffers"},
             "gpu_launches": launches, "clocks": clocks,

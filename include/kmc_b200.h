@@ -129,9 +129,13 @@ int kmcb200_dev_count(kmcb200_ctx* ctx, uint32_t slot, const void* d_sorted, uin
 /* Number of kernels this library has launched on the context so far (bench.py reports the delta). */
 uint64_t kmcb200_kernel_launches(const kmcb200_ctx* ctx);
 /* Duration in ms of the last-run stages of a slot, measured with CUDA events on the launching stream:
- * ms[0] index+expand, ms[1] sort (all passes), ms[2] count/emit, ms[3..3+n_passes) the radix passes.
- * Blocks until the slot's work has finished.  Returns the number of radix passes, negative on error. */
+ * ms[0] index+expand, ms[1] sort (all of it), ms[2] count/emit, ms[3..3+n) the n timed intervals of the sort (hybrid MSD:
+ * level-1 partition, level-2 count, level-2 partition, leaves, LSD fallback; or the plain LSD passes).
+ * Blocks until the slot's work has finished.  Returns n, negative on error. */
 int kmcb200_stage_times(kmcb200_ctx* ctx, uint32_t slot, float* ms, uint32_t capacity);
+/* Comma-separated names of the timed sort intervals ms[3..] of kmcb200_stage_times ("msd_partition_L1,msd_count_L2,...").
+ * Returns their number. */
+int kmcb200_stage_names(kmcb200_ctx* ctx, uint32_t slot, char* buf, uint32_t capacity);
 
 /* Synthetic bin in stage 1's output format (kb_collector.cpp:34-90) for tests and benchmarks: super-k-mers are
  * substrings (random strand, `err_ppm` substitutions per million symbols) of a random genome of genome_len

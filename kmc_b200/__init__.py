@@ -34,7 +34,7 @@ EXPORTS = [
     "kmcb200_create", "kmcb200_destroy", "kmcb200_last_error", "kmcb200_out_rec_bytes", "kmcb200_out_capacity", "kmcb200_lut_entries",
     "kmcb200_host_alloc", "kmcb200_host_free", "kmcb200_process_bin", "kmcb200_submit_bin", "kmcb200_wait_bin", "kmcb200_sort_records",
     "kmcb200_dev_process_bin", "kmcb200_dev_expand", "kmcb200_dev_sort", "kmcb200_dev_count", "kmcb200_kernel_launches",
-    "kmcb200_stage_times", "kmcb200_synth_bin",
+    "kmcb200_stage_times", "kmcb200_stage_names", "kmcb200_synth_bin",
 ]
 
 _lib = None
@@ -75,6 +75,7 @@ def load_library(build_if_needed=True):
     L.kmcb200_kernel_launches.argtypes = [vp]
     L.kmcb200_kernel_launches.restype = u64
     L.kmcb200_stage_times.argtypes = [vp, u32, C.POINTER(C.c_float), u32]
+    L.kmcb200_stage_names.argtypes = [vp, u32, C.c_char_p, u32]
     L.kmcb200_synth_bin.argtypes = [u64, u32, u64, u64, C.c_double, u32, vp, u64, C.POINTER(u64), vp, u32, C.POINTER(u32), C.POINTER(u64)]
     _lib = L
     return L
@@ -181,9 +182,12 @@ class Stage2Context:
         return int(self.lib.kmcb200_kernel_launches(self._h))
 
     def stage_times(self, slot=0):
-        ms = (C.c_float * 40)()
-        n = self._check(self.lib.kmcb200_stage_times(self._h, slot, ms, 40))
-        return {"expand_ms": ms[0], "sort_ms": ms[1], "count_ms": ms[2], "pass_ms": [ms[3 + i] for i in range(n)]}
+        ms = (C.c_float * 48)()
+        n = self._check(self.lib.kmcb200_stage_times(self._h, slot, ms, 48))
+        names = C.create_string_buffer(2048)
+        self._check(self.lib.kmcb200_stage_names(self._h, slot, names, 2048))
+        nm = names.value.decode().split(",") if names.value else []
+        return {"expand_ms": ms[0], "sort_ms": ms[1], "count_ms": ms[2], "pass_ms": [ms[3 + i] for i in range(n)], "pass_names": nm}
 
     # -- seam #2, host buffers
     def process_bin(self, b: SuperKmerBin, out=None, lut=None, bin_id=0) -> BinResult:

@@ -47,7 +47,9 @@ struct ExpandArgs {
 	uint32_t* status;            // [0] error bits, [1] total tiles
 	// output
 	void* recs;
-	uint64_t* hist0;             // [256] histogram of record byte 0 (zero-initialised)
+	uint64_t* hist0;             // [256] histogram of record byte 0 (zero-initialised): first digit of the LSD passes
+	uint32_t* hist_top;          // [256] histogram of bits [top_shift, top_shift + 8): first digit of the MSD partition
+	uint32_t top_shift;
 };
 
 enum : uint32_t { kErrPackWalk = 1, kErrRecCount = 2 };
@@ -224,15 +226,32 @@ __device__ __forceinline__ Rec<WORDS> extract_kmer(const uint8_t* payload, uint3
 	return rec_less<WORDS>(f, r) ? f : r;       // kmer < rev ? kmer : rev  (kb_sorter.h:340,356)
 }
 
+// 8 bits starting at bit `shift` of the record
+template <int WORDS>
+__device__ __forceinline__ uint32_t rec_top_digit(const Rec<WORDS>& r, uint32_t shift)
+{
+	const uint32_t wi = shift >> 6, off = shift & 63u;
+	uint64_t lo = r.w[0], hi = 0;
+#pragma unroll
+	for (int i = 1; i < WORDS; ++i) {
+		if (wi == (uint32_t)i) lo = r.w[i];
+		if (wi + 1 == (uint32_t)i) hi = r.w[i];
+	}
+	uint64_t v = lo >> off;
+	if (WORDS > 1 && off) v |= hi << (64u - off);
+	return (uint32_t)v & 0xFFu;
+}
+
 template <int WORDS>
 __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandArgs a)
 {
 	constexpr int IPT = kExpandTile / kExpandThreads;    // 8
 	__shared__ uint16_t head[kExpandTile];
 	__shared__ uint32_t warp_max[kExpandThreads / 32];
-	__shared__ uint32_t hist[256];
+	__shared__ uint32_t hist[256], htop[256];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	hist[tid] = 0;
+	htop[tid] = 0;
 	const uint32_t total_tiles = a.status[1];
 	Rec<WORDS>* __restrict__ out = reinterpret_cast<Rec<WORDS>*>(a.recs);
 
@@ -294,12 +313,15 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandArgs
 				const Rec<WORDS> r = extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0);
 				out[obase + slot] = r;
 				atomicAdd(&hist[(uint32_t)r.w[0] & 0xFFu], 1u);
+				atomicAdd(&htop[rec_top_digit<WORDS>(r, a.top_shift)], 1u);
 			}
 		}
 	}
 	__syncthreads();
 	const uint32_t c = hist[tid];
 	if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.hist0) + tid, (unsigned long long)c);
+	const uint32_t ct = htop[tid];
+	if (ct) atomicAdd(a.hist_top + tid, ct);
 }
 
 }  // namespace kmcb

@@ -6,10 +6,12 @@
 #include "expand.cuh"
 #include "radix_sort.cuh"
 #include "count.cuh"
+#include "msd_sort.cuh"
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,7 +33,11 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint64_t hist[kHistRows][256];
 	uint32_t counters[kCounterSlots];
 	uint32_t status[2];                           // expand: [0] error bits, [1] total tiles
-	uint32_t pad[6];
+	uint32_t msd_flags[4];                        // [0] kMsdFlagFallback (leaves too large -> LSD passes), [1] always 0
+	uint32_t msd_n_items[2];                      // work items of the level-1 / level-2 segmentation
+	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves
+	uint32_t hist_top[256];                       // histogram of the level-1 digit (counted by expand_kernel)
+	uint32_t msd_hist2[65536];                    // histogram of the level-2 digit inside every level-1 bucket
 };
 
 struct Slot {
@@ -50,6 +56,14 @@ struct Slot {
 	uint32_t* tile_pack = nullptr; size_t tile_pack_cap = 0;
 	ZeroBlock* zero = nullptr;
 	uint64_t* desc = nullptr; size_t desc_cap = 0;          // radix look-back descriptors
+	// hybrid MSD sort: bucket boundaries and work-item tables
+	uint64_t* msd_seg1 = nullptr;                           // [2]      {0, n}
+	uint64_t* msd_start2 = nullptr;                         // [257]    level-1 buckets
+	uint64_t* msd_start3 = nullptr;                         // [65537]  level-2 buckets
+	uint32_t* msd_item_base1 = nullptr;                     // [2]
+	uint32_t* msd_item_base2 = nullptr;                     // [257]
+	uint32_t* msd_item_seg2 = nullptr; size_t msd_item_seg2_cap = 0;
+	const char* pass_names[kMaxPasses + 8] = {};
 	uint64_t* cdesc = nullptr; size_t cdesc_cap = 0;        // count look-back descriptors
 	// outputs of the host-buffer path
 	uint8_t* d_out = nullptr; size_t out_cap = 0;
@@ -58,8 +72,8 @@ struct Slot {
 	// events
 	cudaEvent_t ev_begin = nullptr, ev_expand = nullptr, ev_sort = nullptr, ev_count = nullptr, ev_result = nullptr;
 	cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;           // copy stream <-> compute stream hand-over
-	cudaEvent_t ev_pass[kMaxPasses + 1] = {};
-	int n_passes_run = 0;
+	cudaEvent_t ev_pass[kMaxPasses + 8] = {};
+	int n_passes_run = 0;                                   // number of timed sort intervals (ev_pass[i] .. ev_pass[i+1])
 	bool ran_expand = false, ran_sort = false, ran_count = false;
 	// pending host-buffer bin
 	bool busy = false;
@@ -74,7 +88,8 @@ struct kmcb200_ctx {
 	uint32_t key_bytes = 0, suffix_bytes = 0, counter_bytes = 0;
 	uint64_t lut_entries = 0;
 	int sm_count = 0;
-	int occ_radix = 1, occ_expand = 1;
+	int occ_radix = 1, occ_expand = 1, occ_msd_part = 1, occ_msd_local = 1;
+	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
 	uint32_t epoch = 1;
 	uint64_t launches = 0;
 	// All kernels of a context run on ONE stream: the persistent radix passes size their grids to fill the GPU and two of
@@ -142,8 +157,15 @@ int setup_kernels(kmcb200_ctx* ctx)
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_expand, expand_kernel<WORDS>, kExpandThreads, 0));
 	const size_t cs = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	CU(cudaFuncSetAttribute(count_emit_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
+	CU(cudaFuncSetAttribute(msd_partition_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MsdSmem<WORDS>::kBytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_part, msd_partition_kernel<WORDS>, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes));
+	const int local_smem = msd_local_cap<WORDS>() * 8 * WORDS + (MsdLocalCfg<WORDS>::kThreads / 32) * 1024;
+	CU(cudaFuncSetAttribute(msd_local_sort_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, local_smem));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_local, msd_local_sort_kernel<WORDS>, MsdLocalCfg<WORDS>::kThreads, local_smem));
 	if (ctx->occ_radix < 1) ctx->occ_radix = 1;
 	if (ctx->occ_expand < 1) ctx->occ_expand = 1;
+	if (ctx->occ_msd_part < 1) ctx->occ_msd_part = 1;
+	if (ctx->occ_msd_local < 1) ctx->occ_msd_local = 1;
 	return 0;
 }
 
@@ -158,39 +180,129 @@ int launch_expand(kmcb200_ctx* ctx, const ExpandArgs& a, cudaStream_t st)
 	return 0;
 }
 
+__global__ void msd_setup_kernel(uint64_t* seg1, uint32_t* item_base1, uint32_t* n_items1, uint64_t n, uint32_t tile)
+{
+	seg1[0] = 0; seg1[1] = n;
+	const uint32_t nt = (uint32_t)((n + tile - 1) / tile);
+	item_base1[0] = 0; item_base1[1] = nt;
+	*n_items1 = nt;
+}
+
 template <int WORDS>
-int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, bool hist_ready, cudaStream_t st)
+__global__ void __launch_bounds__(512) bits_histogram_kernel(const void* in, uint64_t n, uint32_t shift, uint32_t* hist)
+{
+	__shared__ uint32_t sh[256];
+	const Rec<WORDS>* __restrict__ g = reinterpret_cast<const Rec<WORDS>*>(in);
+	if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&sh[rec_bits<WORDS>(g[i], shift, 0xFFu)], 1u);
+	__syncthreads();
+	if (threadIdx.x < 256 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// Sorts n records from `a` (with `b` as the second buffer).  *result_in_b tells where the sorted records end up.
+// hist_ready: expand_kernel has zeroed the slot's ZeroBlock and counted hist[0] (LSD digit 0) and hist_top (MSD digit 1).
+template <int WORDS>
+int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, bool hist_ready, cudaStream_t st, bool* result_in_b)
 {
 	constexpr int TILE = SortSmem<WORDS>::kTile;
+	constexpr int MTILE = msd_tile<WORDS>();
 	const uint64_t n_tiles64 = (n + TILE - 1) / TILE;
 	if (n_tiles64 > 0x7fffffffull) return fail(ctx, KMCB200_ERR_INVALID, "bin too large: %llu records", (unsigned long long)n);
 	const uint32_t n_tiles = (uint32_t)n_tiles64;
-	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
+	const uint32_t key_bits = std::min(2u * ctx->prm.kmer_len, key_bytes * 8u);
+	const bool msd = ctx->use_msd && key_bits >= 24 && n >= (1u << 16) && key_bytes == ctx->key_bytes;
+	const uint32_t top_shift = key_bits - 8;
+	const size_t max_items = (size_t)(n / MTILE) + 260;
+	if (int rc = ensure(ctx, s.desc, s.desc_cap, std::max((size_t)n_tiles, max_items) * 256, true)) return rc;
+	if (msd) if (int rc = ensure(ctx, s.msd_item_seg2, s.msd_item_seg2_cap, max_items)) return rc;
+
 	if (!hist_ready) {
 		CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
 		const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 511) / 512, (uint64_t)ctx->sm_count * 4);
 		digit_histogram_kernel<WORDS><<<grid, 512, 0, st>>>(a, n, 0, s.zero->hist[0]);
 		ctx->launches++;
+		if (msd) { bits_histogram_kernel<WORDS><<<grid, 512, 0, st>>>(a, n, top_shift, s.zero->hist_top); ctx->launches++; }
 	}
-	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix));
-	void* in = a; void* out = b;
+	int iv = 0;      // timed interval index
 	CU(cudaEventRecord(s.ev_pass[0], st));
+	void* lsd_in = a; void* lsd_out = b;
+	const uint32_t* lsd_flag = nullptr;
+	if (msd) {
+		// leaves of ~1-2 K records: b2 = bits of the second partition level
+		uint32_t lg = 0;
+		while ((1ull << lg) < (n + 1023) / 1024) ++lg;
+		const uint32_t b2 = lg > 8 ? std::min(lg - 8, 8u) : 0;
+		const uint32_t nd2 = 1u << b2;
+		const uint32_t cap = (uint32_t)msd_local_cap<WORDS>();
+		const bool final_in_b = (key_bytes % 2) == 0;                 // where the LSD passes (started from b) end; the leaves go to the same place
+		void* fin = final_in_b ? b : a;
+		uint32_t* flags = s.zero->msd_flags;
+		const uint32_t pgrid = (uint32_t)std::min<size_t>(max_items, (size_t)ctx->sm_count * ctx->occ_msd_part);
+		const int local_smem = msd_local_cap<WORDS>() * 8 * WORDS + (MsdLocalCfg<WORDS>::kThreads / 32) * 1024;
+
+		msd_setup_kernel<<<1, 1, 0, st>>>(s.msd_seg1, s.msd_item_base1, &s.zero->msd_n_items[0], n, MTILE);
+		MsdScanArgs sc1{};
+		sc1.counts32 = s.zero->hist_top; sc1.M = 256; sc1.start = s.msd_start2; sc1.cap = b2 == 0 ? cap : 0; sc1.flags = flags;
+		sc1.tile = MTILE; sc1.item_base = s.msd_item_base2; sc1.item_seg = s.msd_item_seg2; sc1.n_items = &s.zero->msd_n_items[1];
+		msd_scan_kernel<<<1, 1024, 0, st>>>(sc1);
+		MsdPartArgs p1{};
+		p1.in = a; p1.out = b;
+		p1.items = MsdItems{s.msd_seg1, s.msd_item_base1, nullptr, &s.zero->msd_n_items[0], 1};
+		p1.out_start = s.msd_start2; p1.shift = top_shift; p1.nd = 256; p1.desc = s.desc; p1.epoch = next_epoch(ctx);
+		p1.tile_counter = &s.zero->msd_counters[0]; p1.flags = &flags[1];          // level 1 always runs: the LSD passes start from its output
+		msd_partition_kernel<WORDS><<<pgrid, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p1);
+		ctx->launches += 3;
+		s.pass_names[iv] = "msd_partition_L1"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+		if (b2 > 0) {
+			const MsdItems items2{s.msd_start2, s.msd_item_base2, s.msd_item_seg2, &s.zero->msd_n_items[1], 256};
+			MsdCountArgs c2{b, items2, top_shift - b2, nd2, s.zero->msd_hist2, flags};
+			msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
+			MsdScanArgs sc2{};
+			sc2.counts32 = s.zero->msd_hist2; sc2.M = 256 * nd2; sc2.start = s.msd_start3; sc2.cap = cap; sc2.flags = flags; sc2.tile = 0;
+			msd_scan_kernel<<<1, 1024, 0, st>>>(sc2);
+			ctx->launches += 2;
+			s.pass_names[iv] = "msd_count_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+			MsdPartArgs p2{};
+			p2.in = b; p2.out = a; p2.items = items2; p2.out_start = s.msd_start3; p2.shift = top_shift - b2; p2.nd = nd2;
+			p2.desc = s.desc; p2.epoch = next_epoch(ctx); p2.tile_counter = &s.zero->msd_counters[1]; p2.flags = flags;
+			msd_partition_kernel<WORDS><<<pgrid, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p2);
+			ctx->launches++;
+			s.pass_names[iv] = "msd_partition_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+		}
+		MsdLocalArgs lo{};
+		lo.in = b2 > 0 ? a : b; lo.out = fin; lo.start = b2 > 0 ? s.msd_start3 : s.msd_start2; lo.n_buckets = 256 * nd2;
+		lo.low_bits = top_shift - b2; lo.bucket_counter = &s.zero->msd_counters[2]; lo.flags = flags;
+		const uint32_t lgrid = (uint32_t)std::min<size_t>(lo.n_buckets, (size_t)ctx->sm_count * ctx->occ_msd_local);
+		msd_local_sort_kernel<WORDS><<<lgrid, MsdLocalCfg<WORDS>::kThreads, local_smem, st>>>(lo);
+		ctx->launches++;
+		s.pass_names[iv] = "msd_local_sort"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+		lsd_in = b; lsd_out = a; lsd_flag = flags;
+		*result_in_b = final_in_b;
+	} else
+		*result_in_b = (key_bytes % 2) == 1;
+
+	// 8-bit LSD passes: the whole sort when the hybrid path is off, otherwise its fallback (they return at once unless flagged)
+	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix));
 	for (uint32_t pass = 0; pass < key_bytes; ++pass) {
 		SortPass p;
-		p.in = in; p.out = out; p.n = n; p.n_tiles = n_tiles; p.byte = pass;
+		p.in = lsd_in; p.out = lsd_out; p.n = n; p.n_tiles = n_tiles; p.byte = pass;
 		p.next_byte = pass + 1 < key_bytes ? (int32_t)(pass + 1) : -1;
 		p.hist = s.zero->hist[pass];
 		p.hist_next = s.zero->hist[pass + 1];
 		p.desc = s.desc;
 		p.epoch = next_epoch(ctx);
 		p.tile_counter = &s.zero->counters[pass];
+		p.run_flag = lsd_flag;
 		radix_pass_kernel<WORDS><<<grid, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes, st>>>(p);
 		ctx->launches++;
-		CU(cudaEventRecord(s.ev_pass[pass + 1], st));
-		std::swap(in, out);
+		if (!msd) { s.pass_names[iv] = "radix_pass"; CU(cudaEventRecord(s.ev_pass[++iv], st)); }
+		std::swap(lsd_in, lsd_out);
 	}
+	if (msd) { s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st)); }
 	CU(cudaGetLastError());
-	s.n_passes_run = (int)key_bytes;
+	s.n_passes_run = iv;
 	return 0;
 }
 
@@ -281,6 +393,8 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
 	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.status = s.zero->status;
 	a.recs = d_recs; a.hist0 = s.zero->hist[0];
+	a.hist_top = s.zero->hist_top;
+	a.top_shift = std::max(2u * k, 8u) - 8u;
 
 	CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
 	walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a);
@@ -325,10 +439,11 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st)) return rc;
 	CU(cudaEventRecord(s.ev_expand, st));
 	s.ran_expand = true;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, true, st)) return rc;
+	bool in_b = false;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, true, st, &in_b)) return rc;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true;
-	const void* sorted = (ctx->key_bytes & 1) ? s.recs_b : s.recs_a;
+	const void* sorted = in_b ? s.recs_b : s.recs_a;
 	if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
 	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status);
 	ctx->launches++;
@@ -368,6 +483,7 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	ctx->counter_bytes = prm->counter_max == 1 ? 0 : std::min(byte_log(prm->cutoff_max), byte_log(prm->counter_max));   // defs.h:154-159
 	ctx->lut_entries = 1ull << (2 * prm->lut_prefix_len);
 	ctx->sm_count = dp.multiProcessorCount;
+	if (const char* e = getenv("KMCB200_SORT")) ctx->use_msd = std::string(e) != "lsd";
 	ctx->slots.resize(prm->n_slots);
 	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };
 	if (cudaSetDevice(prm->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(KMCB200_ERR_CUDA); }
@@ -379,6 +495,11 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.zero), sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMemset(s.zero, 0, sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_lut), ctx->lut_entries * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_seg1), 2 * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_start2), 257 * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_start3), 65537 * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_item_base1), 2 * 4) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_item_base2), 257 * 4) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_result), 64) == cudaSuccess;
 		ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_result), 64, cudaHostAllocDefault) == cudaSuccess;
 		for (cudaEvent_t* e : {&s.ev_begin, &s.ev_expand, &s.ev_sort, &s.ev_count, &s.ev_result}) ok = ok && cudaEventCreate(e) == cudaSuccess;
@@ -398,7 +519,8 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 	for (auto& s : ctx->slots) {
 		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
 				 (void*)s.pack_kbase, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
-				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result})
+				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
+				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2})
 			if (p) cudaFree(p);
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
@@ -512,8 +634,9 @@ int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, ui
 	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, n * rec_bytes)) return rc;
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n * rec_bytes)) return rc;
 	CU(cudaMemcpyAsync(s.recs_a, recs, n * rec_bytes, cudaMemcpyHostToDevice, st));
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, false, st)) return rc;
-	CU(cudaMemcpyAsync(where ? tmp : recs, where ? s.recs_b : s.recs_a, n * rec_bytes, cudaMemcpyDeviceToHost, st));
+	bool in_b = false;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, false, st, &in_b)) return rc;
+	CU(cudaMemcpyAsync(where ? tmp : recs, in_b ? s.recs_b : s.recs_a, n * rec_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	return where;
 }
@@ -558,11 +681,12 @@ int kmcb200_dev_sort(kmcb200_ctx* ctx, uint32_t slot, void* d_recs, void* d_tmp,
 	const int where = (key_bytes & 1) ? 1 : 0;
 	if (n == 0) return where;
 	if (!hist_ready) CU(cudaEventRecord(s.ev_expand, st));
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready != 0, st)) return rc;
+	bool in_b = false;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready != 0, st, &in_b)) return rc;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true; s.ran_count = false;
 	if (!hist_ready) s.ran_expand = false;
-	return where;
+	return in_b ? 1 : 0;
 }
 
 int kmcb200_dev_count(kmcb200_ctx* ctx, uint32_t slot, const void* d_sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
@@ -598,6 +722,17 @@ int kmcb200_stage_times(kmcb200_ctx* ctx, uint32_t slot, float* ms, uint32_t cap
 	}
 	if (s.ran_count) CU(cudaEventElapsedTime(&ms[2], s.ev_sort, s.ev_count));
 	return s.ran_sort ? s.n_passes_run : 0;
+}
+
+int kmcb200_stage_names(kmcb200_ctx* ctx, uint32_t slot, char* buf, uint32_t capacity)
+{
+	if (int rc = check_slot(ctx, slot)) return rc;
+	if (!buf || !capacity) return fail(ctx, KMCB200_ERR_INVALID, "buffer");
+	Slot& s = ctx->slots[slot];
+	std::string out;
+	for (int p = 0; p < s.n_passes_run; ++p) { if (p) out += ","; out += s.pass_names[p] ? s.pass_names[p] : "?"; }
+	snprintf(buf, capacity, "%s", out.c_str());
+	return s.n_passes_run;
 }
 
 // ---- synthetic bins (host only; mirrors the byte format of CKmerBinCollector::PutExtendedKmer, kb_collector.cpp:34-90)

@@ -1,0 +1,448 @@
+// kmc_b200 — hybrid MSD radix sort of packed k-mer records (the fast path of the sort stage).
+//
+// Like RADULS (kmc_core/raduls_impl.h:546-754) this is an MSD radix sort with small-sort leaves: the top digits
+// split the bin into buckets, buckets that fit on chip are finished there.  An MSD partition does not have to be
+// stable (a bucket is refined independently of the order inside it), which is what makes it cheap on a GPU: the
+// rank of a record inside its tile is simply the value returned by ONE shared-memory atomicAdd - no match.any,
+// no warp-private histograms, no serial cursor chain.
+//
+//   level 1   msd_partition_kernel   whole bin   -> 2^8 buckets          (digit histogram counted by expand_kernel)
+//   count     msd_count_kernel       per level-1 bucket: histogram of the next digit
+//   scan      msd_scan_kernel        bucket boundaries of the next level (+ work-item table, + oversize check)
+//   level 2   msd_partition_kernel   every level-1 bucket -> 2^b2 sub-buckets (b2 <= 8, chosen so that a leaf has ~1-2 K records)
+//   leaves    msd_local_sort_kernel  one leaf bucket per CTA iteration: load to shared memory, LSD radix sort of the
+//                                    remaining bits entirely on chip, write back
+//
+// Traffic: 2NW (level 1) + NW (count) + 2NW (level 2) + 2NW (leaves) = 7 N*W instead of 16 N*W for 8 LSD passes.
+// A leaf that does not fit in shared memory (heavy skew) makes the scan raise a device flag; every kernel of this file then
+// returns at once and the 8-bit LSD passes of radix_sort.cuh (always enqueued behind, normally returning at once) sort the bin.
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace kmcb {
+
+constexpr uint32_t kMsdFlagFallback = 1;      // flags[0]: leaves too large -> LSD passes take over
+
+// bits [shift, shift+nbits) of a record (nbits <= 8... 32), record = little-endian multi-word integer
+template <int WORDS>
+__device__ __forceinline__ uint32_t rec_bits(const Rec<WORDS>& r, uint32_t shift, uint32_t mask)
+{
+	if (WORDS == 1) return (uint32_t)(r.w[0] >> shift) & mask;
+	const uint32_t wi = shift >> 6, off = shift & 63u;
+	uint64_t lo = r.w[0], hi = 0;
+#pragma unroll
+	for (int i = 1; i < WORDS; ++i) {
+		if (wi == (uint32_t)i) lo = r.w[i];
+		if (wi + 1 == (uint32_t)i) hi = r.w[i];
+	}
+	uint64_t v = lo >> off;
+	if (off) v |= hi << (64u - off);
+	return (uint32_t)v & mask;
+}
+
+template <int WORDS> struct MsdCfg;
+template <> struct MsdCfg<1> { static constexpr int kThreads = 512, kKpt = 8, kMinBlocks = 2; };
+template <> struct MsdCfg<2> { static constexpr int kThreads = 512, kKpt = 4, kMinBlocks = 2; };
+template <> struct MsdCfg<3> { static constexpr int kThreads = 512, kKpt = 3, kMinBlocks = 2; };
+template <> struct MsdCfg<4> { static constexpr int kThreads = 512, kKpt = 2, kMinBlocks = 2; };
+
+template <int WORDS> __host__ __device__ constexpr int msd_tile() { return MsdCfg<WORDS>::kThreads * MsdCfg<WORDS>::kKpt; }
+
+// Work items of a segmented pass: item i = (segment s, aligned tile T).  Tiles live on the absolute grid [T*TILE, (T+1)*TILE)
+// so that TMA sources are 16-byte aligned whatever the segment boundaries are; an item covers the part of its tile that belongs
+// to its segment.  Items of one segment are consecutive, which is what the look-back chain needs.
+struct MsdItems {
+	const uint64_t* seg_start;   // [S + 1] record index where every segment starts
+	const uint32_t* item_base;   // [S + 1] first item of every segment
+	const uint32_t* item_seg;    // [n_items]
+	const uint32_t* n_items;     // device scalar
+	uint32_t S;
+};
+
+struct MsdPartArgs {
+	const void* in;
+	void* out;
+	MsdItems items;
+	const uint64_t* out_start;   // [S * nd + 1] where (segment s, digit d) starts in the output = boundaries of the next level
+	uint32_t shift, nd;          // digit = bits [shift, shift + log2(nd)), nd <= 256
+	uint64_t* desc;              // [n_items][256] look-back descriptors
+	uint32_t epoch;
+	uint32_t* tile_counter;
+	const uint32_t* flags;
+};
+
+template <int WORDS>
+struct MsdSmem {
+	static constexpr int kThreads = MsdCfg<WORDS>::kThreads;
+	static constexpr int kKpt = MsdCfg<WORDS>::kKpt;
+	static constexpr int kTile = kThreads * kKpt;
+	static constexpr int kRecBytes = 8 * WORDS;
+	static constexpr int kBufBytes = (kTile + 2) * kRecBytes;      // + 2: the aligned load may start one record early / end one late
+	static constexpr int oBuf = 0;
+	static constexpr int oHist = 2 * ((kBufBytes + 127) & ~127);   // u32 [256]
+	static constexpr int oExcl = oHist + 1024;                     // u32 [256]
+	static constexpr int oGoff = oExcl + 1024;                     // u64 [256]
+	static constexpr int oWarpTot = oGoff + 2048;                  // u64 [8]
+	static constexpr int oMbar = oWarpTot + 128;                   // u64 [2]
+	static constexpr int oItem = oMbar + 16;                       // u32 [2]
+	static constexpr int kBytes = oItem + 16;
+	static constexpr int kBufStride = (kBufBytes + 127) & ~127;
+};
+
+// geometry of a work item
+struct MsdItemGeom {
+	uint64_t lo, hi;      // records [lo, hi) of the segment that fall into the tile
+	uint64_t lo_al;       // first record of the aligned load
+	uint32_t n_load;      // records of the aligned load (even number for 8-byte records)
+	uint32_t seg;
+	bool chain_start;
+};
+template <int WORDS>
+__device__ __forceinline__ MsdItemGeom msd_item_geom(const MsdItems& it, uint32_t item)
+{
+	constexpr uint64_t TILE = msd_tile<WORDS>();
+	MsdItemGeom g;
+	g.seg = it.S == 1 ? 0u : it.item_seg[item];
+	const uint64_t sb = it.seg_start[g.seg], se = it.seg_start[g.seg + 1];
+	const uint32_t first_item = it.item_base[g.seg];
+	const uint64_t T = sb / TILE + (item - first_item);
+	g.lo = T * TILE > sb ? T * TILE : sb;
+	g.hi = (T + 1) * TILE < se ? (T + 1) * TILE : se;
+	g.lo_al = g.lo & ~1ull;
+	const uint64_t hi_al = (g.hi + 1) & ~1ull;
+	g.n_load = (uint32_t)(hi_al - g.lo_al);
+	g.chain_start = item == first_item;
+	return g;
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads, MsdCfg<WORDS>::kMinBlocks) msd_partition_kernel(const MsdPartArgs p)
+{
+	using S = MsdSmem<WORDS>;
+	using R = Rec<WORDS>;
+	constexpr int THREADS = S::kThreads, KPT = S::kKpt;
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint32_t* hist = reinterpret_cast<uint32_t*>(smem + S::oHist);
+	uint32_t* tile_excl = reinterpret_cast<uint32_t*>(smem + S::oExcl);
+	uint64_t* goff = reinterpret_cast<uint64_t*>(smem + S::oGoff);
+	uint64_t* warp_tot = reinterpret_cast<uint64_t*>(smem + S::oWarpTot);
+	uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + S::oMbar);
+	volatile uint32_t* s_item = reinterpret_cast<volatile uint32_t*>(smem + S::oItem);
+
+	if (*p.flags & kMsdFlagFallback) return;
+	const uint32_t tid = threadIdx.x;
+	const R* __restrict__ gin = reinterpret_cast<const R*>(p.in);
+	R* __restrict__ gout = reinterpret_cast<R*>(p.out);
+	const uint32_t n_items = *p.items.n_items;
+	const uint32_t mask = p.nd - 1;
+
+	if (tid == 0) {
+		mbar_init(&mbar[0], 1);
+		mbar_init(&mbar[1], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+
+	auto issue_load = [&](uint32_t item, int b) {      // thread 0
+		const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item);
+		const uint32_t bytes = g.n_load * S::kRecBytes;
+		fence_proxy_async();
+		mbar_arrive_expect_tx(&mbar[b], bytes);
+		bulk_g2s(smem + S::oBuf + b * S::kBufStride, gin + g.lo_al, bytes, &mbar[b]);
+	};
+
+	if (tid == 0) {
+		const uint32_t t = atomicAdd(p.tile_counter, 1u);
+		s_item[0] = t;
+		if (t < n_items) issue_load(t, 0);
+	}
+	__syncthreads();
+
+	uint32_t phase0 = 0, phase1 = 0;
+	int cur = 0;
+	while (true) {
+		const uint32_t item = s_item[cur];
+		if (item >= n_items) break;
+		if (tid == 0) {
+			const uint32_t t = atomicAdd(p.tile_counter, 1u);
+			s_item[cur ^ 1] = t;
+			if (t < n_items) issue_load(t, cur ^ 1);
+		}
+		const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item);
+		const uint32_t head = (uint32_t)(g.lo - g.lo_al);                 // records of the load that belong to the previous segment / tile
+		const uint32_t valid = (uint32_t)(g.hi - g.lo);
+		R* buf = reinterpret_cast<R*>(smem + S::oBuf + cur * S::kBufStride);
+		if (tid < 256) hist[tid] = 0;
+		if (cur == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
+		else { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+		__syncthreads();
+
+		// ---- phase 1: rank inside (tile, digit) = return value of one shared-memory atomicAdd (an MSD partition need not be stable)
+		R key[KPT];
+		uint16_t rank[KPT];
+#pragma unroll
+		for (int r = 0; r < KPT; ++r) {
+			const uint32_t j = r * THREADS + tid;
+			if (j < valid) {
+				key[r] = buf[head + j];
+				rank[r] = (uint16_t)atomicAdd(&hist[rec_bits<WORDS>(key[r], p.shift, mask)], 1u);
+			}
+		}
+		__syncthreads();
+
+		// ---- phase 2: digit d (thread d): publish the tile aggregate, exclusive scan over the digits
+		uint32_t cnt = tid < 256 ? hist[tid] : 0;
+		if (tid < p.nd) st_relaxed(p.desc + (uint64_t)item * 256 + tid, desc_pack(g.chain_start ? kDescPrefix : kDescAggregate, p.epoch, cnt));
+		const uint64_t texcl = block_excl_scan_256(cnt, warp_tot, nullptr);
+		if (tid < 256) tile_excl[tid] = (uint32_t)texcl;
+		__syncthreads();
+
+		// ---- phase 3: regroup by digit in shared memory (every record is in registers, the buffer is free)
+#pragma unroll
+		for (int r = 0; r < KPT; ++r) {
+			const uint32_t j = r * THREADS + tid;
+			if (j < valid) buf[tile_excl[rec_bits<WORDS>(key[r], p.shift, mask)] + rank[r]] = key[r];
+		}
+
+		// ---- phase 4: chained scan over the items of this segment
+		if (tid < p.nd) {
+			const uint64_t excl = g.chain_start ? 0 : lookback_resolve(p.desc + tid, 256, item, (uint64_t)cnt, p.epoch);
+			goff[tid] = p.out_start[(uint64_t)g.seg * p.nd + tid] + excl - texcl;
+		}
+		__syncthreads();
+
+		// ---- phase 5: digit-contiguous runs leave with coalesced stores
+#pragma unroll
+		for (int i = 0; i < KPT; ++i) {
+			const uint32_t q = i * THREADS + tid;
+			if (q < valid) {
+				const R k = buf[q];
+				gout[goff[rec_bits<WORDS>(k, p.shift, mask)] + q] = k;
+			}
+		}
+		fence_proxy_async();
+		__syncthreads();
+		cur ^= 1;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// histogram of the next digit inside every segment: hist[seg * nd + digit] (u32, zero-initialised)
+struct MsdCountArgs {
+	const void* in;
+	MsdItems items;
+	uint32_t shift, nd;
+	uint32_t* hist;
+	const uint32_t* flags;
+};
+
+template <int WORDS>
+__global__ void __launch_bounds__(512) msd_count_kernel(const MsdCountArgs p)
+{
+	using R = Rec<WORDS>;
+	__shared__ uint32_t sh[256];
+	if (*p.flags & kMsdFlagFallback) return;
+	const R* __restrict__ g = reinterpret_cast<const R*>(p.in);
+	const uint32_t n_items = *p.items.n_items;
+	const uint32_t mask = p.nd - 1;
+	for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+		const MsdItemGeom gm = msd_item_geom<WORDS>(p.items, item);
+		if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+		__syncthreads();
+		for (uint64_t i = gm.lo + threadIdx.x; i < gm.hi; i += blockDim.x) atomicAdd(&sh[rec_bits<WORDS>(g[i], p.shift, mask)], 1u);
+		__syncthreads();
+		if (threadIdx.x < p.nd) {
+			const uint32_t c = sh[threadIdx.x];
+			if (c) atomicAdd(&p.hist[(uint64_t)gm.seg * p.nd + threadIdx.x], c);
+		}
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// single CTA: counts[M] -> start[M + 1] (exclusive scan, plus `base`), optional work-item table over the NEW segments,
+// optional oversize check (any count > cap raises the fallback flag)
+struct MsdScanArgs {
+	const uint32_t* counts32;    // one of the two is non-null
+	const uint64_t* counts64;
+	uint32_t M;
+	uint64_t* start;             // [M + 1]
+	uint32_t cap;                // 0: no check
+	uint32_t* flags;
+	uint32_t tile;               // items: tile size of the pass that will run over the new segments (0: no items)
+	uint32_t* item_base;         // [M + 1]
+	uint32_t* item_seg;
+	uint32_t* n_items;
+};
+
+__global__ void __launch_bounds__(1024) msd_scan_kernel(const MsdScanArgs a)
+{
+	__shared__ uint64_t s_c[32];
+	__shared__ uint32_t s_i[32];
+	__shared__ uint64_t carry_c;
+	__shared__ uint32_t carry_i;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) { carry_c = 0; carry_i = 0; }
+	__syncthreads();
+	bool over = false;
+	for (uint32_t base = 0; base < a.M; base += 1024) {
+		const uint32_t m = base + tid;
+		const uint64_t c = m < a.M ? (a.counts32 ? (uint64_t)a.counts32[m] : a.counts64[m]) : 0;
+		if (a.cap && c > a.cap) over = true;
+		uint64_t ic = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint64_t t = __shfl_up_sync(0xffffffffu, ic, o);
+			if (lane >= (uint32_t)o) ic += t;
+		}
+		if (lane == 31) s_c[warp] = ic;
+		__syncthreads();
+		uint64_t bc = carry_c;
+		for (uint32_t w = 0; w < warp; ++w) bc += s_c[w];
+		const uint64_t ec = bc + ic - c;               // exclusive prefix = where segment m starts
+		if (m < a.M) a.start[m] = ec;
+		// items of segment m: aligned tiles it touches
+		uint32_t ni = 0;
+		if (a.tile && c) ni = (uint32_t)((ec + c - 1) / a.tile - ec / a.tile) + 1;
+		uint32_t ii = ni;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, ii, o);
+			if (lane >= (uint32_t)o) ii += t;
+		}
+		if (lane == 31) s_i[warp] = ii;
+		__syncthreads();
+		uint32_t bi = carry_i;
+		for (uint32_t w = 0; w < warp; ++w) bi += s_i[w];
+		const uint32_t ei = bi + ii - ni;
+		if (a.tile && m < a.M) {
+			a.item_base[m] = ei;
+			if (a.M > 1) for (uint32_t t = 0; t < ni; ++t) a.item_seg[ei + t] = m;      // a single segment needs no map
+		}
+		__syncthreads();
+		if (tid == 1023) { carry_c = ec + c; carry_i = ei + ni; }
+		__syncthreads();
+	}
+	if (tid == 0) {
+		a.start[a.M] = carry_c;
+		if (a.tile) { a.item_base[a.M] = carry_i; *a.n_items = carry_i; }
+	}
+	if (over) atomicOr(a.flags, kMsdFlagFallback);
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaves: one bucket per CTA iteration, sorted on chip by 8-bit LSD passes over its low `low_bits` bits
+struct MsdLocalArgs {
+	const void* in;
+	void* out;
+	const uint64_t* start;       // [n_buckets + 1]
+	uint32_t n_buckets;
+	uint32_t low_bits;           // bits below the partition digits
+	uint32_t* bucket_counter;
+	const uint32_t* flags;
+};
+
+template <int WORDS> struct MsdLocalCfg;
+template <> struct MsdLocalCfg<1> { static constexpr int kThreads = 256, kKpt = 16; };
+template <> struct MsdLocalCfg<2> { static constexpr int kThreads = 256, kKpt = 8; };
+template <> struct MsdLocalCfg<3> { static constexpr int kThreads = 256, kKpt = 5; };
+template <> struct MsdLocalCfg<4> { static constexpr int kThreads = 256, kKpt = 4; };
+template <int WORDS> __host__ __device__ constexpr int msd_local_cap() { return MsdLocalCfg<WORDS>::kThreads * MsdLocalCfg<WORDS>::kKpt; }
+
+template <int WORDS>
+__global__ void __launch_bounds__(MsdLocalCfg<WORDS>::kThreads) msd_local_sort_kernel(const MsdLocalArgs p)
+{
+	using R = Rec<WORDS>;
+	constexpr int THREADS = MsdLocalCfg<WORDS>::kThreads, KPT = MsdLocalCfg<WORDS>::kKpt, WARPS = THREADS / 32, CAP = THREADS * KPT;
+	extern __shared__ __align__(16) uint8_t dsm[];
+	R* buf = reinterpret_cast<R*>(dsm);                                                 // [CAP]
+	uint32_t* whist = reinterpret_cast<uint32_t*>(dsm + (size_t)CAP * sizeof(R));       // [WARPS][256]
+	__shared__ uint32_t tile_excl[256];
+	__shared__ uint64_t warp_tot[8];
+	__shared__ uint32_t s_bucket;
+
+	if (*p.flags & kMsdFlagFallback) return;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const R* __restrict__ gin = reinterpret_cast<const R*>(p.in);
+	R* __restrict__ gout = reinterpret_cast<R*>(p.out);
+	uint32_t* wh = whist + warp * 256;
+
+	while (true) {
+		__syncthreads();
+		if (tid == 0) s_bucket = atomicAdd(p.bucket_counter, 1u);
+		__syncthreads();
+		const uint32_t b = s_bucket;
+		if (b >= p.n_buckets) break;
+		const uint64_t lo = p.start[b];
+		const uint32_t m = (uint32_t)(p.start[b + 1] - lo);
+		if (m == 0) continue;
+		// records to registers: warp w owns [w*32*KPT, ...), round r = 32 consecutive records (stable order = index order)
+		R key[KPT];
+#pragma unroll
+		for (int r = 0; r < KPT; ++r) {
+			const uint32_t idx = warp * (32 * KPT) + r * 32 + lane;
+			if (idx < m) key[r] = gin[lo + idx];
+			else {
+#pragma unroll
+				for (int j = 0; j < WORDS; ++j) key[r].w[j] = ~0ull;       // padding: largest possible key, stays at the end
+			}
+		}
+		if (m > 1) {
+			for (uint32_t shift = 0; shift < p.low_bits; shift += 8) {
+				const uint32_t mask = (p.low_bits - shift) >= 8 ? 0xFFu : ((1u << (p.low_bits - shift)) - 1u);
+				// padding must keep sorting last: its digit is forced to the largest value of this pass
+#pragma unroll
+				for (int i = tid; i < WARPS * 256; i += THREADS) whist[i] = 0;
+				__syncthreads();
+				uint32_t dg[KPT];
+#pragma unroll
+				for (int r = 0; r < KPT; ++r) {
+					const uint32_t idx = warp * (32 * KPT) + r * 32 + lane;
+					dg[r] = idx < m ? rec_bits<WORDS>(key[r], shift, mask) : mask;
+					atomicAdd(&wh[dg[r]], 1u);
+				}
+				__syncthreads();
+				uint32_t cnt = 0;
+#pragma unroll
+				for (int w = 0; w < WARPS; ++w) {
+					const uint32_t t = whist[w * 256 + tid];
+					whist[w * 256 + tid] = cnt;
+					cnt += t;
+				}
+				const uint64_t texcl = block_excl_scan_256(cnt, warp_tot, nullptr);
+				tile_excl[tid] = (uint32_t)texcl;
+				__syncthreads();
+				uint32_t peers[KPT];
+#pragma unroll
+				for (int r = 0; r < KPT; ++r) peers[r] = __match_any_sync(0xffffffffu, dg[r]);
+#pragma unroll
+				for (int r = 0; r < KPT; ++r) {
+					const uint32_t d = dg[r];
+					const uint32_t mm = peers[r];
+					const uint32_t below = __popc(mm & lanemask_lt());
+					const int leader = __ffs(mm) - 1;
+					uint32_t old = 0;
+					if ((int)lane == leader) {
+						old = wh[d];
+						wh[d] = old + __popc(mm);
+					}
+					old = __shfl_sync(0xffffffffu, old, leader);
+					buf[tile_excl[d] + old + below] = key[r];
+					__syncwarp();
+				}
+				__syncthreads();
+#pragma unroll
+				for (int r = 0; r < KPT; ++r) key[r] = buf[warp * (32 * KPT) + r * 32 + lane];
+				// (the next pass synchronises before it writes to buf again)
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < KPT; ++r) {
+			const uint32_t idx = warp * (32 * KPT) + r * 32 + lane;
+			if (idx < m) gout[lo + idx] = key[r];
+		}
+	}
+}
+
+}  // namespace kmcb

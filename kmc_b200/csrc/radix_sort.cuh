@@ -33,6 +33,7 @@ struct SortPass {
 	uint64_t* desc;          // [n_tiles][256] look-back descriptors (epoch-tagged, see common.cuh)
 	uint32_t epoch;          // unique per launch
 	uint32_t* tile_counter;  // zero-initialised
+	const uint32_t* run_flag; // nullptr: always run; else run only when (*run_flag & 1): the hybrid MSD path gave up (msd_sort.cuh)
 };
 
 template <int WORDS> struct SortCfg;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 	uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + S::oMbar);
 	volatile uint32_t* s_tile = reinterpret_cast<volatile uint32_t*>(smem + S::oTileId);
 
+	if (p.run_flag && !(*p.run_flag & 1u)) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const R* __restrict__ gin = reinterpret_cast<const R*>(p.in);
 	R* __restrict__ gout = reinterpret_cast<R*>(p.out);

@@ -25,5 +25,5 @@ for it in range(5):
     ps = t["pass_ms"]
     print("it%d total %.3f ms (%.2f G k-mers/s) expand %.3f sort %.3f count %.3f | pass avg %.3f ms = %.0f GB/s | %s" % (
         it, tot, n_rec / tot / 1e6, t["expand_ms"], t["sort_ms"], t["count_ms"], sum(ps) / len(ps), 2 * n_rec * W / (sum(ps) / len(ps)) / 1e6,
-        " ".join("%.3f" % x for x in ps)))
+        " ".join("%s=%.3f" % (nm, x) for nm, x in zip(t["pass_names"], ps))))
 print("result", d_res.cpu().numpy())

@@ -62,8 +62,11 @@ def test_expand_matches_oracle(oracle):
         ctx.close()
 
 
-@pytest.mark.parametrize("words,key_bytes,n", [(1, 8, 100000), (1, 8, 4096), (1, 8, 4097), (1, 5, 33333), (1, 1, 1000), (2, 14, 50001), (2, 16, 2048), (3, 20, 30000), (4, 32, 20000), (1, 8, 1), (1, 8, 3)])
-def test_sort_records_matches_oracle(oracle, words, key_bytes, n):
+@pytest.mark.parametrize("mode", ["hybrid", "lsd"])
+@pytest.mark.parametrize("words,key_bytes,n", [(1, 8, 100000), (1, 8, 4096), (1, 8, 4097), (1, 5, 33333), (1, 1, 1000), (2, 14, 50001), (2, 16, 2048), (3, 20, 30000), (4, 32, 20000), (1, 8, 1), (1, 8, 3),
+                                               (1, 8, 700001), (2, 14, 300000), (3, 23, 150000), (4, 32, 120000)])
+def test_sort_records_matches_oracle(oracle, monkeypatch, mode, words, key_bytes, n):
+    monkeypatch.setenv("KMCB200_SORT", "lsd" if mode == "lsd" else "msd")
     rng = np.random.default_rng(n + words)
     recs = rng.integers(0, 1 << 63, size=(n, words), dtype=np.uint64)
     # duplicate-rich + masked to the key bytes (bytes above key_bytes are zero in KMC records)
@@ -228,3 +231,23 @@ def test_dropin_inside_reference_pipeline(oracle):
         for b, g, c in zip(bins, got, cpu):
             assert g.same_as(c)
             assert g.same_as(oracle.process_bin(b, p))
+
+
+@pytest.mark.parametrize("kind", ["one_leaf", "heavy_key", "two_level_skew"])
+def test_skewed_keys_fall_back_to_lsd(oracle, kind):
+    """Leaves that do not fit on chip raise the device flag; the LSD passes queued behind the hybrid path then sort the bin."""
+    rng = np.random.default_rng(9)
+    n = 300000
+    if kind == "one_leaf":            # all keys share their top 16 bits
+        recs = (rng.integers(0, 1 << 40, n, dtype=np.uint64) | (np.uint64(0x2A5B) << np.uint64(46))).reshape(-1, 1)
+    elif kind == "heavy_key":         # one key holds a third of the bin, the rest is uniform
+        recs = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+        recs[: n // 3] = recs[0]
+        recs = rng.permutation(recs).reshape(-1, 1)
+    else:                             # uniform first digit, second digit constant
+        recs = (rng.integers(0, 1 << 62, n, dtype=np.uint64) & ~(np.uint64(0xFF) << np.uint64(46))).reshape(-1, 1)
+    p = Params(k=31, lut_prefix_len=7)
+    ctx = _ctx(p)
+    got = ctx.sort_records(recs, 8)
+    assert np.array_equal(got, oracle.sort(recs, 8))
+    ctx.close()
