@@ -48,7 +48,10 @@ struct ExpandArgs {
 	// output
 	void* recs;
 	uint64_t* hist0;             // [256] histogram of record byte 0 (zero-initialised): first digit of the LSD passes
-	uint32_t* hist_top;          // [256] histogram of bits [top_shift, top_shift + 8): first digit of the MSD partition
+	// level-1 work items of the MSD partition = the output tiles of this kernel (msd_sort.cuh)
+	uint16_t* cells1;            // [256][total_tiles] counts of bits [top_shift, top_shift + 8) per tile
+	uint64_t* item_lo1;          // [total_tiles] first output record of the tile
+	uint16_t* item_cnt1;         // [total_tiles]
 	uint32_t top_shift;
 };
 
@@ -316,12 +319,15 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandArgs
 				atomicAdd(&htop[rec_top_digit<WORDS>(r, a.top_shift)], 1u);
 			}
 		}
+		__syncthreads();
+		// this tile is one work item of the level-1 partition: its digit counts go straight into the cell layout
+		a.cells1[(uint64_t)tid * total_tiles + g] = (uint16_t)htop[tid];
+		htop[tid] = 0;
+		if (tid == 0) { a.item_lo1[g] = obase; a.item_cnt1[g] = (uint16_t)cnt; }
 	}
 	__syncthreads();
 	const uint32_t c = hist[tid];
 	if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.hist0) + tid, (unsigned long long)c);
-	const uint32_t ct = htop[tid];
-	if (ct) atomicAdd(a.hist_top + tid, ct);
 }
 
 }  // namespace kmcb

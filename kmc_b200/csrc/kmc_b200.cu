@@ -36,8 +36,6 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint32_t msd_flags[4];                        // [0] kMsdFlagFallback (leaves too large -> LSD passes), [1] always 0
 	uint32_t msd_n_items[2];                      // work items of the level-1 / level-2 segmentation
 	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves
-	uint32_t hist_top[256];                       // histogram of the level-1 digit (counted by expand_kernel)
-	uint32_t msd_hist2[65536];                    // histogram of the level-2 digit inside every level-1 bucket
 };
 
 struct Slot {
@@ -63,7 +61,13 @@ struct Slot {
 	uint32_t* msd_item_base1 = nullptr;                     // [2]
 	uint32_t* msd_item_base2 = nullptr;                     // [257]
 	uint32_t* msd_item_seg2 = nullptr; size_t msd_item_seg2_cap = 0;
+	uint64_t* msd_item_lo1 = nullptr; size_t msd_item_lo1_cap = 0;      // level-1 items = expand tiles
+	uint16_t* msd_item_cnt1 = nullptr; size_t msd_item_cnt1_cap = 0;
+	uint16_t* msd_cells = nullptr; size_t msd_cells_cap = 0;            // counts[segment][digit][item] (level 1, then reused by level 2)
+	uint32_t* msd_cell_scan = nullptr; size_t msd_cell_scan_cap = 0;    // their exclusive scan
+	uint32_t* msd_block_sums = nullptr; size_t msd_block_sums_cap = 0;
 	const char* pass_names[kMaxPasses + 8] = {};
+	uint32_t last_n_packs = 1;
 	uint64_t* cdesc = nullptr; size_t cdesc_cap = 0;        // count look-back descriptors
 	// outputs of the host-buffer path
 	uint8_t* d_out = nullptr; size_t out_cap = 0;
@@ -188,49 +192,63 @@ __global__ void msd_setup_kernel(uint64_t* seg1, uint32_t* item_base1, uint32_t*
 	*n_items1 = nt;
 }
 
+// upper bound of the level-1 work items of a bin
+size_t msd_max_items1(uint64_t n_rec, uint32_t n_packs) { return (size_t)(n_rec / kExpandTile) + n_packs + 2; }
+
 template <int WORDS>
-__global__ void __launch_bounds__(512) bits_histogram_kernel(const void* in, uint64_t n, uint32_t shift, uint32_t* hist)
+int ensure_msd(kmcb200_ctx* ctx, Slot& s, uint64_t n, uint32_t n_packs)
 {
-	__shared__ uint32_t sh[256];
-	const Rec<WORDS>* __restrict__ g = reinterpret_cast<const Rec<WORDS>*>(in);
-	if (threadIdx.x < 256) sh[threadIdx.x] = 0;
-	__syncthreads();
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&sh[rec_bits<WORDS>(g[i], shift, 0xFFu)], 1u);
-	__syncthreads();
-	if (threadIdx.x < 256 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+	const size_t items1 = std::max(msd_max_items1(n, n_packs), (size_t)(n / msd_tile<WORDS>()) + 2);
+	const size_t items2 = (size_t)(n / msd_tile<WORDS>()) + 260;
+	const size_t cells = 256 * std::max(items1, items2);
+	if (int rc = ensure(ctx, s.msd_item_lo1, s.msd_item_lo1_cap, items1)) return rc;
+	if (int rc = ensure(ctx, s.msd_item_cnt1, s.msd_item_cnt1_cap, items1)) return rc;
+	if (int rc = ensure(ctx, s.msd_item_seg2, s.msd_item_seg2_cap, std::max(items1, items2))) return rc;
+	if (int rc = ensure(ctx, s.msd_cells, s.msd_cells_cap, cells)) return rc;
+	if (int rc = ensure(ctx, s.msd_cell_scan, s.msd_cell_scan_cap, cells)) return rc;
+	if (int rc = ensure(ctx, s.msd_block_sums, s.msd_block_sums_cap, cells / kCellChunk + 2)) return rc;
+	return 0;
+}
+
+int launch_cell_scan(kmcb200_ctx* ctx, Slot& s, const uint32_t* n_items, uint32_t nd, size_t max_items, const uint32_t* flags, cudaStream_t st)
+{
+	const uint32_t nb = (uint32_t)(((size_t)nd * max_items + kCellChunk - 1) / kCellChunk);
+	cell_reduce_kernel<<<nb, 256, 0, st>>>(s.msd_cells, n_items, nd, s.msd_block_sums, flags);
+	cell_scan_sums_kernel<<<1, 1024, 0, st>>>(s.msd_block_sums, n_items, nd, flags);
+	cell_scan_kernel<<<nb, 256, 0, st>>>(s.msd_cells, n_items, nd, s.msd_block_sums, s.msd_cell_scan, flags);
+	ctx->launches += 3;
+	CU(cudaGetLastError());
+	return 0;
 }
 
 // Sorts n records from `a` (with `b` as the second buffer).  *result_in_b tells where the sorted records end up.
-// hist_ready: expand_kernel has zeroed the slot's ZeroBlock and counted hist[0] (LSD digit 0) and hist_top (MSD digit 1).
+// hist_ready: expand_kernel has zeroed the slot's ZeroBlock, counted hist[0] (LSD digit 0) and written the level-1 cells / items.
 template <int WORDS>
-int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, bool hist_ready, cudaStream_t st, bool* result_in_b)
+int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, bool hist_ready, uint32_t n_packs, cudaStream_t st, bool* result_in_b)
 {
 	constexpr int TILE = SortSmem<WORDS>::kTile;
 	constexpr int MTILE = msd_tile<WORDS>();
 	const uint64_t n_tiles64 = (n + TILE - 1) / TILE;
-	if (n_tiles64 > 0x7fffffffull) return fail(ctx, KMCB200_ERR_INVALID, "bin too large: %llu records", (unsigned long long)n);
+	if (n_tiles64 > 0x7fffffffull || n >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin too large: %llu records", (unsigned long long)n);
 	const uint32_t n_tiles = (uint32_t)n_tiles64;
 	const uint32_t key_bits = std::min(2u * ctx->prm.kmer_len, key_bytes * 8u);
 	const bool msd = ctx->use_msd && key_bits >= 24 && n >= (1u << 16) && key_bytes == ctx->key_bytes;
 	const uint32_t top_shift = key_bits - 8;
-	const size_t max_items = (size_t)(n / MTILE) + 260;
-	if (int rc = ensure(ctx, s.desc, s.desc_cap, std::max((size_t)n_tiles, max_items) * 256, true)) return rc;
-	if (msd) if (int rc = ensure(ctx, s.msd_item_seg2, s.msd_item_seg2_cap, max_items)) return rc;
+	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
+	if (msd) if (int rc = ensure_msd<WORDS>(ctx, s, n, n_packs)) return rc;
 
 	if (!hist_ready) {
 		CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
 		const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 511) / 512, (uint64_t)ctx->sm_count * 4);
 		digit_histogram_kernel<WORDS><<<grid, 512, 0, st>>>(a, n, 0, s.zero->hist[0]);
 		ctx->launches++;
-		if (msd) { bits_histogram_kernel<WORDS><<<grid, 512, 0, st>>>(a, n, top_shift, s.zero->hist_top); ctx->launches++; }
 	}
 	int iv = 0;      // timed interval index
 	CU(cudaEventRecord(s.ev_pass[0], st));
 	void* lsd_in = a; void* lsd_out = b;
 	const uint32_t* lsd_flag = nullptr;
 	if (msd) {
-		// leaves of ~1-2 K records: b2 = bits of the second partition level
+		// leaves of ~1 K records: b2 = bits of the second partition level
 		uint32_t lg = 0;
 		while ((1ull << lg) < (n + 1023) / 1024) ++lg;
 		const uint32_t b2 = lg > 8 ? std::min(lg - 8, 8u) : 0;
@@ -239,35 +257,54 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		const bool final_in_b = (key_bytes % 2) == 0;                 // where the LSD passes (started from b) end; the leaves go to the same place
 		void* fin = final_in_b ? b : a;
 		uint32_t* flags = s.zero->msd_flags;
-		const uint32_t pgrid = (uint32_t)std::min<size_t>(max_items, (size_t)ctx->sm_count * ctx->occ_msd_part);
+		const uint32_t* never = &flags[1];                             // level 1 always runs: the LSD passes start from its output
+		const size_t max_items1 = hist_ready ? msd_max_items1(n, n_packs) : (size_t)(n / MTILE) + 2;
+		const size_t max_items2 = (size_t)(n / MTILE) + 260;
+		const uint32_t pgrid1 = (uint32_t)std::min<size_t>(max_items1, (size_t)ctx->sm_count * ctx->occ_msd_part);
+		const uint32_t pgrid2 = (uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * ctx->occ_msd_part);
 		const int local_smem = msd_local_cap<WORDS>() * 8 * WORDS + (MsdLocalCfg<WORDS>::kThreads / 32) * 1024;
 
-		msd_setup_kernel<<<1, 1, 0, st>>>(s.msd_seg1, s.msd_item_base1, &s.zero->msd_n_items[0], n, MTILE);
-		MsdScanArgs sc1{};
-		sc1.counts32 = s.zero->hist_top; sc1.M = 256; sc1.start = s.msd_start2; sc1.cap = b2 == 0 ? cap : 0; sc1.flags = flags;
-		sc1.tile = MTILE; sc1.item_base = s.msd_item_base2; sc1.item_seg = s.msd_item_seg2; sc1.n_items = &s.zero->msd_n_items[1];
-		msd_scan_kernel<<<1, 1024, 0, st>>>(sc1);
+		MsdItems items1{};
+		if (hist_ready) {          // items and cells were written by expand_kernel
+			items1.item_lo = s.msd_item_lo1; items1.item_cnt = s.msd_item_cnt1; items1.n_items = &s.zero->status[1];
+		} else {
+			msd_setup_kernel<<<1, 1, 0, st>>>(s.msd_seg1, s.msd_item_base1, &s.zero->msd_n_items[0], n, MTILE);
+			items1.seg_start = s.msd_seg1; items1.item_base = s.msd_item_base1; items1.item_seg = s.msd_item_seg2 /* all zero: see below */;
+			items1.n_items = &s.zero->msd_n_items[0];
+			CU(cudaMemsetAsync(s.msd_item_seg2, 0, max_items1 * sizeof(uint32_t), st));      // single segment: every item belongs to segment 0
+			MsdCountArgs c1{a, items1, top_shift, 256, s.msd_cells, never};
+			msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items1, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c1);
+			ctx->launches += 2;
+		}
+		if (int rc = launch_cell_scan(ctx, s, items1.n_items, 256, max_items1, never, st)) return rc;
+		MsdBoundsArgs b1{};
+		b1.cell_scan = s.msd_cell_scan; b1.items = items1; b1.S = 1; b1.nd = 256; b1.n = n; b1.start = s.msd_start2;
+		b1.cap = b2 == 0 ? cap : 0; b1.flags = flags;
+		b1.tile = b2 > 0 ? MTILE : 0; b1.item_base = s.msd_item_base2; b1.item_seg = s.msd_item_seg2; b1.n_items = &s.zero->msd_n_items[1];
 		MsdPartArgs p1{};
-		p1.in = a; p1.out = b;
-		p1.items = MsdItems{s.msd_seg1, s.msd_item_base1, nullptr, &s.zero->msd_n_items[0], 1};
-		p1.out_start = s.msd_start2; p1.shift = top_shift; p1.nd = 256; p1.desc = s.desc; p1.epoch = next_epoch(ctx);
-		p1.tile_counter = &s.zero->msd_counters[0]; p1.flags = &flags[1];          // level 1 always runs: the LSD passes start from its output
-		msd_partition_kernel<WORDS><<<pgrid, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p1);
-		ctx->launches += 3;
+		p1.in = a; p1.out = b; p1.items = items1; p1.cell_scan = s.msd_cell_scan; p1.shift = top_shift; p1.nd = 256;
+		p1.tile_counter = &s.zero->msd_counters[0]; p1.flags = never;
+		// (the item_seg table of the level-2 items shares its buffer with the all-zero level-1 table: partition first, bounds after)
+		msd_partition_kernel<WORDS><<<pgrid1, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p1);
+		msd_bounds_kernel<<<1, 1024, 0, st>>>(b1);
+		ctx->launches += 2;
 		s.pass_names[iv] = "msd_partition_L1"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		if (b2 > 0) {
-			const MsdItems items2{s.msd_start2, s.msd_item_base2, s.msd_item_seg2, &s.zero->msd_n_items[1], 256};
-			MsdCountArgs c2{b, items2, top_shift - b2, nd2, s.zero->msd_hist2, flags};
-			msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
-			MsdScanArgs sc2{};
-			sc2.counts32 = s.zero->msd_hist2; sc2.M = 256 * nd2; sc2.start = s.msd_start3; sc2.cap = cap; sc2.flags = flags; sc2.tile = 0;
-			msd_scan_kernel<<<1, 1024, 0, st>>>(sc2);
-			ctx->launches += 2;
+			MsdItems items2{};
+			items2.seg_start = s.msd_start2; items2.item_base = s.msd_item_base2; items2.item_seg = s.msd_item_seg2; items2.n_items = &s.zero->msd_n_items[1];
+			MsdCountArgs c2{b, items2, top_shift - b2, nd2, s.msd_cells, flags};
+			msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
+			ctx->launches++;
+			if (int rc = launch_cell_scan(ctx, s, items2.n_items, nd2, max_items2, flags, st)) return rc;
+			MsdBoundsArgs bb{};
+			bb.cell_scan = s.msd_cell_scan; bb.items = items2; bb.S = 256; bb.nd = nd2; bb.n = n; bb.start = s.msd_start3; bb.cap = cap; bb.flags = flags; bb.tile = 0;
+			msd_bounds_kernel<<<1, 1024, 0, st>>>(bb);
+			ctx->launches++;
 			s.pass_names[iv] = "msd_count_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 			MsdPartArgs p2{};
-			p2.in = b; p2.out = a; p2.items = items2; p2.out_start = s.msd_start3; p2.shift = top_shift - b2; p2.nd = nd2;
-			p2.desc = s.desc; p2.epoch = next_epoch(ctx); p2.tile_counter = &s.zero->msd_counters[1]; p2.flags = flags;
-			msd_partition_kernel<WORDS><<<pgrid, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p2);
+			p2.in = b; p2.out = a; p2.items = items2; p2.cell_scan = s.msd_cell_scan; p2.shift = top_shift - b2; p2.nd = nd2;
+			p2.tile_counter = &s.zero->msd_counters[1]; p2.flags = flags;
+			msd_partition_kernel<WORDS><<<pgrid2, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p2);
 			ctx->launches++;
 			s.pass_names[iv] = "msd_partition_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		}
@@ -393,8 +430,10 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
 	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.status = s.zero->status;
 	a.recs = d_recs; a.hist0 = s.zero->hist[0];
-	a.hist_top = s.zero->hist_top;
+	if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np)) return rc;
+	a.cells1 = s.msd_cells; a.item_lo1 = s.msd_item_lo1; a.item_cnt1 = s.msd_item_cnt1;
 	a.top_shift = std::max(2u * k, 8u) - 8u;
+	s.last_n_packs = np;
 
 	CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
 	walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a);
@@ -440,7 +479,7 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	CU(cudaEventRecord(s.ev_expand, st));
 	s.ran_expand = true;
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, true, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, true, (n_packs && pack_bytes) ? n_packs : 1u, st, &in_b)) return rc;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true;
 	const void* sorted = in_b ? s.recs_b : s.recs_a;
@@ -520,7 +559,8 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
 				 (void*)s.pack_kbase, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
-				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2})
+				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
+				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums})
 			if (p) cudaFree(p);
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
@@ -635,7 +675,7 @@ int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, ui
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n * rec_bytes)) return rc;
 	CU(cudaMemcpyAsync(s.recs_a, recs, n * rec_bytes, cudaMemcpyHostToDevice, st));
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, false, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, false, 0u, st, &in_b)) return rc;
 	CU(cudaMemcpyAsync(where ? tmp : recs, in_b ? s.recs_b : s.recs_a, n * rec_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	return where;
@@ -682,7 +722,7 @@ int kmcb200_dev_sort(kmcb200_ctx* ctx, uint32_t slot, void* d_recs, void* d_tmp,
 	if (n == 0) return where;
 	if (!hist_ready) CU(cudaEventRecord(s.ev_expand, st));
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready != 0, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready != 0, s.last_n_packs, st, &in_b)) return rc;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true; s.ran_count = false;
 	if (!hist_ready) s.ran_expand = false;

@@ -6,14 +6,14 @@
 // rank of a record inside its tile is simply the value returned by ONE shared-memory atomicAdd - no match.any,
 // no warp-private histograms, no serial cursor chain.
 //
-//   level 1   msd_partition_kernel   whole bin   -> 2^8 buckets          (digit histogram counted by expand_kernel)
-//   count     msd_count_kernel       per level-1 bucket: histogram of the next digit
-//   scan      msd_scan_kernel        bucket boundaries of the next level (+ work-item table, + oversize check)
-//   level 2   msd_partition_kernel   every level-1 bucket -> 2^b2 sub-buckets (b2 <= 8, chosen so that a leaf has ~1-2 K records)
+//   level 1   msd_partition_kernel   whole bin   -> 2^8 buckets          (per-tile digit counts written by expand_kernel)
+//   count     msd_count_kernel       per tile of every level-1 bucket: counts of the next digit
+//   scan      cell_*_kernel, msd_bounds_kernel   flat scan of the counts = output offsets + bucket boundaries (+ oversize check)
+//   level 2   msd_partition_kernel   every level-1 bucket -> 2^b2 sub-buckets (b2 <= 8, chosen so that a leaf has ~1 K records)
 //   leaves    msd_local_sort_kernel  one leaf bucket per CTA iteration: load to shared memory, LSD radix sort of the
 //                                    remaining bits entirely on chip, write back
 //
-// Traffic: 2NW (level 1) + NW (count) + 2NW (level 2) + 2NW (leaves) = 7 N*W instead of 16 N*W for 8 LSD passes.
+// Traffic: 2NW (level 1) + NW (count) + 2NW (level 2) + 2NW (leaves) = 7 N*W instead of 16 N*W for 8 LSD passes; no look-back anywhere.
 // A leaf that does not fit in shared memory (heavy skew) makes the scan raise a device flag; every kernel of this file then
 // returns at once and the 8-bit LSD passes of radix_sort.cuh (always enqueued behind, normally returning at once) sort the bin.
 #pragma once
@@ -49,25 +49,64 @@ template <> struct MsdCfg<4> { static constexpr int kThreads = 512, kKpt = 2, kM
 
 template <int WORDS> __host__ __device__ constexpr int msd_tile() { return MsdCfg<WORDS>::kThreads * MsdCfg<WORDS>::kKpt; }
 
-// Work items of a segmented pass: item i = (segment s, aligned tile T).  Tiles live on the absolute grid [T*TILE, (T+1)*TILE)
-// so that TMA sources are 16-byte aligned whatever the segment boundaries are; an item covers the part of its tile that belongs
-// to its segment.  Items of one segment are consecutive, which is what the look-back chain needs.
+// A partition pass is "count, scan, scatter", with the counting fused into whoever touched the records last:
+//   * work items: contiguous record ranges of at most msd_tile() records that never straddle a segment.  Level 1: the output
+//     tiles of expand_kernel (explicit ranges); level 2: the aligned tiles of every level-1 bucket (tables built on the device);
+//   * cells: counts[segment][digit][item of the segment] (u16) - the ORDER OF THE OUTPUT.  One flat exclusive scan over the
+//     cells therefore yields, for every (item, digit), the global index where that item's records of that digit go, and for
+//     every (segment, digit) the boundary of the next level's bucket;
+//   * the scatter kernel needs no look-back, no descriptors and no spinning: rank = return value of a shared-memory
+//     atomicAdd, base = one precomputed cell.
 struct MsdItems {
-	const uint64_t* seg_start;   // [S + 1] record index where every segment starts
+	// explicit ranges (level 1) ...
+	const uint64_t* item_lo;     // [n_items] or nullptr
+	const uint16_t* item_cnt;
+	// ... or aligned tiles inside segments (level 2)
+	const uint64_t* seg_start;   // [S + 1]
 	const uint32_t* item_base;   // [S + 1] first item of every segment
 	const uint32_t* item_seg;    // [n_items]
 	const uint32_t* n_items;     // device scalar
-	uint32_t S;
 };
+
+struct MsdItemGeom {
+	uint64_t lo, hi;      // records [lo, hi)
+	uint64_t lo_al;       // first record of the 16-byte aligned load
+	uint32_t n_load;
+	uint64_t cell0;       // cell of (this item, digit 0); digit d is at cell0 + d * cell_stride
+	uint32_t cell_stride; // items of the segment
+};
+
+template <int WORDS>
+__device__ __forceinline__ MsdItemGeom msd_item_geom(const MsdItems& it, uint32_t item, uint32_t nd)
+{
+	constexpr uint64_t TILE = msd_tile<WORDS>();
+	MsdItemGeom g;
+	if (it.item_lo) {
+		g.lo = it.item_lo[item];
+		g.hi = g.lo + it.item_cnt[item];
+		g.cell_stride = *it.n_items;
+		g.cell0 = item;
+	} else {
+		const uint32_t seg = it.item_seg[item];
+		const uint64_t sb = it.seg_start[seg], se = it.seg_start[seg + 1];
+		const uint32_t first_item = it.item_base[seg];
+		const uint64_t T = sb / TILE + (item - first_item);
+		g.lo = T * TILE > sb ? T * TILE : sb;
+		g.hi = (T + 1) * TILE < se ? (T + 1) * TILE : se;
+		g.cell_stride = it.item_base[seg + 1] - first_item;
+		g.cell0 = (uint64_t)nd * first_item + (item - first_item);
+	}
+	g.lo_al = g.lo & ~1ull;
+	g.n_load = (uint32_t)(((g.hi + 1) & ~1ull) - g.lo_al);
+	return g;
+}
 
 struct MsdPartArgs {
 	const void* in;
 	void* out;
 	MsdItems items;
-	const uint64_t* out_start;   // [S * nd + 1] where (segment s, digit d) starts in the output = boundaries of the next level
+	const uint32_t* cell_scan;   // exclusive scan of the cells = global output index of (item, digit)
 	uint32_t shift, nd;          // digit = bits [shift, shift + log2(nd)), nd <= 256
-	uint64_t* desc;              // [n_items][256] look-back descriptors
-	uint32_t epoch;
 	uint32_t* tile_counter;
 	const uint32_t* flags;
 };
@@ -78,43 +117,16 @@ struct MsdSmem {
 	static constexpr int kKpt = MsdCfg<WORDS>::kKpt;
 	static constexpr int kTile = kThreads * kKpt;
 	static constexpr int kRecBytes = 8 * WORDS;
-	static constexpr int kBufBytes = (kTile + 2) * kRecBytes;      // + 2: the aligned load may start one record early / end one late
+	static constexpr int kBufStride = ((kTile + 2) * kRecBytes + 127) & ~127;   // + 2: the aligned load may start one record early / end one late
 	static constexpr int oBuf = 0;
-	static constexpr int oHist = 2 * ((kBufBytes + 127) & ~127);   // u32 [256]
+	static constexpr int oHist = 2 * kBufStride;                   // u32 [256]
 	static constexpr int oExcl = oHist + 1024;                     // u32 [256]
-	static constexpr int oGoff = oExcl + 1024;                     // u64 [256]
-	static constexpr int oWarpTot = oGoff + 2048;                  // u64 [8]
+	static constexpr int oGoff = oExcl + 1024;                     // u32 [256]
+	static constexpr int oWarpTot = oGoff + 1024;                  // u64 [8]
 	static constexpr int oMbar = oWarpTot + 128;                   // u64 [2]
 	static constexpr int oItem = oMbar + 16;                       // u32 [2]
 	static constexpr int kBytes = oItem + 16;
-	static constexpr int kBufStride = (kBufBytes + 127) & ~127;
 };
-
-// geometry of a work item
-struct MsdItemGeom {
-	uint64_t lo, hi;      // records [lo, hi) of the segment that fall into the tile
-	uint64_t lo_al;       // first record of the aligned load
-	uint32_t n_load;      // records of the aligned load (even number for 8-byte records)
-	uint32_t seg;
-	bool chain_start;
-};
-template <int WORDS>
-__device__ __forceinline__ MsdItemGeom msd_item_geom(const MsdItems& it, uint32_t item)
-{
-	constexpr uint64_t TILE = msd_tile<WORDS>();
-	MsdItemGeom g;
-	g.seg = it.S == 1 ? 0u : it.item_seg[item];
-	const uint64_t sb = it.seg_start[g.seg], se = it.seg_start[g.seg + 1];
-	const uint32_t first_item = it.item_base[g.seg];
-	const uint64_t T = sb / TILE + (item - first_item);
-	g.lo = T * TILE > sb ? T * TILE : sb;
-	g.hi = (T + 1) * TILE < se ? (T + 1) * TILE : se;
-	g.lo_al = g.lo & ~1ull;
-	const uint64_t hi_al = (g.hi + 1) & ~1ull;
-	g.n_load = (uint32_t)(hi_al - g.lo_al);
-	g.chain_start = item == first_item;
-	return g;
-}
 
 template <int WORDS>
 __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads, MsdCfg<WORDS>::kMinBlocks) msd_partition_kernel(const MsdPartArgs p)
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads, MsdCfg<WORDS>::kMinBl
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint32_t* hist = reinterpret_cast<uint32_t*>(smem + S::oHist);
 	uint32_t* tile_excl = reinterpret_cast<uint32_t*>(smem + S::oExcl);
-	uint64_t* goff = reinterpret_cast<uint64_t*>(smem + S::oGoff);
+	uint32_t* goff = reinterpret_cast<uint32_t*>(smem + S::oGoff);
 	uint64_t* warp_tot = reinterpret_cast<uint64_t*>(smem + S::oWarpTot);
 	uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + S::oMbar);
 	volatile uint32_t* s_item = reinterpret_cast<volatile uint32_t*>(smem + S::oItem);
@@ -145,7 +157,7 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads, MsdCfg<WORDS>::kMinBl
 	__syncthreads();
 
 	auto issue_load = [&](uint32_t item, int b) {      // thread 0
-		const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item);
+		const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item, p.nd);
 		const uint32_t bytes = g.n_load * S::kRecBytes;
 		fence_proxy_async();
 		mbar_arrive_expect_tx(&mbar[b], bytes);
@@ -169,16 +181,19 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads, MsdCfg<WORDS>::kMinBl
 			s_item[cur ^ 1] = t;
 			if (t < n_items) issue_load(t, cur ^ 1);
 		}
-		const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item);
-		const uint32_t head = (uint32_t)(g.lo - g.lo_al);                 // records of the load that belong to the previous segment / tile
+		const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item, p.nd);
+		const uint32_t head = (uint32_t)(g.lo - g.lo_al);
 		const uint32_t valid = (uint32_t)(g.hi - g.lo);
 		R* buf = reinterpret_cast<R*>(smem + S::oBuf + cur * S::kBufStride);
+		// the global base of (item, digit d): issued now, needed after the ranking
+		uint32_t base = 0;
+		if (tid < p.nd) base = __ldg(p.cell_scan + g.cell0 + (uint64_t)tid * g.cell_stride);
 		if (tid < 256) hist[tid] = 0;
 		if (cur == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
 		else { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
 		__syncthreads();
 
-		// ---- phase 1: rank inside (tile, digit) = return value of one shared-memory atomicAdd (an MSD partition need not be stable)
+		// ---- rank inside (tile, digit) = return value of one shared-memory atomicAdd (an MSD partition need not be stable)
 		R key[KPT];
 		uint16_t rank[KPT];
 #pragma unroll
@@ -191,28 +206,23 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads, MsdCfg<WORDS>::kMinBl
 		}
 		__syncthreads();
 
-		// ---- phase 2: digit d (thread d): publish the tile aggregate, exclusive scan over the digits
-		uint32_t cnt = tid < 256 ? hist[tid] : 0;
-		if (tid < p.nd) st_relaxed(p.desc + (uint64_t)item * 256 + tid, desc_pack(g.chain_start ? kDescPrefix : kDescAggregate, p.epoch, cnt));
-		const uint64_t texcl = block_excl_scan_256(cnt, warp_tot, nullptr);
-		if (tid < 256) tile_excl[tid] = (uint32_t)texcl;
+		const uint32_t cnt = tid < 256 ? hist[tid] : 0;
+		const uint32_t texcl = (uint32_t)block_excl_scan_256(cnt, warp_tot, nullptr);
+		if (tid < 256) {
+			tile_excl[tid] = texcl;
+			goff[tid] = base - texcl;                  // global index of tile-sorted position q is goff[d] + q
+		}
 		__syncthreads();
 
-		// ---- phase 3: regroup by digit in shared memory (every record is in registers, the buffer is free)
+		// ---- regroup by digit in shared memory (every record is in registers, the buffer is free)
 #pragma unroll
 		for (int r = 0; r < KPT; ++r) {
 			const uint32_t j = r * THREADS + tid;
 			if (j < valid) buf[tile_excl[rec_bits<WORDS>(key[r], p.shift, mask)] + rank[r]] = key[r];
 		}
-
-		// ---- phase 4: chained scan over the items of this segment
-		if (tid < p.nd) {
-			const uint64_t excl = g.chain_start ? 0 : lookback_resolve(p.desc + tid, 256, item, (uint64_t)cnt, p.epoch);
-			goff[tid] = p.out_start[(uint64_t)g.seg * p.nd + tid] + excl - texcl;
-		}
 		__syncthreads();
 
-		// ---- phase 5: digit-contiguous runs leave with coalesced stores
+		// ---- digit-contiguous runs leave with coalesced stores
 #pragma unroll
 		for (int i = 0; i < KPT; ++i) {
 			const uint32_t q = i * THREADS + tid;
@@ -228,12 +238,12 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads, MsdCfg<WORDS>::kMinBl
 }
 
 // ---------------------------------------------------------------------------------------------
-// histogram of the next digit inside every segment: hist[seg * nd + digit] (u32, zero-initialised)
+// counts of the next digit per item, written straight into the cell layout (u16)
 struct MsdCountArgs {
 	const void* in;
 	MsdItems items;
 	uint32_t shift, nd;
-	uint32_t* hist;
+	uint16_t* cells;
 	const uint32_t* flags;
 };
 
@@ -246,65 +256,166 @@ __global__ void __launch_bounds__(512) msd_count_kernel(const MsdCountArgs p)
 	const R* __restrict__ g = reinterpret_cast<const R*>(p.in);
 	const uint32_t n_items = *p.items.n_items;
 	const uint32_t mask = p.nd - 1;
+	const uint32_t tid = threadIdx.x;
 	for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-		const MsdItemGeom gm = msd_item_geom<WORDS>(p.items, item);
-		if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+		const MsdItemGeom gm = msd_item_geom<WORDS>(p.items, item, p.nd);
+		if (tid < 256) sh[tid] = 0;
 		__syncthreads();
-		for (uint64_t i = gm.lo + threadIdx.x; i < gm.hi; i += blockDim.x) atomicAdd(&sh[rec_bits<WORDS>(g[i], p.shift, mask)], 1u);
+		const uint32_t m = (uint32_t)(gm.hi - gm.lo);
+		constexpr int U = (msd_tile<WORDS>() + 511) / 512;
+		R k[U];
+#pragma unroll
+		for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) k[u] = g[gm.lo + j]; }      // all loads in flight first
+#pragma unroll
+		for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) atomicAdd(&sh[rec_bits<WORDS>(k[u], p.shift, mask)], 1u); }
 		__syncthreads();
-		if (threadIdx.x < p.nd) {
-			const uint32_t c = sh[threadIdx.x];
-			if (c) atomicAdd(&p.hist[(uint64_t)gm.seg * p.nd + threadIdx.x], c);
-		}
+		if (tid < p.nd) p.cells[gm.cell0 + (uint64_t)tid * gm.cell_stride] = (uint16_t)sh[tid];
 		__syncthreads();
 	}
 }
 
 // ---------------------------------------------------------------------------------------------
-// single CTA: counts[M] -> start[M + 1] (exclusive scan, plus `base`), optional work-item table over the NEW segments,
-// optional oversize check (any count > cap raises the fallback flag)
-struct MsdScanArgs {
-	const uint32_t* counts32;    // one of the two is non-null
-	const uint64_t* counts64;
-	uint32_t M;
+// flat exclusive scan over u16 cells -> u32 (three small kernels; the number of cells lives on the device)
+constexpr int kCellChunk = 4096;     // cells per block
+
+__global__ void __launch_bounds__(256) cell_reduce_kernel(const uint16_t* cells, const uint32_t* n_items, uint32_t nd, uint32_t* block_sums, const uint32_t* flags)
+{
+	__shared__ uint32_t s_w[8];
+	if (*flags & kMsdFlagFallback) return;
+	const uint64_t n_cells = (uint64_t)nd * *n_items;
+	const uint64_t c0 = (uint64_t)blockIdx.x * kCellChunk;
+	if (c0 >= n_cells) return;
+	uint32_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < kCellChunk / 256; ++i) {
+		const uint64_t c = c0 + i * 256 + threadIdx.x;
+		if (c < n_cells) sum += cells[c];
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int w = 0; w < 8; ++w) t += s_w[w];
+		block_sums[blockIdx.x] = t;
+	}
+}
+
+__global__ void __launch_bounds__(1024) cell_scan_sums_kernel(uint32_t* block_sums, const uint32_t* n_items, uint32_t nd, const uint32_t* flags)
+{
+	__shared__ uint32_t s_w[32];
+	__shared__ uint32_t carry;
+	if (*flags & kMsdFlagFallback) return;
+	const uint64_t n_cells = (uint64_t)nd * *n_items;
+	const uint32_t nb = (uint32_t)((n_cells + kCellChunk - 1) / kCellChunk);
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	for (uint32_t b0 = 0; b0 < nb; b0 += 1024) {
+		const uint32_t b = b0 + tid;
+		const uint32_t v = b < nb ? block_sums[b] : 0;
+		uint32_t inc = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc += t;
+		}
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		uint32_t base = carry;
+		for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
+		if (b < nb) block_sums[b] = base + inc - v;
+		__syncthreads();
+		if (tid == 1023) carry = base + inc;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(256) cell_scan_kernel(const uint16_t* cells, const uint32_t* n_items, uint32_t nd, const uint32_t* block_sums, uint32_t* out, const uint32_t* flags)
+{
+	__shared__ uint32_t s_w[8];
+	if (*flags & kMsdFlagFallback) return;
+	const uint64_t n_cells = (uint64_t)nd * *n_items;
+	const uint64_t c0 = (uint64_t)blockIdx.x * kCellChunk;
+	if (c0 >= n_cells) return;
+	constexpr int PER = kCellChunk / 256;      // 16 consecutive cells per thread
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	uint32_t v[PER];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < PER; ++i) {
+		const uint64_t c = c0 + (uint64_t)tid * PER + i;
+		v[i] = c < n_cells ? cells[c] : 0;
+		sum += v[i];
+	}
+	uint32_t inc = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= (uint32_t)o) inc += t;
+	}
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads();
+	uint32_t base = block_sums[blockIdx.x] + inc - sum;
+	for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
+#pragma unroll
+	for (int i = 0; i < PER; ++i) {
+		const uint64_t c = c0 + (uint64_t)tid * PER + i;
+		if (c < n_cells) out[c] = base;
+		base += v[i];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// single CTA: boundaries of the buckets a partition level produced (= scan value of the first item's cell of every (segment, digit)),
+// optional oversize check, optional work-item table (aligned tiles) over the NEW buckets for the next level.
+struct MsdBoundsArgs {
+	const uint32_t* cell_scan;
+	MsdItems items;              // the items of the level that was just scanned
+	uint32_t S, nd;              // its segments and digits: M = S * nd new buckets
+	uint64_t n;                  // records in total
 	uint64_t* start;             // [M + 1]
 	uint32_t cap;                // 0: no check
 	uint32_t* flags;
-	uint32_t tile;               // items: tile size of the pass that will run over the new segments (0: no items)
+	uint32_t tile;               // items of the next level (0: none)
 	uint32_t* item_base;         // [M + 1]
 	uint32_t* item_seg;
 	uint32_t* n_items;
 };
 
-__global__ void __launch_bounds__(1024) msd_scan_kernel(const MsdScanArgs a)
+__global__ void __launch_bounds__(1024) msd_bounds_kernel(const MsdBoundsArgs a)
 {
-	__shared__ uint64_t s_c[32];
 	__shared__ uint32_t s_i[32];
-	__shared__ uint64_t carry_c;
 	__shared__ uint32_t carry_i;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) { carry_c = 0; carry_i = 0; }
+	if (*a.flags & kMsdFlagFallback) return;
+	const uint32_t M = a.S * a.nd;
+	// pass 1: boundaries.  Buckets of an empty segment (no items, no cells) collapse onto the segment start.
+	for (uint32_t m = tid; m <= M; m += 1024) {
+		uint64_t v = a.n;
+		if (m < M) {
+			const uint32_t seg = m / a.nd, d = m % a.nd;
+			if (a.items.item_lo) v = a.cell_scan[(uint64_t)d * *a.items.n_items];
+			else {
+				const uint32_t first = a.items.item_base[seg], nis = a.items.item_base[seg + 1] - first;
+				v = nis ? (uint64_t)a.cell_scan[(uint64_t)a.nd * first + (uint64_t)d * nis] : a.items.seg_start[seg];
+			}
+		}
+		a.start[m] = v;
+	}
+	__threadfence();
+	__syncthreads();
+	if (tid == 0) carry_i = 0;
 	__syncthreads();
 	bool over = false;
-	for (uint32_t base = 0; base < a.M; base += 1024) {
+	for (uint32_t base = 0; base < M; base += 1024) {
 		const uint32_t m = base + tid;
-		const uint64_t c = m < a.M ? (a.counts32 ? (uint64_t)a.counts32[m] : a.counts64[m]) : 0;
+		uint64_t sb = 0, c = 0;
+		if (m < M) { sb = a.start[m]; c = a.start[m + 1] - sb; }
 		if (a.cap && c > a.cap) over = true;
-		uint64_t ic = c;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint64_t t = __shfl_up_sync(0xffffffffu, ic, o);
-			if (lane >= (uint32_t)o) ic += t;
-		}
-		if (lane == 31) s_c[warp] = ic;
-		__syncthreads();
-		uint64_t bc = carry_c;
-		for (uint32_t w = 0; w < warp; ++w) bc += s_c[w];
-		const uint64_t ec = bc + ic - c;               // exclusive prefix = where segment m starts
-		if (m < a.M) a.start[m] = ec;
-		// items of segment m: aligned tiles it touches
 		uint32_t ni = 0;
-		if (a.tile && c) ni = (uint32_t)((ec + c - 1) / a.tile - ec / a.tile) + 1;
+		if (a.tile && c) ni = (uint32_t)((sb + c - 1) / a.tile - sb / a.tile) + 1;
 		uint32_t ii = ni;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -316,18 +427,15 @@ __global__ void __launch_bounds__(1024) msd_scan_kernel(const MsdScanArgs a)
 		uint32_t bi = carry_i;
 		for (uint32_t w = 0; w < warp; ++w) bi += s_i[w];
 		const uint32_t ei = bi + ii - ni;
-		if (a.tile && m < a.M) {
+		if (a.tile && m < M) {
 			a.item_base[m] = ei;
-			if (a.M > 1) for (uint32_t t = 0; t < ni; ++t) a.item_seg[ei + t] = m;      // a single segment needs no map
+			for (uint32_t t = 0; t < ni; ++t) a.item_seg[ei + t] = m;
 		}
 		__syncthreads();
-		if (tid == 1023) { carry_c = ec + c; carry_i = ei + ni; }
+		if (tid == 1023) carry_i = ei + ni;
 		__syncthreads();
 	}
-	if (tid == 0) {
-		a.start[a.M] = carry_c;
-		if (a.tile) { a.item_base[a.M] = carry_i; *a.n_items = carry_i; }
-	}
+	if (tid == 0 && a.tile) { a.item_base[M] = carry_i; *a.n_items = carry_i; }
 	if (over) atomicOr(a.flags, kMsdFlagFallback);
 }
 
