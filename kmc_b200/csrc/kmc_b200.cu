@@ -198,6 +198,7 @@ size_t msd_max_items1(uint64_t n_rec, uint32_t n_packs) { return (size_t)(n_rec 
 template <int WORDS>
 int ensure_msd(kmcb200_ctx* ctx, Slot& s, uint64_t n, uint32_t n_packs)
 {
+	static_assert(msd_tile<WORDS>() >= kExpandTile, "a partition tile must hold an expand tile");
 	const size_t items1 = std::max(msd_max_items1(n, n_packs), (size_t)(n / msd_tile<WORDS>()) + 2);
 	const size_t items2 = (size_t)(n / msd_tile<WORDS>()) + 260;
 	const size_t cells = 256 * std::max(items1, items2);
@@ -224,15 +225,15 @@ int launch_cell_scan(kmcb200_ctx* ctx, Slot& s, const uint32_t* n_items, uint32_
 // Sorts n records from `a` (with `b` as the second buffer).  *result_in_b tells where the sorted records end up.
 // hist_ready: expand_kernel has zeroed the slot's ZeroBlock, counted hist[0] (LSD digit 0) and written the level-1 cells / items.
 template <int WORDS>
-int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, bool hist_ready, uint32_t n_packs, cudaStream_t st, bool* result_in_b)
+int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, uint32_t key_bits, bool hist_ready, uint32_t n_packs, cudaStream_t st, bool* result_in_b)
 {
 	constexpr int TILE = SortSmem<WORDS>::kTile;
 	constexpr int MTILE = msd_tile<WORDS>();
 	const uint64_t n_tiles64 = (n + TILE - 1) / TILE;
 	if (n_tiles64 > 0x7fffffffull || n >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin too large: %llu records", (unsigned long long)n);
 	const uint32_t n_tiles = (uint32_t)n_tiles64;
-	const uint32_t key_bits = std::min(2u * ctx->prm.kmer_len, key_bytes * 8u);
-	const bool msd = ctx->use_msd && key_bits >= 24 && n >= (1u << 16) && key_bytes == ctx->key_bytes;
+	// key_bits: significant bits of a record.  2k for records we expanded ourselves; all key bytes for foreign records (seam #1)
+	const bool msd = ctx->use_msd && key_bits >= 24 && n >= (1u << 16);
 	const uint32_t top_shift = key_bits - 8;
 	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
 	if (msd) if (int rc = ensure_msd<WORDS>(ctx, s, n, n_packs)) return rc;
@@ -479,7 +480,7 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	CU(cudaEventRecord(s.ev_expand, st));
 	s.ran_expand = true;
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, true, (n_packs && pack_bytes) ? n_packs : 1u, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, (n_packs && pack_bytes) ? n_packs : 1u, st, &in_b)) return rc;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true;
 	const void* sorted = in_b ? s.recs_b : s.recs_a;
@@ -675,7 +676,7 @@ int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, ui
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n * rec_bytes)) return rc;
 	CU(cudaMemcpyAsync(s.recs_a, recs, n * rec_bytes, cudaMemcpyHostToDevice, st));
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, false, 0u, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, 8u * key_bytes, false, 0u, st, &in_b)) return rc;
 	CU(cudaMemcpyAsync(where ? tmp : recs, in_b ? s.recs_b : s.recs_a, n * rec_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	return where;
@@ -722,7 +723,7 @@ int kmcb200_dev_sort(kmcb200_ctx* ctx, uint32_t slot, void* d_recs, void* d_tmp,
 	if (n == 0) return where;
 	if (!hist_ready) CU(cudaEventRecord(s.ev_expand, st));
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready != 0, s.last_n_packs, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready ? 2u * ctx->prm.kmer_len : 8u * key_bytes, hist_ready != 0, s.last_n_packs, st, &in_b)) return rc;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true; s.ran_count = false;
 	if (!hist_ready) s.ran_expand = false;

@@ -44,8 +44,9 @@ __device__ __forceinline__ uint32_t rec_bits(const Rec<WORDS>& r, uint32_t shift
 template <int WORDS> struct MsdCfg;
 template <> struct MsdCfg<1> { static constexpr int kThreads = 512, kKpt = 8, kMinBlocks = 2; };
 template <> struct MsdCfg<2> { static constexpr int kThreads = 512, kKpt = 4, kMinBlocks = 2; };
-template <> struct MsdCfg<3> { static constexpr int kThreads = 512, kKpt = 3, kMinBlocks = 2; };
-template <> struct MsdCfg<4> { static constexpr int kThreads = 512, kKpt = 2, kMinBlocks = 2; };
+template <> struct MsdCfg<3> { static constexpr int kThreads = 512, kKpt = 4, kMinBlocks = 1; };     // a tile must hold an expand tile (2048 records)
+template <> struct MsdCfg<4> { static constexpr int kThreads = 512, kKpt = 4, kMinBlocks = 1; };
+static_assert(true, "");
 
 template <int WORDS> __host__ __device__ constexpr int msd_tile() { return MsdCfg<WORDS>::kThreads * MsdCfg<WORDS>::kKpt; }
 
