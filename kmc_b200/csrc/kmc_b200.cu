@@ -7,6 +7,7 @@
 #include "radix_sort.cuh"
 #include "count.cuh"
 #include "msd_sort.cuh"
+#include "leaf_count.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -35,7 +36,7 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint32_t status[2];                           // expand: [0] error bits, [1] total tiles
 	uint32_t msd_flags[4];                        // [0] kMsdFlagFallback (leaves too large -> LSD passes), [1] always 0
 	uint32_t msd_n_items[2];                      // work items of the level-1 / level-2 segmentation
-	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves
+	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves, leaf-count
 };
 
 struct Slot {
@@ -66,6 +67,9 @@ struct Slot {
 	uint16_t* msd_cells = nullptr; size_t msd_cells_cap = 0;            // counts[segment][digit][item] (level 1, then reused by level 2)
 	uint32_t* msd_cell_scan = nullptr; size_t msd_cell_scan_cap = 0;    // their exclusive scan
 	uint32_t* msd_block_sums = nullptr; size_t msd_block_sums_cap = 0;
+	// leaf-count path
+	uint8_t* leaf_tmp = nullptr; size_t leaf_tmp_cap = 0;
+	uint32_t* leaf_emit = nullptr; uint64_t* leaf_off = nullptr;          // [65536]
 	const char* pass_names[kMaxPasses + 8] = {};
 	uint32_t last_n_packs = 1;
 	uint64_t* cdesc = nullptr; size_t cdesc_cap = 0;        // count look-back descriptors
@@ -94,6 +98,8 @@ struct kmcb200_ctx {
 	int sm_count = 0;
 	int occ_radix = 1, occ_expand = 1, occ_msd_part = 1, occ_msd_local = 1;
 	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
+	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
+	int occ_leaf = 1;
 	uint32_t epoch = 1;
 	uint64_t launches = 0;
 	// All kernels of a context run on ONE stream: the persistent radix passes size their grids to fill the GPU and two of
@@ -222,10 +228,44 @@ int launch_cell_scan(kmcb200_ctx* ctx, Slot& s, const uint32_t* n_items, uint32_
 	return 0;
 }
 
+// key_bytes 8-bit LSD passes from `in` (ping-pong with `out`); run_flag != nullptr: every pass returns at once unless the flag is raised
+template <int WORDS>
+int launch_lsd_passes(kmcb200_ctx* ctx, Slot& s, void* in, void* out, uint64_t n, uint32_t key_bytes, const uint32_t* run_flag, bool timed, int& iv, cudaStream_t st)
+{
+	constexpr int TILE = SortSmem<WORDS>::kTile;
+	const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
+	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix));
+	for (uint32_t pass = 0; pass < key_bytes; ++pass) {
+		SortPass p;
+		p.in = in; p.out = out; p.n = n; p.n_tiles = n_tiles; p.byte = pass;
+		p.next_byte = pass + 1 < key_bytes ? (int32_t)(pass + 1) : -1;
+		p.hist = s.zero->hist[pass];
+		p.hist_next = s.zero->hist[pass + 1];
+		p.desc = s.desc;
+		p.epoch = next_epoch(ctx);
+		p.tile_counter = &s.zero->counters[pass];
+		p.run_flag = run_flag;
+		radix_pass_kernel<WORDS><<<grid, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes, st>>>(p);
+		ctx->launches++;
+		if (timed) { s.pass_names[iv] = "radix_pass"; CU(cudaEventRecord(s.ev_pass[++iv], st)); }
+		std::swap(in, out);
+	}
+	CU(cudaGetLastError());
+	return 0;
+}
+
+// Filled by launch_sort when the caller wants to count the leaves itself (leaf_count.cuh) instead of sorting them.
+struct LeafPlan {
+	bool active = false;
+	const void* recs = nullptr;      // partitioned records
+	const uint64_t* start = nullptr; // leaf boundaries
+	uint32_t n_leaves = 0, low_bits = 0;
+};
+
 // Sorts n records from `a` (with `b` as the second buffer).  *result_in_b tells where the sorted records end up.
 // hist_ready: expand_kernel has zeroed the slot's ZeroBlock, counted hist[0] (LSD digit 0) and written the level-1 cells / items.
 template <int WORDS>
-int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, uint32_t key_bits, bool hist_ready, uint32_t n_packs, cudaStream_t st, bool* result_in_b)
+int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, uint32_t key_bits, bool hist_ready, uint32_t n_packs, cudaStream_t st, bool* result_in_b, LeafPlan* plan = nullptr)
 {
 	constexpr int TILE = SortSmem<WORDS>::kTile;
 	constexpr int MTILE = msd_tile<WORDS>();
@@ -254,7 +294,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		while ((1ull << lg) < (n + 1023) / 1024) ++lg;
 		const uint32_t b2 = lg > 8 ? std::min(lg - 8, 8u) : 0;
 		const uint32_t nd2 = 1u << b2;
-		const uint32_t cap = (uint32_t)msd_local_cap<WORDS>();
+		const uint32_t cap = (plan && WORDS == 1) ? 0u : (uint32_t)msd_local_cap<WORDS>();      // counted leaves are streamed: no size limit
 		const bool final_in_b = (key_bytes % 2) == 0;                 // where the LSD passes (started from b) end; the leaves go to the same place
 		void* fin = final_in_b ? b : a;
 		uint32_t* flags = s.zero->msd_flags;
@@ -309,35 +349,30 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			ctx->launches++;
 			s.pass_names[iv] = "msd_partition_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		}
-		MsdLocalArgs lo{};
-		lo.in = b2 > 0 ? a : b; lo.out = fin; lo.start = b2 > 0 ? s.msd_start3 : s.msd_start2; lo.n_buckets = 256 * nd2;
-		lo.low_bits = top_shift - b2; lo.bucket_counter = &s.zero->msd_counters[2]; lo.flags = flags;
-		const uint32_t lgrid = (uint32_t)std::min<size_t>(lo.n_buckets, (size_t)ctx->sm_count * ctx->occ_msd_local);
-		msd_local_sort_kernel<WORDS><<<lgrid, MsdLocalCfg<WORDS>::kThreads, local_smem, st>>>(lo);
-		ctx->launches++;
-		s.pass_names[iv] = "msd_local_sort"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+		if (plan && WORDS == 1) {          // the caller counts the leaves (no sort of the duplicates)
+			plan->active = true;
+			plan->recs = b2 > 0 ? a : b; plan->start = b2 > 0 ? s.msd_start3 : s.msd_start2; plan->n_leaves = 256 * nd2; plan->low_bits = top_shift - b2;
+		} else {
+			MsdLocalArgs lo{};
+			lo.in = b2 > 0 ? a : b; lo.out = fin; lo.start = b2 > 0 ? s.msd_start3 : s.msd_start2; lo.n_buckets = 256 * nd2;
+			lo.low_bits = top_shift - b2; lo.bucket_counter = &s.zero->msd_counters[2]; lo.flags = flags;
+			const uint32_t lgrid = (uint32_t)std::min<size_t>(lo.n_buckets, (size_t)ctx->sm_count * ctx->occ_msd_local);
+			msd_local_sort_kernel<WORDS><<<lgrid, MsdLocalCfg<WORDS>::kThreads, local_smem, st>>>(lo);
+			ctx->launches++;
+			s.pass_names[iv] = "msd_local_sort"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+		}
 		lsd_in = b; lsd_out = a; lsd_flag = flags;
 		*result_in_b = final_in_b;
 	} else
 		*result_in_b = (key_bytes % 2) == 1;
 
-	// 8-bit LSD passes: the whole sort when the hybrid path is off, otherwise its fallback (they return at once unless flagged)
-	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix));
-	for (uint32_t pass = 0; pass < key_bytes; ++pass) {
-		SortPass p;
-		p.in = lsd_in; p.out = lsd_out; p.n = n; p.n_tiles = n_tiles; p.byte = pass;
-		p.next_byte = pass + 1 < key_bytes ? (int32_t)(pass + 1) : -1;
-		p.hist = s.zero->hist[pass];
-		p.hist_next = s.zero->hist[pass + 1];
-		p.desc = s.desc;
-		p.epoch = next_epoch(ctx);
-		p.tile_counter = &s.zero->counters[pass];
-		p.run_flag = lsd_flag;
-		radix_pass_kernel<WORDS><<<grid, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes, st>>>(p);
-		ctx->launches++;
-		if (!msd) { s.pass_names[iv] = "radix_pass"; CU(cudaEventRecord(s.ev_pass[++iv], st)); }
-		std::swap(lsd_in, lsd_out);
+	if (plan && plan->active) {        // the caller runs the leaves first, then calls launch_lsd_fallback
+		CU(cudaGetLastError());
+		s.n_passes_run = iv;
+		return 0;
 	}
+	// 8-bit LSD passes: the whole sort when the hybrid path is off, otherwise its fallback (they return at once unless flagged)
+	if (int rc = launch_lsd_passes<WORDS>(ctx, s, lsd_in, lsd_out, n, key_bytes, lsd_flag, !msd, iv, st)) return rc;
 	if (msd) { s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st)); }
 	CU(cudaGetLastError());
 	s.n_passes_run = iv;
@@ -346,7 +381,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 
 template <int WORDS>
 int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
-	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+	uint64_t* d_lut, uint64_t* d_result, const uint32_t* run_flag, cudaStream_t st)
 {
 	constexpr int TILE = count_tile<WORDS>();
 	const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
@@ -357,6 +392,7 @@ int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint
 	a.counter_bytes = ctx->counter_bytes; a.suffix_bytes = ctx->suffix_bytes;
 	a.out = d_out; a.out_capacity = out_capacity; a.lut = d_lut; a.result = d_result;
 	a.desc = s.cdesc; a.epoch = next_epoch(ctx); a.tile_counter = &s.zero->counters[kMaxPasses];
+	a.run_flag = run_flag;
 	const size_t smem = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	count_emit_kernel<WORDS><<<n_tiles, CountCfg<WORDS>::kThreads, smem, st>>>(a);
 	ctx->launches++;
@@ -451,7 +487,7 @@ int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8
 	CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
 	CU(cudaMemsetAsync(&s.zero->counters[kMaxPasses], 0, sizeof(uint32_t), st));
 	if (n == 0) return 0;
-	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, st);
+	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, nullptr, st);
 }
 
 __global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uint32_t* status)
@@ -480,11 +516,53 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	CU(cudaEventRecord(s.ev_expand, st));
 	s.ran_expand = true;
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, (n_packs && pack_bytes) ? n_packs : 1u, st, &in_b)) return rc;
-	CU(cudaEventRecord(s.ev_sort, st));
-	s.ran_sort = true;
-	const void* sorted = in_b ? s.recs_b : s.recs_a;
-	if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
+	const uint32_t np_eff = (n_packs && pack_bytes) ? n_packs : 1u;
+	if (ctx->words == 1 && ctx->use_leaf) {
+		// ---- k <= 32: partition, then COUNT the leaves (leaf_count.cuh); LSD passes + count_emit_kernel stand behind as the flagged fallback
+		LeafPlan plan;
+		if (int rc = launch_sort<1>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b, &plan)) return rc;
+		if (plan.active) {
+			const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
+			if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * ob + 64)) return rc;
+			CU(cudaMemsetAsync(d_lut, 0, ctx->lut_entries * 8, st));
+			CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
+			uint32_t* flags = s.zero->msd_flags;
+			LeafArgs la{};
+			la.recs = reinterpret_cast<const uint64_t*>(plan.recs); la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
+			la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
+			la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
+			la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
+			const uint32_t lgrid = std::min<uint32_t>(plan.n_leaves, (uint32_t)(ctx->sm_count * ctx->occ_leaf));
+			leaf_count_kernel<<<lgrid, kLeafThreads, sizeof(LeafSmem), st>>>(la);
+			leaf_scan_kernel<<<1, 1024, 0, st>>>(s.leaf_emit, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags);
+			leaf_gather_kernel<<<(plan.n_leaves + 7) / 8, 256, 0, st>>>(s.leaf_tmp, plan.start, s.leaf_emit, s.leaf_off, plan.n_leaves, ob, d_out, d_result, flags);
+			ctx->launches += 3;
+			int iv = s.n_passes_run;
+			s.pass_names[iv] = "leaf_count"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+			// fallback (returns at once unless a leaf overflowed): LSD passes from the level-1 output, then the classic count
+			if (int rc = launch_lsd_passes<1>(ctx, s, s.recs_b, s.recs_a, n_rec, ctx->key_bytes, flags, false, iv, st)) return rc;
+			leaf_reset_kernel<<<64, 256, 0, st>>>(d_lut, ctx->lut_entries, d_result, flags);
+			ctx->launches++;
+			s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+			s.n_passes_run = iv;
+			CU(cudaEventRecord(s.ev_sort, st));
+			s.ran_sort = true;
+			const void* sorted = (ctx->key_bytes % 2 == 0) ? s.recs_b : s.recs_a;
+			CU(cudaMemsetAsync(&s.zero->counters[kMaxPasses], 0, sizeof(uint32_t), st));
+			if (int rc = launch_count<1>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, st)) return rc;
+		} else {
+			CU(cudaEventRecord(s.ev_sort, st));
+			s.ran_sort = true;
+			const void* sorted = in_b ? s.recs_b : s.recs_a;
+			if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
+		}
+	} else {
+		if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b)) return rc;
+		CU(cudaEventRecord(s.ev_sort, st));
+		s.ran_sort = true;
+		const void* sorted = in_b ? s.recs_b : s.recs_a;
+		if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
+	}
 	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status);
 	ctx->launches++;
 	CU(cudaEventRecord(s.ev_count, st));
@@ -524,10 +602,16 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	ctx->lut_entries = 1ull << (2 * prm->lut_prefix_len);
 	ctx->sm_count = dp.multiProcessorCount;
 	if (const char* e = getenv("KMCB200_SORT")) ctx->use_msd = std::string(e) != "lsd";
+	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
 	ctx->slots.resize(prm->n_slots);
 	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };
 	if (cudaSetDevice(prm->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(KMCB200_ERR_CUDA); }
 	if (int rc = DISPATCH_WORDS(ctx, setup_kernels, ctx)) return bail(rc);
+	if (cudaFuncSetAttribute(leaf_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeafSmem)) != cudaSuccess ||
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf, leaf_count_kernel, kLeafThreads, sizeof(LeafSmem)) != cudaSuccess) {
+		ctx->err = "leaf_count_kernel setup failed"; return bail(KMCB200_ERR_CUDA);
+	}
+	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
 	if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(KMCB200_ERR_CUDA); }
 	for (auto& s : ctx->slots) {
 		bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -536,6 +620,8 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 		ok = ok && cudaMemset(s.zero, 0, sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_lut), ctx->lut_entries * 8) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_seg1), 2 * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.leaf_emit), 65536 * 4) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.leaf_off), 65536 * 8) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_start2), 257 * 8) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_start3), 65537 * 8) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_item_base1), 2 * 4) == cudaSuccess;
@@ -561,7 +647,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 				 (void*)s.pack_kbase, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
-				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums})
+				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off})
 			if (p) cudaFree(p);
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);

@@ -1,0 +1,346 @@
+// kmc_b200 — leaves of the hybrid MSD path for one-word k-mers (k <= 32): COUNT WITHOUT SORTING THE DUPLICATES.
+//
+// What stage 2 needs from a leaf bucket is the sorted list of its DISTINCT k-mers with their multiplicities
+// (CompactKmers, kmc_core/kb_sorter.h:1128-1281).  With sequencing coverage c a k-mer occurs ~c times, so sorting every
+// copy (RADULS, or our own leaf sort) does ~c times the necessary work.  A leaf (records that share their top 8+b2 bits,
+// ~1 K records) is therefore counted in an order-preserving table in shared memory instead:
+//   * slot = the next 11 bits of the k-mer, claimed with one 64-bit atomicCAS; a copy of a k-mer already there is one
+//     atomicAdd.  Slot order is key order, so no sort is needed;
+//   * two different k-mers in one slot (same next 11 bits) are rare (~15 % of the distinct k-mers at 30x coverage): the later
+//     one goes to a small open-addressing side table; side entries are ranked against the few entries of their own slot;
+//   * cutoffs / clamping / record bytes / LUT exactly as kb_sorter.h:1174-1203; a prefix sum over the slots gives every
+//     surviving k-mer its position, the records are staged in shared memory and written to the leaf's region of a
+//     temporary buffer; a tiny scan over the leaves + leaf_gather_kernel packs the regions into the output.
+// No look-back, no inter-CTA dependency.  A leaf whose side table overflows (heavy skew) raises the fallback flag:
+// the LSD passes + count_emit_kernel then redo the bin (msd_sort.cuh).
+#pragma once
+#include "common.cuh"
+#include "msd_sort.cuh"
+
+namespace kmcb {
+
+constexpr int kLeafThreads = 256;
+constexpr int kLeafSlotBits = 11;
+constexpr int kLeafSlots = 1 << kLeafSlotBits;      // main table
+constexpr int kLeafSide = 512;                      // side table (open addressing)
+constexpr int kLeafSideMax = 448;
+constexpr uint64_t kLeafEmpty = ~0ull;
+
+struct LeafArgs {
+	const uint64_t* recs;        // partitioned records
+	const uint64_t* start;       // [n_leaves + 1]
+	uint32_t n_leaves;
+	uint32_t low_bits;           // bits below the partition digits
+	uint32_t k, lut_prefix_len, cutoff_min, cutoff_max, counter_max, counter_bytes, suffix_bytes;
+	uint8_t* tmp;                // leaf L stages its records at tmp + start[L] * out_rec_bytes
+	uint32_t* leaf_emit;         // [n_leaves] emitted records
+	uint64_t* lut;
+	uint64_t* result;            // [0] n_unique [1] n_cutoff_min [2] n_cutoff_max
+	uint32_t* ticket;
+	uint32_t* flags;
+};
+
+struct LeafSmem {
+	uint64_t mkey[kLeafSlots];       // 16 KB   (re-used as the staging area of the emitted bytes, together with mcnt)
+	uint32_t mcnt[kLeafSlots];       //  8 KB
+	uint32_t val[kLeafSlots];        //  8 KB   surviving entries per slot, then their exclusive prefix
+	uint64_t skey[kLeafSide];        //  4 KB
+	uint32_t scnt[kLeafSide];        //  2 KB
+	uint16_t sslot[kLeafSide];       //  1 KB
+	uint16_t dense[kLeafSide];       //  1 KB   side entries in use
+	uint32_t warp_tot[8];
+	uint32_t n_side, n_dense, n_allones, leaf, total_emit;
+};
+
+__device__ __forceinline__ bool leaf_classify(uint32_t c, const LeafArgs& a, uint32_t& n_min, uint32_t& n_max, uint32_t& value)
+{
+	if (c < a.cutoff_min) { ++n_min; return false; }       // kb_sorter.h:1174
+	if (c > a.cutoff_max) { ++n_max; return false; }       // :1181
+	value = c > a.counter_max ? a.counter_max : c;          // :1190
+	return true;
+}
+
+// record bytes: (k-p)/4 suffix bytes most significant first, then the counter least significant first (kb_sorter.h:1198-1201)
+__device__ __forceinline__ void leaf_put(uint8_t* o, uint64_t key, uint32_t value, const LeafArgs& a)
+{
+	for (uint32_t j = 0; j < a.suffix_bytes; ++j) o[j] = (uint8_t)(key >> (8 * (a.suffix_bytes - 1 - j)));
+	for (uint32_t j = 0; j < a.counter_bytes; ++j) o[a.suffix_bytes + j] = (uint8_t)(value >> (8 * j));
+}
+
+__global__ void __launch_bounds__(kLeafThreads) leaf_count_kernel(const LeafArgs a)
+{
+	extern __shared__ __align__(16) uint8_t dsm[];
+	LeafSmem& S = *reinterpret_cast<LeafSmem*>(dsm);
+	if (*a.flags & kMsdFlagFallback) return;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t ob = a.suffix_bytes + a.counter_bytes;
+	const uint32_t slot_shift = a.low_bits > (uint32_t)kLeafSlotBits ? a.low_bits - kLeafSlotBits : 0;
+	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
+	const bool one_prefix = prefix_shift >= a.low_bits;        // every k-mer of a leaf has the same LUT prefix
+	uint32_t n_unique = 0, n_min = 0, n_max = 0;
+	bool failed = false;
+
+	while (true) {
+		__syncthreads();
+		if (tid == 0) S.leaf = atomicAdd(a.ticket, 1u);
+		__syncthreads();
+		const uint32_t leaf = S.leaf;
+		if (leaf >= a.n_leaves) break;
+		const uint64_t lo = a.start[leaf];
+		const uint32_t m = (uint32_t)(a.start[leaf + 1] - lo);
+		if (m == 0) { if (tid == 0) a.leaf_emit[leaf] = 0; continue; }
+
+		// ---- clear
+#pragma unroll
+		for (int i = 0; i < kLeafSlots / kLeafThreads; ++i) { S.mkey[i * kLeafThreads + tid] = kLeafEmpty; S.mcnt[i * kLeafThreads + tid] = 0; }
+#pragma unroll
+		for (int i = 0; i < kLeafSide / kLeafThreads; ++i) { S.skey[i * kLeafThreads + tid] = kLeafEmpty; S.scnt[i * kLeafThreads + tid] = 0; }
+		if (tid == 0) { S.n_side = 0; S.n_dense = 0; S.n_allones = 0; }
+		__syncthreads();
+
+		// ---- count: slot = next 11 bits of the k-mer
+		for (uint32_t j0 = 0; j0 < m; j0 += 4 * kLeafThreads) {
+			uint64_t key[4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * kLeafThreads + tid; key[u] = j < m ? a.recs[lo + j] : 0; }
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				const uint32_t j = j0 + u * kLeafThreads + tid;
+				if (j >= m) continue;
+				const uint64_t kk = key[u];
+				if (kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
+				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
+				const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[b]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
+				if (old == kLeafEmpty || old == kk) { atomicAdd(&S.mcnt[b], 1u); continue; }
+				// a different k-mer owns the slot: side table
+				uint32_t h = (uint32_t)((kk * 0x9E3779B97F4A7C15ull) >> 55) & (kLeafSide - 1);
+				for (int probe = 0; probe < kLeafSide; ++probe) {
+					const unsigned long long o2 = atomicCAS(reinterpret_cast<unsigned long long*>(&S.skey[h]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
+					if (o2 == kLeafEmpty) { S.sslot[h] = (uint16_t)b; atomicAdd(&S.n_side, 1u); }
+					if (o2 == kLeafEmpty || o2 == kk) { atomicAdd(&S.scnt[h], 1u); break; }
+					h = (h + 1) & (kLeafSide - 1);
+					if (probe == kLeafSide - 1) failed = true;
+				}
+			}
+		}
+		__syncthreads();
+		if (S.n_side > (uint32_t)kLeafSideMax) failed = true;
+
+		// ---- main slots (thread owns 8 consecutive slots): cutoffs, survivors per slot
+		uint64_t mk[8];
+		uint32_t mv[8];
+		uint32_t mpass = 0;
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const uint32_t b = tid * 8 + i;
+			const uint32_t c = S.mcnt[b];
+			mk[i] = S.mkey[b];
+			mv[i] = 0;
+			bool pass = false;
+			if (c) { ++n_unique; pass = leaf_classify(c, a, n_min, n_max, mv[i]); }
+			mpass |= (uint32_t)pass << i;
+			S.val[b] = pass ? 1u : 0u;
+		}
+		// side entries: dense list, cutoffs
+#pragma unroll
+		for (int i = 0; i < kLeafSide / kLeafThreads; ++i) {
+			const uint32_t h = i * kLeafThreads + tid;
+			if (S.skey[h] != kLeafEmpty) {
+				++n_unique;
+				uint32_t v;
+				if (leaf_classify(S.scnt[h], a, n_min, n_max, v)) { S.scnt[h] = v; S.dense[atomicAdd(&S.n_dense, 1u)] = (uint16_t)h; }
+				else S.scnt[h] = 0;
+			}
+		}
+		uint32_t allones_val = 0;
+		bool allones_pass = false;
+		if (tid == 0 && S.n_allones) { ++n_unique; allones_pass = leaf_classify(S.n_allones, a, n_min, n_max, allones_val); }
+		__syncthreads();
+		const uint32_t n_dense = S.n_dense;
+		for (uint32_t e = tid; e < n_dense; e += kLeafThreads) atomicAdd(&S.val[S.sslot[S.dense[e]]], 1u);
+		__syncthreads();
+
+		// ---- exclusive prefix over the slots = position of every surviving k-mer in the leaf's output
+		uint32_t cs[8];
+		uint32_t sum = 0;
+#pragma unroll
+		for (int i = 0; i < 8; ++i) { cs[i] = S.val[tid * 8 + i]; sum += cs[i]; }
+		uint32_t inc = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc += t;
+		}
+		if (lane == 31) S.warp_tot[warp] = inc;
+		__syncthreads();
+		uint32_t base = inc - sum, tot = 0;
+#pragma unroll
+		for (int w = 0; w < 8; ++w) { const uint32_t t = S.warp_tot[w]; if ((uint32_t)w < warp) base += t; tot += t; }
+#pragma unroll
+		for (int i = 0; i < 8; ++i) { S.val[tid * 8 + i] = base; base += cs[i]; }
+		const uint32_t total = tot;      // the all-ones k-mer, if any, is appended by thread 0 below
+		__syncthreads();
+
+		// ---- side entries: rank inside their slot (against the slot's main entry and the other side entries of that slot)
+		uint32_t side_pos[2] = {0, 0};
+		uint64_t side_key[2] = {0, 0};
+		uint32_t side_val[2] = {0, 0};
+		int n_my_side = 0;
+		for (uint32_t e = tid; e < n_dense; e += kLeafThreads) {
+			const uint32_t h = S.dense[e];
+			const uint64_t kk = S.skey[h];
+			const uint32_t b = S.sslot[h];
+			uint32_t r = (S.mcnt[b] != 0 && S.mkey[b] < kk && true) ? 1u : 0u;      // main entry of the slot (counted only if it survived, fixed below)
+			for (uint32_t f = 0; f < n_dense; ++f) {
+				const uint32_t h2 = S.dense[f];
+				if (S.sslot[h2] == b && S.skey[h2] < kk) ++r;
+			}
+			if (n_my_side < 2) { side_pos[n_my_side] = (b << 16) | r; side_key[n_my_side] = kk; side_val[n_my_side] = S.scnt[h]; ++n_my_side; }
+			else failed = true;       // more than 2 side entries per thread: n_dense > 512 cannot happen
+		}
+		// the main entry of a slot that also has side entries: how many surviving side entries precede it
+		uint32_t main_rank[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			main_rank[i] = 0;
+			if (((mpass >> i) & 1u) && cs[i] > 1) {
+				const uint32_t b = tid * 8 + i;
+				for (uint32_t f = 0; f < n_dense; ++f) {
+					const uint32_t h2 = S.dense[f];
+					if (S.sslot[h2] == b && S.skey[h2] < mk[i]) ++main_rank[i];
+				}
+			}
+		}
+		// a side entry counted the main entry of its slot only if that one survived the cutoffs
+		for (int q = 0; q < n_my_side; ++q) {
+			const uint32_t b = side_pos[q] >> 16;
+			uint32_t r = side_pos[q] & 0xFFFFu;
+			const uint32_t c = S.mcnt[b];
+			uint32_t dummy_min = 0, dummy_max = 0, v;
+			if (c != 0 && S.mkey[b] < side_key[q] && !leaf_classify(c, a, dummy_min, dummy_max, v)) --r;
+			side_pos[q] = S.val[b] + r;
+		}
+		uint32_t vpre[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) vpre[i] = S.val[tid * 8 + i] + main_rank[i];
+		__syncthreads();      // all reads of mkey / mcnt / val are done: the table becomes the staging area
+
+		uint8_t* stage = reinterpret_cast<uint8_t*>(S.mkey);
+		const uint32_t total_emit = total + ((tid == 0 && allones_pass) ? 1u : 0u);
+		if ((uint64_t)(total + 1) * ob > sizeof(S.mkey) + sizeof(S.mcnt)) failed = true;
+		else {
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+				if ((mpass >> i) & 1u) leaf_put(stage + (size_t)vpre[i] * ob, mk[i], mv[i], a);
+			for (int q = 0; q < n_my_side; ++q) leaf_put(stage + (size_t)side_pos[q] * ob, side_key[q], side_val[q], a);
+			if (tid == 0 && allones_pass) leaf_put(stage + (size_t)total * ob, kLeafEmpty, allones_val, a);
+		}
+		if (tid == 0) {
+			S.total_emit = total_emit;
+			a.leaf_emit[leaf] = total_emit;
+		}
+		// lut[prefix]++ for every emitted k-mer (kb_sorter.h:1203)
+		if (one_prefix) {
+			if (tid == 0 && total_emit) {
+				const uint64_t any = ((uint64_t)leaf << a.low_bits);
+				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (any >> prefix_shift), (unsigned long long)total_emit);
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+				if ((mpass >> i) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (mk[i] >> prefix_shift), 1ull);
+			for (int q = 0; q < n_my_side; ++q) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (side_key[q] >> prefix_shift), 1ull);
+			if (tid == 0 && allones_pass) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kLeafEmpty >> prefix_shift), 1ull);
+		}
+		__syncthreads();
+		// ---- staged bytes -> the leaf's region of the temporary buffer
+		{
+			const uint32_t nbytes = S.total_emit * ob;
+			uint8_t* dst = a.tmp + lo * ob;
+			const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
+			const uint32_t headb = min(nbytes, (4u - mis) & 3u);
+			if (tid < headb) dst[tid] = stage[tid];
+			// the staging area is 4-byte aligned at offset 0, the destination at offset headb: byte-shifted word copy
+			const uint32_t nwords = (nbytes - headb) >> 2;
+			for (uint32_t w = tid; w < nwords; w += kLeafThreads) {
+				const uint32_t sb = headb + 4 * w;          // byte offset in the staging area
+				const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage) + (sb >> 2);
+				const uint32_t sh = (sb & 3u) * 8u;
+				const uint32_t v = sh ? __funnelshift_r(sw[0], sw[1], sh) : sw[0];
+				reinterpret_cast<uint32_t*>(dst + headb)[w] = v;
+			}
+			const uint32_t done = headb + 4 * nwords;
+			if (tid < nbytes - done) dst[done + tid] = stage[done + tid];
+		}
+	}
+	// ---- statistics of this CTA
+	if (failed) atomicOr(a.flags, kMsdFlagFallback);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		n_unique += __shfl_down_sync(0xffffffffu, n_unique, o);
+		n_min += __shfl_down_sync(0xffffffffu, n_min, o);
+		n_max += __shfl_down_sync(0xffffffffu, n_max, o);
+	}
+	if (lane == 0) {
+		if (n_unique) atomicAdd(reinterpret_cast<unsigned long long*>(a.result), (unsigned long long)n_unique);
+		if (n_min) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 1, (unsigned long long)n_min);
+		if (n_max) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 2, (unsigned long long)n_max);
+	}
+}
+
+// exclusive scan of the per-leaf record counts (single CTA), total -> result[4]
+__global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_emit, uint32_t n_leaves, uint64_t* leaf_off, uint64_t* result, uint64_t out_capacity, uint32_t ob, const uint32_t* flags)
+{
+	__shared__ uint64_t s_w[32];
+	__shared__ uint64_t carry;
+	if (*flags & kMsdFlagFallback) return;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	for (uint32_t b0 = 0; b0 < n_leaves; b0 += 1024) {
+		const uint32_t i = b0 + tid;
+		const uint64_t v = i < n_leaves ? leaf_emit[i] : 0;
+		uint64_t inc = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc += t;
+		}
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		uint64_t base = carry;
+		for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
+		if (i < n_leaves) leaf_off[i] = base + inc - v;
+		__syncthreads();
+		if (tid == 1023) carry = base + inc;
+		__syncthreads();
+	}
+	if (tid == 0) {
+		result[4] = carry;
+		if (carry * ob > out_capacity) result[5] = 1;
+	}
+}
+
+// one warp per leaf: its staged records -> their final place
+__global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, const uint64_t* start, const uint32_t* leaf_emit, const uint64_t* leaf_off,
+	uint32_t n_leaves, uint32_t ob, uint8_t* out, const uint64_t* result, const uint32_t* flags)
+{
+	if (*flags & kMsdFlagFallback) return;
+	if (result[5]) return;                        // capacity error: nothing is written
+	const uint32_t leaf = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+	if (leaf >= n_leaves) return;
+	const uint32_t nbytes = leaf_emit[leaf] * ob;
+	const uint8_t* src = tmp + start[leaf] * ob;
+	uint8_t* dst = out + leaf_off[leaf] * ob;
+	for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = src[i];
+}
+
+// when the hybrid path gave up after the leaves had already touched lut / result: start over for the fallback
+__global__ void leaf_reset_kernel(uint64_t* lut, uint64_t lut_entries, uint64_t* result, const uint32_t* flags)
+{
+	if (!(*flags & kMsdFlagFallback)) return;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < lut_entries; i += (uint64_t)gridDim.x * blockDim.x) lut[i] = 0;
+	if (blockIdx.x == 0 && threadIdx.x < 6) result[threadIdx.x] = 0;
+}
+
+}  // namespace kmcb

@@ -31,10 +31,28 @@ def _check_bin(oracle, b: Bin, p: Params, ctx=None):
         ctx.close()
 
 
-@pytest.mark.parametrize("k,both,cmin", [(31, True, 2), (31, False, 1), (28, True, 1), (17, True, 1), (32, True, 2), (15, True, 1), (5, True, 1)])
-def test_bin_parity_one_word(oracle, k, both, cmin):
+@pytest.mark.parametrize("leaf", ["count", "sort"])
+@pytest.mark.parametrize("k,both,cmin", [(31, True, 2), (31, False, 1), (28, True, 1), (17, True, 1), (32, True, 2), (32, False, 1), (15, True, 1), (5, True, 1)])
+def test_bin_parity_one_word(oracle, monkeypatch, leaf, k, both, cmin):
+    monkeypatch.setenv("KMCB200_LEAF", leaf)
     p = Params(k=k, both_strands=both, cutoff_min=cmin, lut_prefix_len=choose_lut_prefix_len(k))
     _check_bin(oracle, synth_bin(7, k, 20000, genome_len=30000, err=0.02), p)
+
+
+@pytest.mark.parametrize("p_len,cmin,cmax,cntmax", [(7, 1, 10 ** 9, 255), (11, 2, 10 ** 9, 65535), (15, 1, 40, 3), (3, 3, 10 ** 9, 1)])
+def test_leaf_count_cutoffs_and_prefix_lengths(oracle, p_len, cmin, cmax, cntmax):
+    """The leaf-count path with LUT prefixes shorter and longer than the partition bits, cutoffs, clamping, 0-byte counters."""
+    p = Params(k=31, cutoff_min=cmin, cutoff_max=cmax, counter_max=cntmax, lut_prefix_len=p_len)
+    _check_bin(oracle, synth_bin(21, 31, 60000, genome_len=20000, err=0.01), p)
+
+
+def test_leaf_count_all_T_kmers(oracle):
+    """k = 32, -b: TTT...T is the table's EMPTY sentinel and must still be counted (it sorts last)."""
+    rng = np.random.default_rng(3)
+    p = Params(k=32, both_strands=False, cutoff_min=1, lut_prefix_len=4)
+    lists = [np.full(32 + 200, 3, dtype=np.uint8) for _ in range(200)] + [rng.integers(0, 4, 32 + 100) for _ in range(600)]
+    _check_bin(oracle, pack_superkmers(32, lists), p)
+
 
 
 @pytest.mark.parametrize("k,both,cmin", [(55, True, 2), (55, False, 1), (33, True, 1), (64, True, 2), (70, True, 1), (96, True, 2), (127, False, 1), (128, True, 1)])
