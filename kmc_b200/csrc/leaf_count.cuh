@@ -32,7 +32,7 @@ struct LeafArgs {
 	uint32_t n_leaves;
 	uint32_t low_bits;           // bits below the partition digits
 	uint32_t k, lut_prefix_len, cutoff_min, cutoff_max, counter_max, counter_bytes, suffix_bytes;
-	uint8_t* tmp;                // leaf L stages its records at tmp + start[L] * out_rec_bytes
+	uint8_t* tmp;                // leaf L packs its records at tmp + start[L] * 8 (a leaf never emits more bytes than it holds: checked on the host)
 	uint32_t* leaf_emit;         // [n_leaves] emitted records
 	uint64_t* lut;
 	uint64_t* result;            // [0] n_unique [1] n_cutoff_min [2] n_cutoff_max
@@ -40,14 +40,20 @@ struct LeafArgs {
 	uint32_t* flags;
 };
 
+constexpr int kLeafPad = 8;                         // staged / temporary records are padded to 8 bytes (16 when they are longer)
+
 struct LeafSmem {
-	uint64_t mkey[kLeafSlots];       // 16 KB   (re-used as the staging area of the emitted bytes, together with mcnt)
-	uint32_t mcnt[kLeafSlots];       //  8 KB
-	uint32_t val[kLeafSlots];        //  8 KB   surviving entries per slot, then their exclusive prefix
-	uint64_t skey[kLeafSide];        //  4 KB
+	uint64_t mkey[kLeafSlots];       // 16 KB   main table: k-mers          (re-used, with mcnt, as the staging area of the emitted records)
+	uint32_t mcnt[kLeafSlots];       //  8 KB   main table: multiplicities
+	uint32_t val[kLeafSlots / 4];    //  2 KB   survivors per slot, one byte each
+	uint32_t push[kLeafSlots / 4];   //  2 KB   surviving side entries that sort before the main entry of the slot, one byte each
+	uint32_t nside[kLeafSlots / 4];  //  2 KB   surviving side entries per slot, one byte each
+	uint16_t pre[kLeafSlots];        //  4 KB   exclusive prefix of val = position of the slot's first survivor
+	uint32_t mainpass[kLeafSlots / 32];
+	uint64_t skey[kLeafSide];        //  4 KB   side table
 	uint32_t scnt[kLeafSide];        //  2 KB
 	uint16_t sslot[kLeafSide];       //  1 KB
-	uint16_t dense[kLeafSide];       //  1 KB   side entries in use
+	uint16_t dense[kLeafSide];       //  1 KB   surviving side entries
 	uint32_t warp_tot[8];
 	uint32_t n_side, n_dense, n_allones, leaf, total_emit;
 };
@@ -60,25 +66,38 @@ __device__ __forceinline__ bool leaf_classify(uint32_t c, const LeafArgs& a, uin
 	return true;
 }
 
-// record bytes: (k-p)/4 suffix bytes most significant first, then the counter least significant first (kb_sorter.h:1198-1201)
-__device__ __forceinline__ void leaf_put(uint8_t* o, uint64_t key, uint32_t value, const LeafArgs& a)
+// record image: (k-p)/4 suffix bytes most significant first, then the counter least significant first (kb_sorter.h:1198-1201),
+// as a little-endian integer (byte 0 of the record = bits 0-7)
+__device__ __forceinline__ void leaf_record(uint64_t key, uint32_t value, const LeafArgs& a, uint64_t& lo, uint32_t& hi)
 {
-	for (uint32_t j = 0; j < a.suffix_bytes; ++j) o[j] = (uint8_t)(key >> (8 * (a.suffix_bytes - 1 - j)));
-	for (uint32_t j = 0; j < a.counter_bytes; ++j) o[a.suffix_bytes + j] = (uint8_t)(value >> (8 * j));
+	const uint32_t sb = a.suffix_bytes;
+	// suffix = low sb bytes of the k-mer, big endian
+	uint64_t suf = sb >= 8 ? key : (key & ((1ull << (8 * sb)) - 1));
+	suf = (uint64_t)__byte_perm((uint32_t)(suf >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)suf, 0, 0x0123) << 32);     // byte-reversed: MSB first in memory ...
+	suf = sb >= 8 ? suf : (suf >> (8 * (8 - sb)));                                                                              // ... starting at byte 0
+	lo = suf;
+	hi = 0;
+	if (sb < 8) lo |= (uint64_t)value << (8 * sb);
+	if (sb + a.counter_bytes > 8) hi = sb >= 8 ? value : (value >> (8 * (8 - sb)));
 }
 
-__global__ void __launch_bounds__(kLeafThreads) leaf_count_kernel(const LeafArgs a)
+__global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafArgs a)
 {
 	extern __shared__ __align__(16) uint8_t dsm[];
 	LeafSmem& S = *reinterpret_cast<LeafSmem*>(dsm);
 	if (*a.flags & kMsdFlagFallback) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t ob = a.suffix_bytes + a.counter_bytes;
+	const uint32_t pad = ob > 8 ? 16u : 8u;
+	const uint32_t ob_magic = 0xFFFFFFFFu / ob + 1;              // p / ob == umulhi(p, ob_magic) for p < 2^16
 	const uint32_t slot_shift = a.low_bits > (uint32_t)kLeafSlotBits ? a.low_bits - kLeafSlotBits : 0;
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const bool one_prefix = prefix_shift >= a.low_bits;        // every k-mer of a leaf has the same LUT prefix
 	uint32_t n_unique = 0, n_min = 0, n_max = 0;
 	bool failed = false;
+	uint8_t* const val8 = reinterpret_cast<uint8_t*>(S.val);
+	uint8_t* const push8 = reinterpret_cast<uint8_t*>(S.push);
+	uint8_t* const nside8 = reinterpret_cast<uint8_t*>(S.nside);
 
 	while (true) {
 		__syncthreads();
@@ -90,12 +109,22 @@ __global__ void __launch_bounds__(kLeafThreads) leaf_count_kernel(const LeafArgs
 		const uint32_t m = (uint32_t)(a.start[leaf + 1] - lo);
 		if (m == 0) { if (tid == 0) a.leaf_emit[leaf] = 0; continue; }
 
-		// ---- clear
+		// ---- clear (16-byte stores)
+		{
+			uint4* k4 = reinterpret_cast<uint4*>(S.mkey);
+			const uint4 e = make_uint4(~0u, ~0u, ~0u, ~0u), z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-		for (int i = 0; i < kLeafSlots / kLeafThreads; ++i) { S.mkey[i * kLeafThreads + tid] = kLeafEmpty; S.mcnt[i * kLeafThreads + tid] = 0; }
+			for (int i = 0; i < kLeafSlots * 8 / 16 / kLeafThreads; ++i) k4[i * kLeafThreads + tid] = e;
+			uint4* c4 = reinterpret_cast<uint4*>(S.mcnt);
 #pragma unroll
-		for (int i = 0; i < kLeafSide / kLeafThreads; ++i) { S.skey[i * kLeafThreads + tid] = kLeafEmpty; S.scnt[i * kLeafThreads + tid] = 0; }
-		if (tid == 0) { S.n_side = 0; S.n_dense = 0; S.n_allones = 0; }
+			for (int i = 0; i < kLeafSlots * 4 / 16 / kLeafThreads; ++i) c4[i * kLeafThreads + tid] = z;
+			reinterpret_cast<uint4*>(S.skey)[tid] = e;                                  // 512 * 8 B = 256 * 16 B
+			reinterpret_cast<uint2*>(S.scnt)[tid] = make_uint2(0, 0);
+			reinterpret_cast<uint2*>(S.val)[tid] = make_uint2(0, 0);
+			reinterpret_cast<uint2*>(S.push)[tid] = make_uint2(0, 0);
+			reinterpret_cast<uint2*>(S.nside)[tid] = make_uint2(0, 0);
+			if (tid == 0) { S.n_side = 0; S.n_dense = 0; S.n_allones = 0; }
+		}
 		__syncthreads();
 
 		// ---- count: slot = next 11 bits of the k-mer
@@ -126,114 +155,129 @@ __global__ void __launch_bounds__(kLeafThreads) leaf_count_kernel(const LeafArgs
 		__syncthreads();
 		if (S.n_side > (uint32_t)kLeafSideMax) failed = true;
 
-		// ---- main slots (thread owns 8 consecutive slots): cutoffs, survivors per slot
-		uint64_t mk[8];
+		// ---- cutoffs.  Main slots striped over the threads (conflict-free), side entries one per thread.
 		uint32_t mv[8];
 		uint32_t mpass = 0;
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
-			const uint32_t b = tid * 8 + i;
+			const uint32_t b = i * kLeafThreads + tid;
 			const uint32_t c = S.mcnt[b];
-			mk[i] = S.mkey[b];
-			mv[i] = 0;
 			bool pass = false;
+			mv[i] = 0;
 			if (c) { ++n_unique; pass = leaf_classify(c, a, n_min, n_max, mv[i]); }
+			if (pass) atomicAdd(&S.val[b >> 2], 1u << (8 * (b & 3)));
+			const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+			if (lane == 0) S.mainpass[b >> 5] = bal;
 			mpass |= (uint32_t)pass << i;
-			S.val[b] = pass ? 1u : 0u;
 		}
-		// side entries: dense list, cutoffs
 #pragma unroll
 		for (int i = 0; i < kLeafSide / kLeafThreads; ++i) {
 			const uint32_t h = i * kLeafThreads + tid;
-			if (S.skey[h] != kLeafEmpty) {
+			const uint64_t kk = S.skey[h];
+			if (kk != kLeafEmpty) {
 				++n_unique;
 				uint32_t v;
-				if (leaf_classify(S.scnt[h], a, n_min, n_max, v)) { S.scnt[h] = v; S.dense[atomicAdd(&S.n_dense, 1u)] = (uint16_t)h; }
-				else S.scnt[h] = 0;
+				if (leaf_classify(S.scnt[h], a, n_min, n_max, v)) {
+					S.scnt[h] = v;
+					S.dense[atomicAdd(&S.n_dense, 1u)] = (uint16_t)h;
+					const uint32_t b = S.sslot[h];
+					atomicAdd(&S.val[b >> 2], 1u << (8 * (b & 3)));
+					const uint32_t before = atomicAdd(&S.nside[b >> 2], 1u << (8 * (b & 3)));
+					if (((before >> (8 * (b & 3))) & 0xFFu) >= 200u) failed = true;        // byte counters: absurdly many k-mers share 11 bits
+					if (kk < S.mkey[b]) atomicAdd(&S.push[b >> 2], 1u << (8 * (b & 3)));
+				}
 			}
 		}
 		uint32_t allones_val = 0;
 		bool allones_pass = false;
 		if (tid == 0 && S.n_allones) { ++n_unique; allones_pass = leaf_classify(S.n_allones, a, n_min, n_max, allones_val); }
 		__syncthreads();
-		const uint32_t n_dense = S.n_dense;
-		for (uint32_t e = tid; e < n_dense; e += kLeafThreads) atomicAdd(&S.val[S.sslot[S.dense[e]]], 1u);
-		__syncthreads();
 
-		// ---- exclusive prefix over the slots = position of every surviving k-mer in the leaf's output
-		uint32_t cs[8];
-		uint32_t sum = 0;
+		// ---- exclusive prefix over the slots: thread t owns slots [8t, 8t+8), their byte counters are one 64-bit word
+		{
+			const uint64_t v = reinterpret_cast<const uint64_t*>(S.val)[tid];
+			uint64_t x = v;
+			x += x << 8; x += x << 16; x += x << 32;               // inclusive byte prefix sums (no carry: checked below)
+			const uint32_t sum = (uint32_t)(x >> 56);
+			uint32_t bsum = (uint32_t)(v & 0xFF) + (uint32_t)((v >> 8) & 0xFF) + (uint32_t)((v >> 16) & 0xFF) + (uint32_t)((v >> 24) & 0xFF) +
+							(uint32_t)((v >> 32) & 0xFF) + (uint32_t)((v >> 40) & 0xFF) + (uint32_t)((v >> 48) & 0xFF) + (uint32_t)(v >> 56);
+			if (bsum > 255) failed = true;                          // byte counters overflowed: absurd skew, let the fallback redo the bin
+			uint32_t inc = sum;
 #pragma unroll
-		for (int i = 0; i < 8; ++i) { cs[i] = S.val[tid * 8 + i]; sum += cs[i]; }
-		uint32_t inc = sum;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+				if (lane >= (uint32_t)o) inc += t;
+			}
+			if (lane == 31) S.warp_tot[warp] = inc;
+			__syncthreads();
+			uint32_t base = inc - sum, tot = 0;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= (uint32_t)o) inc += t;
+			for (int w = 0; w < 8; ++w) { const uint32_t t = S.warp_tot[w]; if ((uint32_t)w < warp) base += t; tot += t; }
+			const uint64_t excl = x - v;                            // exclusive byte prefix inside the thread
+			uint32_t p16[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t e0 = base + (uint32_t)((excl >> (16 * q)) & 0xFF), e1 = base + (uint32_t)((excl >> (16 * q + 8)) & 0xFF);
+				p16[q] = e0 | (e1 << 16);
+			}
+			reinterpret_cast<uint4*>(S.pre)[tid] = make_uint4(p16[0], p16[1], p16[2], p16[3]);
+			if (tid == 0) S.total_emit = tot;
 		}
-		if (lane == 31) S.warp_tot[warp] = inc;
 		__syncthreads();
-		uint32_t base = inc - sum, tot = 0;
-#pragma unroll
-		for (int w = 0; w < 8; ++w) { const uint32_t t = S.warp_tot[w]; if ((uint32_t)w < warp) base += t; tot += t; }
-#pragma unroll
-		for (int i = 0; i < 8; ++i) { S.val[tid * 8 + i] = base; base += cs[i]; }
-		const uint32_t total = tot;      // the all-ones k-mer, if any, is appended by thread 0 below
-		__syncthreads();
+		const uint32_t total = S.total_emit;
 
-		// ---- side entries: rank inside their slot (against the slot's main entry and the other side entries of that slot)
-		uint32_t side_pos[2] = {0, 0};
+		// ---- positions; k-mers to registers (the table is about to become the staging area)
+		uint64_t mk[8];
+		uint16_t mpos[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			if ((mpass >> i) & 1u) {
+				const uint32_t b = i * kLeafThreads + tid;
+				mk[i] = S.mkey[b];
+				mpos[i] = (uint16_t)(S.pre[b] + push8[b]);
+			}
+		}
 		uint64_t side_key[2] = {0, 0};
-		uint32_t side_val[2] = {0, 0};
+		uint32_t side_val[2] = {0, 0}, side_pos[2] = {0, 0};
 		int n_my_side = 0;
+		const uint32_t n_dense = S.n_dense;
 		for (uint32_t e = tid; e < n_dense; e += kLeafThreads) {
 			const uint32_t h = S.dense[e];
 			const uint64_t kk = S.skey[h];
 			const uint32_t b = S.sslot[h];
-			uint32_t r = (S.mcnt[b] != 0 && S.mkey[b] < kk && true) ? 1u : 0u;      // main entry of the slot (counted only if it survived, fixed below)
-			for (uint32_t f = 0; f < n_dense; ++f) {
-				const uint32_t h2 = S.dense[f];
-				if (S.sslot[h2] == b && S.skey[h2] < kk) ++r;
-			}
-			if (n_my_side < 2) { side_pos[n_my_side] = (b << 16) | r; side_key[n_my_side] = kk; side_val[n_my_side] = S.scnt[h]; ++n_my_side; }
-			else failed = true;       // more than 2 side entries per thread: n_dense > 512 cannot happen
-		}
-		// the main entry of a slot that also has side entries: how many surviving side entries precede it
-		uint32_t main_rank[8];
-#pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			main_rank[i] = 0;
-			if (((mpass >> i) & 1u) && cs[i] > 1) {
-				const uint32_t b = tid * 8 + i;
+			uint32_t r = (((S.mainpass[b >> 5] >> (b & 31)) & 1u) && S.mkey[b] < kk) ? 1u : 0u;
+			if (nside8[b] > 1)                                      // three or more k-mers in one slot: rank among the side entries
 				for (uint32_t f = 0; f < n_dense; ++f) {
 					const uint32_t h2 = S.dense[f];
-					if (S.sslot[h2] == b && S.skey[h2] < mk[i]) ++main_rank[i];
+					if (S.sslot[h2] == b && S.skey[h2] < kk) ++r;
 				}
-			}
+			if (n_my_side < 2) { side_key[n_my_side] = kk; side_val[n_my_side] = S.scnt[h]; side_pos[n_my_side] = S.pre[b] + r; ++n_my_side; }
 		}
-		// a side entry counted the main entry of its slot only if that one survived the cutoffs
-		for (int q = 0; q < n_my_side; ++q) {
-			const uint32_t b = side_pos[q] >> 16;
-			uint32_t r = side_pos[q] & 0xFFFFu;
-			const uint32_t c = S.mcnt[b];
-			uint32_t dummy_min = 0, dummy_max = 0, v;
-			if (c != 0 && S.mkey[b] < side_key[q] && !leaf_classify(c, a, dummy_min, dummy_max, v)) --r;
-			side_pos[q] = S.val[b] + r;
-		}
-		uint32_t vpre[8];
-#pragma unroll
-		for (int i = 0; i < 8; ++i) vpre[i] = S.val[tid * 8 + i] + main_rank[i];
-		__syncthreads();      // all reads of mkey / mcnt / val are done: the table becomes the staging area
+		__syncthreads();      // all reads of the tables are done
 
+		// ---- stage the records (padded), then pack them into the leaf's region of the temporary buffer
 		uint8_t* stage = reinterpret_cast<uint8_t*>(S.mkey);
 		const uint32_t total_emit = total + ((tid == 0 && allones_pass) ? 1u : 0u);
-		if ((uint64_t)(total + 1) * ob > sizeof(S.mkey) + sizeof(S.mcnt)) failed = true;
+		if ((uint64_t)(total + 1) * pad > sizeof(S.mkey) + sizeof(S.mcnt)) failed = true;
 		else {
+			uint64_t rl; uint32_t rh;
 #pragma unroll
 			for (int i = 0; i < 8; ++i)
-				if ((mpass >> i) & 1u) leaf_put(stage + (size_t)vpre[i] * ob, mk[i], mv[i], a);
-			for (int q = 0; q < n_my_side; ++q) leaf_put(stage + (size_t)side_pos[q] * ob, side_key[q], side_val[q], a);
-			if (tid == 0 && allones_pass) leaf_put(stage + (size_t)total * ob, kLeafEmpty, allones_val, a);
+				if ((mpass >> i) & 1u) {
+					leaf_record(mk[i], mv[i], a, rl, rh);
+					*reinterpret_cast<uint64_t*>(stage + (size_t)mpos[i] * pad) = rl;
+					if (pad == 16) *reinterpret_cast<uint32_t*>(stage + (size_t)mpos[i] * pad + 8) = rh;
+				}
+			for (int q = 0; q < n_my_side; ++q) {
+				leaf_record(side_key[q], side_val[q], a, rl, rh);
+				*reinterpret_cast<uint64_t*>(stage + (size_t)side_pos[q] * pad) = rl;
+				if (pad == 16) *reinterpret_cast<uint32_t*>(stage + (size_t)side_pos[q] * pad + 8) = rh;
+			}
+			if (tid == 0 && allones_pass) {
+				leaf_record(kLeafEmpty, allones_val, a, rl, rh);
+				*reinterpret_cast<uint64_t*>(stage + (size_t)total * pad) = rl;
+				if (pad == 16) *reinterpret_cast<uint32_t*>(stage + (size_t)total * pad + 8) = rh;
+			}
 		}
 		if (tid == 0) {
 			S.total_emit = total_emit;
@@ -241,10 +285,8 @@ __global__ void __launch_bounds__(kLeafThreads) leaf_count_kernel(const LeafArgs
 		}
 		// lut[prefix]++ for every emitted k-mer (kb_sorter.h:1203)
 		if (one_prefix) {
-			if (tid == 0 && total_emit) {
-				const uint64_t any = ((uint64_t)leaf << a.low_bits);
-				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (any >> prefix_shift), (unsigned long long)total_emit);
-			}
+			if (tid == 0 && total_emit)
+				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (((uint64_t)leaf << a.low_bits) >> prefix_shift), (unsigned long long)total_emit);
 		} else {
 #pragma unroll
 			for (int i = 0; i < 8; ++i)
@@ -253,24 +295,20 @@ __global__ void __launch_bounds__(kLeafThreads) leaf_count_kernel(const LeafArgs
 			if (tid == 0 && allones_pass) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kLeafEmpty >> prefix_shift), 1ull);
 		}
 		__syncthreads();
-		// ---- staged bytes -> the leaf's region of the temporary buffer
-		{
+		if (!failed) {
+			// packed record bytes, 4 at a time; the leaf's region starts at an 8-byte aligned address (lo * 8)
 			const uint32_t nbytes = S.total_emit * ob;
-			uint8_t* dst = a.tmp + lo * ob;
-			const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
-			const uint32_t headb = min(nbytes, (4u - mis) & 3u);
-			if (tid < headb) dst[tid] = stage[tid];
-			// the staging area is 4-byte aligned at offset 0, the destination at offset headb: byte-shifted word copy
-			const uint32_t nwords = (nbytes - headb) >> 2;
-			for (uint32_t w = tid; w < nwords; w += kLeafThreads) {
-				const uint32_t sb = headb + 4 * w;          // byte offset in the staging area
-				const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage) + (sb >> 2);
-				const uint32_t sh = (sb & 3u) * 8u;
-				const uint32_t v = sh ? __funnelshift_r(sw[0], sw[1], sh) : sw[0];
-				reinterpret_cast<uint32_t*>(dst + headb)[w] = v;
+			uint32_t* dst = reinterpret_cast<uint32_t*>(a.tmp + lo * kLeafPad);
+			for (uint32_t w = tid; w * 4 < nbytes; w += kLeafThreads) {
+				uint32_t word = 0;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const uint32_t pb = 4 * w + j;
+					const uint32_t r = __umulhi(pb, ob_magic);
+					if (pb < nbytes) word |= (uint32_t)stage[r * pad + (pb - r * ob)] << (8 * j);
+				}
+				dst[w] = word;
 			}
-			const uint32_t done = headb + 4 * nwords;
-			if (tid < nbytes - done) dst[done + tid] = stage[done + tid];
 		}
 	}
 	// ---- statistics of this CTA
@@ -330,7 +368,7 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, co
 	const uint32_t leaf = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
 	if (leaf >= n_leaves) return;
 	const uint32_t nbytes = leaf_emit[leaf] * ob;
-	const uint8_t* src = tmp + start[leaf] * ob;
+	const uint8_t* src = tmp + start[leaf] * kLeafPad;
 	uint8_t* dst = out + leaf_off[leaf] * ob;
 	for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = src[i];
 }
