@@ -517,15 +517,13 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	s.ran_expand = true;
 	bool in_b = false;
 	const uint32_t np_eff = (n_packs && pack_bytes) ? n_packs : 1u;
-	// (a leaf packs its records into 8 bytes per input record: fine whenever a record is at most 8 bytes, or every k-mer is seen twice)
-	const bool leaf_ok = (ctx->suffix_bytes + ctx->counter_bytes) <= 8 || ctx->prm.cutoff_min >= 2;
-	if (ctx->words == 1 && ctx->use_leaf && leaf_ok) {
+	if (ctx->words == 1 && ctx->use_leaf) {
 		// ---- k <= 32: partition, then COUNT the leaves (leaf_count.cuh); LSD passes + count_emit_kernel stand behind as the flagged fallback
 		LeafPlan plan;
 		if (int rc = launch_sort<1>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b, &plan)) return rc;
 		if (plan.active) {
 			const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
-			if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * kLeafPad + 64)) return rc;
+			if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * (ob > 8 ? 16 : 8) + 64)) return rc;
 			CU(cudaMemsetAsync(d_lut, 0, ctx->lut_entries * 8, st));
 			CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
 			uint32_t* flags = s.zero->msd_flags;

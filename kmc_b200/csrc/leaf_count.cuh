@@ -32,7 +32,7 @@ struct LeafArgs {
 	uint32_t n_leaves;
 	uint32_t low_bits;           // bits below the partition digits
 	uint32_t k, lut_prefix_len, cutoff_min, cutoff_max, counter_max, counter_bytes, suffix_bytes;
-	uint8_t* tmp;                // leaf L packs its records at tmp + start[L] * 8 (a leaf never emits more bytes than it holds: checked on the host)
+	uint8_t* tmp;                // leaf L writes its records, padded to 8 (16) bytes, at tmp + start[L] * 8 (16)
 	uint32_t* leaf_emit;         // [n_leaves] emitted records
 	uint64_t* lut;
 	uint64_t* result;            // [0] n_unique [1] n_cutoff_min [2] n_cutoff_max
@@ -40,40 +40,33 @@ struct LeafArgs {
 	uint32_t* flags;
 };
 
-constexpr int kLeafPad = 8;                         // staged / temporary records are padded to 8 bytes (16 when they are longer)
+constexpr int kLeafRetry = 2048;                    // copies of k-mers that lost their slot to another k-mer, handled in a dense second round
+constexpr int kLeafMaxEmit = kLeafSlots + kLeafSide;
 
 struct LeafSmem {
-	uint64_t mkey[kLeafSlots];       // 16 KB   main table: k-mers          (re-used, with mcnt, as the staging area of the emitted records)
+	uint64_t mkey[kLeafSlots];       // 16 KB   main table: k-mers
 	uint32_t mcnt[kLeafSlots];       //  8 KB   main table: multiplicities
-	uint32_t val[kLeafSlots / 4];    //  2 KB   survivors per slot, one byte each
 	uint32_t push[kLeafSlots / 4];   //  2 KB   surviving side entries that sort before the main entry of the slot, one byte each
 	uint32_t nside[kLeafSlots / 4];  //  2 KB   surviving side entries per slot, one byte each
-	uint16_t pre[kLeafSlots];        //  4 KB   exclusive prefix of val = position of the slot's first survivor
+	uint16_t pre[kLeafSlots];        //  4 KB   position of the slot's first surviving k-mer
 	uint32_t mainpass[kLeafSlots / 32];
 	uint64_t skey[kLeafSide];        //  4 KB   side table
 	uint32_t scnt[kLeafSide];        //  2 KB
 	uint16_t sslot[kLeafSide];       //  1 KB
 	uint16_t dense[kLeafSide];       //  1 KB   surviving side entries
+	uint16_t retry[kLeafRetry];      //  4 KB   indices (inside the leaf) of records whose slot was taken
+	uint16_t emit_src[kLeafMaxEmit]; //  5 KB   position -> main slot, or 0x8000 | side slot
 	uint32_t warp_tot[8];
-	uint32_t n_side, n_dense, n_allones, leaf, total_emit;
+	uint32_t n_side, n_dense, n_allones, n_retry, leaf, total_emit;
 };
-
-__device__ __forceinline__ bool leaf_classify(uint32_t c, const LeafArgs& a, uint32_t& n_min, uint32_t& n_max, uint32_t& value)
-{
-	if (c < a.cutoff_min) { ++n_min; return false; }       // kb_sorter.h:1174
-	if (c > a.cutoff_max) { ++n_max; return false; }       // :1181
-	value = c > a.counter_max ? a.counter_max : c;          // :1190
-	return true;
-}
 
 // record image: (k-p)/4 suffix bytes most significant first, then the counter least significant first (kb_sorter.h:1198-1201),
 // as a little-endian integer (byte 0 of the record = bits 0-7)
 __device__ __forceinline__ void leaf_record(uint64_t key, uint32_t value, const LeafArgs& a, uint64_t& lo, uint32_t& hi)
 {
 	const uint32_t sb = a.suffix_bytes;
-	// suffix = low sb bytes of the k-mer, big endian
 	uint64_t suf = sb >= 8 ? key : (key & ((1ull << (8 * sb)) - 1));
-	suf = (uint64_t)__byte_perm((uint32_t)(suf >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)suf, 0, 0x0123) << 32);     // byte-reversed: MSB first in memory ...
+	suf = (uint64_t)__byte_perm((uint32_t)(suf >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)suf, 0, 0x0123) << 32);     // byte-reversed: most significant byte first in memory ...
 	suf = sb >= 8 ? suf : (suf >> (8 * (8 - sb)));                                                                              // ... starting at byte 0
 	lo = suf;
 	hi = 0;
@@ -81,23 +74,24 @@ __device__ __forceinline__ void leaf_record(uint64_t key, uint32_t value, const 
 	if (sb + a.counter_bytes > 8) hi = sb >= 8 ? value : (value >> (8 * (8 - sb)));
 }
 
+// cutoffs and clamp (kb_sorter.h:1174-1191): 0 = below cutoff_min, 1 = above cutoff_max, 2 = emitted
+__device__ __forceinline__ uint32_t leaf_class(uint32_t c, const LeafArgs& a) { return c < a.cutoff_min ? 0u : c > a.cutoff_max ? 1u : 2u; }
+
 __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafArgs a)
 {
 	extern __shared__ __align__(16) uint8_t dsm[];
 	LeafSmem& S = *reinterpret_cast<LeafSmem*>(dsm);
 	if (*a.flags & kMsdFlagFallback) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	const uint32_t ob = a.suffix_bytes + a.counter_bytes;
-	const uint32_t pad = ob > 8 ? 16u : 8u;
-	const uint32_t ob_magic = 0xFFFFFFFFu / ob + 1;              // p / ob == umulhi(p, ob_magic) for p < 2^16
+	const uint32_t pad8 = (a.suffix_bytes + a.counter_bytes) > 8 ? 2u : 1u;          // temporary records: 8 or 16 bytes
 	const uint32_t slot_shift = a.low_bits > (uint32_t)kLeafSlotBits ? a.low_bits - kLeafSlotBits : 0;
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const bool one_prefix = prefix_shift >= a.low_bits;        // every k-mer of a leaf has the same LUT prefix
 	uint32_t n_unique = 0, n_min = 0, n_max = 0;
 	bool failed = false;
-	uint8_t* const val8 = reinterpret_cast<uint8_t*>(S.val);
-	uint8_t* const push8 = reinterpret_cast<uint8_t*>(S.push);
-	uint8_t* const nside8 = reinterpret_cast<uint8_t*>(S.nside);
+	const uint8_t* const push8 = reinterpret_cast<const uint8_t*>(S.push);
+	const uint8_t* const nside8 = reinterpret_cast<const uint8_t*>(S.nside);
+	uint64_t* const tmp64 = reinterpret_cast<uint64_t*>(a.tmp);
 
 	while (true) {
 		__syncthreads();
@@ -120,14 +114,13 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 			for (int i = 0; i < kLeafSlots * 4 / 16 / kLeafThreads; ++i) c4[i * kLeafThreads + tid] = z;
 			reinterpret_cast<uint4*>(S.skey)[tid] = e;                                  // 512 * 8 B = 256 * 16 B
 			reinterpret_cast<uint2*>(S.scnt)[tid] = make_uint2(0, 0);
-			reinterpret_cast<uint2*>(S.val)[tid] = make_uint2(0, 0);
 			reinterpret_cast<uint2*>(S.push)[tid] = make_uint2(0, 0);
 			reinterpret_cast<uint2*>(S.nside)[tid] = make_uint2(0, 0);
-			if (tid == 0) { S.n_side = 0; S.n_dense = 0; S.n_allones = 0; }
+			if (tid == 0) { S.n_side = 0; S.n_dense = 0; S.n_allones = 0; S.n_retry = 0; }
 		}
 		__syncthreads();
 
-		// ---- count: slot = next 11 bits of the k-mer
+		// ---- count, round 1: slot = next 11 bits of the k-mer; a record whose slot belongs to another k-mer is only noted down
 		for (uint32_t j0 = 0; j0 < m; j0 += 4 * kLeafThreads) {
 			uint64_t key[4];
 #pragma unroll
@@ -140,68 +133,81 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 				if (kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
 				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
 				const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[b]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
-				if (old == kLeafEmpty || old == kk) { atomicAdd(&S.mcnt[b], 1u); continue; }
-				// a different k-mer owns the slot: side table
+				if (old == kLeafEmpty || old == kk) atomicAdd(&S.mcnt[b], 1u);
+				else {
+					const uint32_t q = atomicAdd(&S.n_retry, 1u);
+					if (q < (uint32_t)kLeafRetry && j < 65536u) S.retry[q] = (uint16_t)j;
+					else failed = true;
+				}
+			}
+		}
+		__syncthreads();
+		// ---- count, round 2 (dense): the noted records go to the side table (open addressing)
+		{
+			const uint32_t nr = min(S.n_retry, (uint32_t)kLeafRetry);
+			for (uint32_t q = tid; q < nr; q += kLeafThreads) {
+				const uint64_t kk = a.recs[lo + S.retry[q]];
+				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
 				uint32_t h = (uint32_t)((kk * 0x9E3779B97F4A7C15ull) >> 55) & (kLeafSide - 1);
-				for (int probe = 0; probe < kLeafSide; ++probe) {
+				int probe = 0;
+				for (; probe < kLeafSide; ++probe) {
 					const unsigned long long o2 = atomicCAS(reinterpret_cast<unsigned long long*>(&S.skey[h]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
 					if (o2 == kLeafEmpty) { S.sslot[h] = (uint16_t)b; atomicAdd(&S.n_side, 1u); }
 					if (o2 == kLeafEmpty || o2 == kk) { atomicAdd(&S.scnt[h], 1u); break; }
 					h = (h + 1) & (kLeafSide - 1);
-					if (probe == kLeafSide - 1) failed = true;
 				}
+				if (probe == kLeafSide) failed = true;
 			}
 		}
 		__syncthreads();
 		if (S.n_side > (uint32_t)kLeafSideMax) failed = true;
 
-		// ---- cutoffs.  Main slots striped over the threads (conflict-free), side entries one per thread.
-		uint32_t mv[8];
-		uint32_t mpass = 0;
+		// ---- cutoffs.  Main slots striped over the threads (conflict-free): one ballot word per 32 slots says who survives.
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
 			const uint32_t b = i * kLeafThreads + tid;
 			const uint32_t c = S.mcnt[b];
-			bool pass = false;
-			mv[i] = 0;
-			if (c) { ++n_unique; pass = leaf_classify(c, a, n_min, n_max, mv[i]); }
-			if (pass) atomicAdd(&S.val[b >> 2], 1u << (8 * (b & 3)));
-			const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+			const uint32_t cl = leaf_class(c, a);
+			n_unique += c != 0;
+			n_min += (c != 0) & (cl == 0);
+			n_max += cl == 1;
+			const uint32_t bal = __ballot_sync(0xffffffffu, (c != 0) & (cl == 2));
 			if (lane == 0) S.mainpass[b >> 5] = bal;
-			mpass |= (uint32_t)pass << i;
 		}
+		// side entries: one or two per thread
 #pragma unroll
 		for (int i = 0; i < kLeafSide / kLeafThreads; ++i) {
 			const uint32_t h = i * kLeafThreads + tid;
 			const uint64_t kk = S.skey[h];
 			if (kk != kLeafEmpty) {
 				++n_unique;
-				uint32_t v;
-				if (leaf_classify(S.scnt[h], a, n_min, n_max, v)) {
-					S.scnt[h] = v;
+				const uint32_t cl = leaf_class(S.scnt[h], a);
+				n_min += cl == 0;
+				n_max += cl == 1;
+				if (cl == 2) {
 					S.dense[atomicAdd(&S.n_dense, 1u)] = (uint16_t)h;
 					const uint32_t b = S.sslot[h];
-					atomicAdd(&S.val[b >> 2], 1u << (8 * (b & 3)));
 					const uint32_t before = atomicAdd(&S.nside[b >> 2], 1u << (8 * (b & 3)));
 					if (((before >> (8 * (b & 3))) & 0xFFu) >= 200u) failed = true;        // byte counters: absurdly many k-mers share 11 bits
 					if (kk < S.mkey[b]) atomicAdd(&S.push[b >> 2], 1u << (8 * (b & 3)));
 				}
 			}
 		}
-		uint32_t allones_val = 0;
-		bool allones_pass = false;
-		if (tid == 0 && S.n_allones) { ++n_unique; allones_pass = leaf_classify(S.n_allones, a, n_min, n_max, allones_val); }
+		uint32_t allones_cl = 0;
+		if (tid == 0 && S.n_allones) { ++n_unique; allones_cl = leaf_class(S.n_allones, a); n_min += allones_cl == 0; n_max += allones_cl == 1; }
 		__syncthreads();
 
-		// ---- exclusive prefix over the slots: thread t owns slots [8t, 8t+8), their byte counters are one 64-bit word
+		// ---- exclusive prefix over the slots: thread t owns slots [8t, 8t+8): 8 ballot bits + 8 side-entry bytes
 		{
-			const uint64_t v = reinterpret_cast<const uint64_t*>(S.val)[tid];
+			const uint32_t bits = (S.mainpass[tid >> 2] >> (8 * (tid & 3))) & 0xFFu;
+			const uint64_t spread = ((uint64_t)bits * 0x0101010101010101ull) & 0x8040201008040201ull;       // bit i -> byte i (non-zero)
+			const uint64_t mainb = ((spread + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;          // 0 / 1 per byte
+			const uint64_t v = mainb + reinterpret_cast<const uint64_t*>(S.nside)[tid];                       // survivors per slot (bytes <= 201)
+			// byte sums may exceed 255 over 8 slots only with absurd skew: use 16-bit lanes for the thread total
+			const uint32_t sum = (uint32_t)((((v & 0x00FF00FF00FF00FFull) + ((v >> 8) & 0x00FF00FF00FF00FFull)) * 0x0001000100010001ull) >> 48);
+			if (sum > 255) failed = true;
 			uint64_t x = v;
-			x += x << 8; x += x << 16; x += x << 32;               // inclusive byte prefix sums (no carry: checked below)
-			const uint32_t sum = (uint32_t)(x >> 56);
-			uint32_t bsum = (uint32_t)(v & 0xFF) + (uint32_t)((v >> 8) & 0xFF) + (uint32_t)((v >> 16) & 0xFF) + (uint32_t)((v >> 24) & 0xFF) +
-							(uint32_t)((v >> 32) & 0xFF) + (uint32_t)((v >> 40) & 0xFF) + (uint32_t)((v >> 48) & 0xFF) + (uint32_t)(v >> 56);
-			if (bsum > 255) failed = true;                          // byte counters overflowed: absurd skew, let the fallback redo the bin
+			x += x << 8; x += x << 16; x += x << 32;               // inclusive byte prefix sums
 			uint32_t inc = sum;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 			uint32_t base = inc - sum, tot = 0;
 #pragma unroll
 			for (int w = 0; w < 8; ++w) { const uint32_t t = S.warp_tot[w]; if ((uint32_t)w < warp) base += t; tot += t; }
-			const uint64_t excl = x - v;                            // exclusive byte prefix inside the thread
+			const uint64_t excl = x - v;
 			uint32_t p16[4];
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
@@ -225,90 +231,52 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 		}
 		__syncthreads();
 		const uint32_t total = S.total_emit;
+		if (total > (uint32_t)kLeafMaxEmit) failed = true;
 
-		// ---- positions; k-mers to registers (the table is about to become the staging area)
-		uint64_t mk[8];
-		uint16_t mpos[8];
+		// ---- who is at which position
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
-			if ((mpass >> i) & 1u) {
-				const uint32_t b = i * kLeafThreads + tid;
-				mk[i] = S.mkey[b];
-				mpos[i] = (uint16_t)(S.pre[b] + push8[b]);
+			const uint32_t b = i * kLeafThreads + tid;
+			if ((S.mainpass[b >> 5] >> (b & 31)) & 1u) S.emit_src[min(S.pre[b] + push8[b], (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)b;
+		}
+		{
+			const uint32_t n_dense = S.n_dense;
+			for (uint32_t e = tid; e < n_dense; e += kLeafThreads) {
+				const uint32_t h = S.dense[e];
+				const uint64_t kk = S.skey[h];
+				const uint32_t b = S.sslot[h];
+				uint32_t r = (((S.mainpass[b >> 5] >> (b & 31)) & 1u) && S.mkey[b] < kk) ? 1u : 0u;
+				if (nside8[b] > 1)                                      // three or more k-mers in one slot: rank among the side entries
+					for (uint32_t f = 0; f < n_dense; ++f) {
+						const uint32_t h2 = S.dense[f];
+						if (S.sslot[h2] == b && S.skey[h2] < kk) ++r;
+					}
+				S.emit_src[min(S.pre[b] + r, (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)(0x8000u | h);
 			}
-		}
-		uint64_t side_key[2] = {0, 0};
-		uint32_t side_val[2] = {0, 0}, side_pos[2] = {0, 0};
-		int n_my_side = 0;
-		const uint32_t n_dense = S.n_dense;
-		for (uint32_t e = tid; e < n_dense; e += kLeafThreads) {
-			const uint32_t h = S.dense[e];
-			const uint64_t kk = S.skey[h];
-			const uint32_t b = S.sslot[h];
-			uint32_t r = (((S.mainpass[b >> 5] >> (b & 31)) & 1u) && S.mkey[b] < kk) ? 1u : 0u;
-			if (nside8[b] > 1)                                      // three or more k-mers in one slot: rank among the side entries
-				for (uint32_t f = 0; f < n_dense; ++f) {
-					const uint32_t h2 = S.dense[f];
-					if (S.sslot[h2] == b && S.skey[h2] < kk) ++r;
-				}
-			if (n_my_side < 2) { side_key[n_my_side] = kk; side_val[n_my_side] = S.scnt[h]; side_pos[n_my_side] = S.pre[b] + r; ++n_my_side; }
-		}
-		__syncthreads();      // all reads of the tables are done
-
-		// ---- stage the records (padded), then pack them into the leaf's region of the temporary buffer
-		uint8_t* stage = reinterpret_cast<uint8_t*>(S.mkey);
-		const uint32_t total_emit = total + ((tid == 0 && allones_pass) ? 1u : 0u);
-		if ((uint64_t)(total + 1) * pad > sizeof(S.mkey) + sizeof(S.mcnt)) failed = true;
-		else {
-			uint64_t rl; uint32_t rh;
-#pragma unroll
-			for (int i = 0; i < 8; ++i)
-				if ((mpass >> i) & 1u) {
-					leaf_record(mk[i], mv[i], a, rl, rh);
-					*reinterpret_cast<uint64_t*>(stage + (size_t)mpos[i] * pad) = rl;
-					if (pad == 16) *reinterpret_cast<uint32_t*>(stage + (size_t)mpos[i] * pad + 8) = rh;
-				}
-			for (int q = 0; q < n_my_side; ++q) {
-				leaf_record(side_key[q], side_val[q], a, rl, rh);
-				*reinterpret_cast<uint64_t*>(stage + (size_t)side_pos[q] * pad) = rl;
-				if (pad == 16) *reinterpret_cast<uint32_t*>(stage + (size_t)side_pos[q] * pad + 8) = rh;
-			}
-			if (tid == 0 && allones_pass) {
-				leaf_record(kLeafEmpty, allones_val, a, rl, rh);
-				*reinterpret_cast<uint64_t*>(stage + (size_t)total * pad) = rl;
-				if (pad == 16) *reinterpret_cast<uint32_t*>(stage + (size_t)total * pad + 8) = rh;
-			}
-		}
-		if (tid == 0) {
-			S.total_emit = total_emit;
-			a.leaf_emit[leaf] = total_emit;
-		}
-		// lut[prefix]++ for every emitted k-mer (kb_sorter.h:1203)
-		if (one_prefix) {
-			if (tid == 0 && total_emit)
-				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (((uint64_t)leaf << a.low_bits) >> prefix_shift), (unsigned long long)total_emit);
-		} else {
-#pragma unroll
-			for (int i = 0; i < 8; ++i)
-				if ((mpass >> i) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (mk[i] >> prefix_shift), 1ull);
-			for (int q = 0; q < n_my_side; ++q) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (side_key[q] >> prefix_shift), 1ull);
-			if (tid == 0 && allones_pass) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kLeafEmpty >> prefix_shift), 1ull);
 		}
 		__syncthreads();
-		if (!failed) {
-			// packed record bytes, 4 at a time; the leaf's region starts at an 8-byte aligned address (lo * 8)
-			const uint32_t nbytes = S.total_emit * ob;
-			uint32_t* dst = reinterpret_cast<uint32_t*>(a.tmp + lo * kLeafPad);
-			for (uint32_t w = tid; w * 4 < nbytes; w += kLeafThreads) {
-				uint32_t word = 0;
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const uint32_t pb = 4 * w + j;
-					const uint32_t r = __umulhi(pb, ob_magic);
-					if (pb < nbytes) word |= (uint32_t)stage[r * pad + (pb - r * ob)] << (8 * j);
-				}
-				dst[w] = word;
-			}
+
+		// ---- dense emission: one thread per surviving k-mer, one aligned 8-byte store each into the leaf's region of the temporary buffer
+		const uint32_t allones_emit = (S.n_allones && leaf_class(S.n_allones, a) == 2) ? 1u : 0u;
+		const uint32_t total_emit = total + allones_emit;
+		for (uint32_t e = tid; e < total_emit && !failed; e += kLeafThreads) {
+			uint64_t kk; uint32_t c;
+			if (e < total) {
+				const uint32_t src = S.emit_src[e];
+				if (src & 0x8000u) { kk = S.skey[src & 0x7FFFu]; c = S.scnt[src & 0x7FFFu]; }
+				else { kk = S.mkey[src]; c = S.mcnt[src]; }
+			} else { kk = kLeafEmpty; c = S.n_allones; }
+			const uint32_t value = c > a.counter_max ? a.counter_max : c;          // kb_sorter.h:1190
+			uint64_t rl; uint32_t rh;
+			leaf_record(kk, value, a, rl, rh);
+			tmp64[(lo + e) * pad8] = rl;
+			if (pad8 == 2) tmp64[(lo + e) * 2 + 1] = rh;
+			if (!one_prefix) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kk >> prefix_shift), 1ull);     // kb_sorter.h:1203
+		}
+		if (tid == 0) {
+			a.leaf_emit[leaf] = total_emit;
+			if (one_prefix && total_emit)
+				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (((uint64_t)leaf << a.low_bits) >> prefix_shift), (unsigned long long)total_emit);
 		}
 	}
 	// ---- statistics of this CTA
@@ -359,7 +327,7 @@ __global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_em
 	}
 }
 
-// one warp per leaf: its staged records -> their final place
+// one warp per leaf: its padded temporary records -> packed records at their final place
 __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, const uint64_t* start, const uint32_t* leaf_emit, const uint64_t* leaf_off,
 	uint32_t n_leaves, uint32_t ob, uint8_t* out, const uint64_t* result, const uint32_t* flags)
 {
@@ -367,10 +335,15 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, co
 	if (result[5]) return;                        // capacity error: nothing is written
 	const uint32_t leaf = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
 	if (leaf >= n_leaves) return;
+	const uint32_t pad = ob > 8 ? 16u : 8u;
 	const uint32_t nbytes = leaf_emit[leaf] * ob;
-	const uint8_t* src = tmp + start[leaf] * kLeafPad;
+	const uint8_t* src = tmp + start[leaf] * pad;
 	uint8_t* dst = out + leaf_off[leaf] * ob;
-	for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = src[i];
+	const uint32_t magic = 0xFFFFFFFFu / ob + 1;          // p / ob == umulhi(p, magic) for p < 2^16 ... checked: larger leaves take the division
+	for (uint32_t p = lane; p < nbytes; p += 32) {
+		const uint32_t r = nbytes < 65536u ? __umulhi(p, magic) : p / ob;
+		dst[p] = src[(size_t)r * pad + (p - r * ob)];
+	}
 }
 
 // when the hybrid path gave up after the leaves had already touched lut / result: start over for the fallback
