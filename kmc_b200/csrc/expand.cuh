@@ -23,8 +23,9 @@
 
 namespace kmcb {
 
-constexpr int kExpandTile = 2048;
-constexpr int kExpandThreads = 256;
+// output tile of expand_kernel = work item of the level-1 MSD partition: 4096 one-word records, 2048 wider ones
+template <int WORDS> struct ExpandCfg { static constexpr int kThreads = WORDS == 1 ? 512 : 256, kTile = 8 * kThreads; };
+constexpr int kExpandMinTile = 2048;
 
 struct ExpandArgs {
 	const uint8_t* bin;          // bin byte stream (device)
@@ -33,6 +34,7 @@ struct ExpandArgs {
 	uint32_t n_packs;
 	uint32_t k;
 	uint32_t min_rec_bytes;      // 1 + ceil(k/4)
+	uint32_t tile;               // ExpandCfg<WORDS>::kTile
 	uint32_t both_strands;
 	uint64_t n_rec;              // expected number of k-mers (CBinDesc::n_rec)
 	// index produced by walk/scan
@@ -57,7 +59,90 @@ struct ExpandArgs {
 
 enum : uint32_t { kErrPackWalk = 1, kErrRecCount = 2 };
 
-__device__ __forceinline__ uint64_t tile_first_base(uint64_t pack_start, uint32_t p) { return pack_start * 4 / kExpandTile + p; }
+__device__ __forceinline__ uint64_t tile_first_base(uint64_t pack_start, uint32_t p, uint32_t tile) { return pack_start * 4 / tile + p; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Walking a pack is a serial chain (the length byte of a record says where the next record starts).  For the usual pack
+// (one collector flush, <= 64 KiB) the chain is cut into 256 segments of 256 bytes that are walked IN PARALLEL, one thread each,
+// from shared memory: thread t does not know where the first record of its segment begins, so it starts 8 KB earlier at an
+// arbitrary byte and follows the chain from there.  Any chain that ever lands on a true record start stays on the true chain,
+// and a landing hits a true start with probability ~1/12, so after 8 KB (>= 200 landings) the two have merged
+// (miss probability ~ (11/12)^200 ~ 3e-8 per segment).  This is then VERIFIED, not assumed: the entry of segment t must be
+// exactly the exit of segment t-1 (thread 0 starts on the true start); one mismatch and the pack is left to the exact
+// warp-per-pack walker below.  A step costs one shared-memory load (~45 cycles); 8 KB + 2 x 256 B = ~750 steps per thread.
+constexpr int kWalkSegBytes = 256;
+constexpr int kWalkSegs = 256;                                   // threads per CTA = segments per pack
+constexpr int kWalkChunk = kWalkSegBytes * kWalkSegs;            // 64 KiB
+constexpr int kWalkSpec = 8192;
+
+__global__ void __launch_bounds__(kWalkSegs) walk_packs_parallel_kernel(const ExpandArgs a, uint32_t* pack_done)
+{
+	extern __shared__ __align__(16) uint8_t wsm[];               // the pack (+ 16 bytes of slack)
+	__shared__ uint32_t s_entry[kWalkSegs], s_exit[kWalkSegs], s_nrec[kWalkSegs], s_nk[kWalkSegs], s_w[16];
+	__shared__ uint32_t s_bad;
+	const uint32_t p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint64_t pstart = a.pack_start[p];
+	const uint32_t len = (uint32_t)min(a.pack_start[p + 1] - pstart, (uint64_t)kWalkChunk + 1);
+	if (len > (uint32_t)kWalkChunk || len == 0) { if (tid == 0) pack_done[p] = len == 0 ? 1u : 0u; if (len == 0 && tid == 0) { a.pack_nsk[p] = 0; a.pack_nk[p] = 0; } return; }
+	// ---- the pack into shared memory (16-byte loads on the absolute 16-byte grid)
+	{
+		const uintptr_t g0 = reinterpret_cast<uintptr_t>(a.bin + pstart);
+		const uintptr_t g0a = g0 & ~(uintptr_t)15;
+		const uint32_t shift = (uint32_t)(g0 - g0a);
+		const uint32_t nvec = (len + shift + 15) >> 4;
+		for (uint32_t v = tid; v < nvec; v += kWalkSegs) reinterpret_cast<uint4*>(wsm)[v] = __ldg(reinterpret_cast<const uint4*>(g0a) + v);
+		if (tid == 0) s_bad = 0;
+		__syncthreads();
+		// byte i of the pack is wsm[shift + i]
+		const uint8_t* pk = wsm + shift;
+		const uint32_t k3 = a.k + 3;
+		const uint32_t seg_lo = tid * kWalkSegBytes, seg_hi = min(seg_lo + (uint32_t)kWalkSegBytes, len);
+		uint32_t pos = seg_lo > (uint32_t)kWalkSpec ? seg_lo - kWalkSpec : 0;       // speculative start (exact for the first 32 segments)
+		if (seg_lo < len) {
+			while (pos < seg_lo) pos += 1 + ((pk[pos] + k3) >> 2);
+		} else pos = len;
+		const uint32_t entry = min(pos, len);
+		uint32_t nrec = 0, nk = 0;
+		pos = entry;
+		while (pos < seg_hi) { const uint32_t x = pk[pos]; nk += x + 1; ++nrec; pos += 1 + ((x + k3) >> 2); }
+		s_entry[tid] = entry; s_exit[tid] = seg_lo < len ? pos : len; s_nrec[tid] = nrec; s_nk[tid] = nk;
+		__syncthreads();
+		// ---- verify the chain of segments
+		bool bad = false;
+		if (tid > 0 && seg_lo < len && s_entry[tid] != min(s_exit[tid - 1], len)) bad = true;
+		if (tid == kWalkSegs - 1 || seg_hi == len) { if (seg_lo < len && s_exit[tid] != len) bad = true; }     // the last record must end with the pack
+		if (bad) atomicOr(&s_bad, 1u);
+		// ---- exclusive scans of records and k-mers over the segments
+		uint32_t ir = nrec, ik = nk;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t tr = __shfl_up_sync(0xffffffffu, ir, o), tk = __shfl_up_sync(0xffffffffu, ik, o);
+			if (lane >= (uint32_t)o) { ir += tr; ik += tk; }
+		}
+		if (lane == 31) { s_w[warp] = ir; s_w[8 + warp] = ik; }
+		__syncthreads();
+		if (s_bad) { if (tid == 0) pack_done[p] = 0; return; }          // left to walk_packs_kernel
+		uint32_t br = ir - nrec, bk = ik - nk, tr = 0, tk = 0;
+#pragma unroll
+		for (int w = 0; w < 8; ++w) { if ((uint32_t)w < warp) { br += s_w[w]; bk += s_w[8 + w]; } tr += s_w[w]; tk += s_w[8 + w]; }
+		// ---- second walk of the own segment: the index
+		const uint64_t slot = pstart / a.min_rec_bytes;
+		const uint64_t tfb = tile_first_base(pstart, p, a.tile);
+		uint32_t j = br, kk = bk;
+		pos = entry;
+		while (pos < seg_hi) {
+			const uint32_t x = pk[pos];
+			a.sk_off[slot + j] = (uint32_t)(pstart + pos);
+			a.sk_kpre[slot + j] = kk;
+			const uint32_t tb = (kk + a.tile - 1) / a.tile;                     // first tile boundary at or after this super-k-mer's first k-mer
+			if (tb * a.tile < kk + x + 1) a.tile_first[tfb + tb] = j;
+			kk += x + 1;
+			pos += 1 + ((x + k3) >> 2);
+			++j;
+		}
+		if (tid == 0) { a.pack_nsk[p] = tr; a.pack_nk[p] = tk; pack_done[p] = 1; }
+	}
+}
 
 // One WARP per pack.  The walk itself is a serial chain (the length byte of a record tells where the next one
 // starts), so the only thing that matters is the latency of one step.  The warp keeps a 512-byte window of the stream
@@ -71,15 +156,16 @@ __device__ __forceinline__ uint4 walk_load_window(const uint8_t* bin_aligned, ui
 	return o < limit ? __ldg(reinterpret_cast<const uint4*>(bin_aligned + o)) : make_uint4(0, 0, 0, 0);
 }
 
-__global__ void __launch_bounds__(32 * kWalkWarpsPerBlock) walk_packs_kernel(const ExpandArgs a)
+__global__ void __launch_bounds__(32 * kWalkWarpsPerBlock) walk_packs_kernel(const ExpandArgs a, const uint32_t* pack_done)
 {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t p = blockIdx.x * kWalkWarpsPerBlock + (threadIdx.x >> 5);
 	if (p >= a.n_packs) return;
+	if (pack_done && pack_done[p]) return;              // the parallel walker has done this pack
 	uint64_t pos = a.pack_start[p];
 	const uint64_t end = a.pack_start[p + 1];
 	const uint64_t slot = pos / a.min_rec_bytes;
-	const uint64_t tfb = tile_first_base(pos, p);
+	const uint64_t tfb = tile_first_base(pos, p, a.tile);
 	// 16-byte aligned view of the stream (the bin pointer is at least 8-byte aligned; the window grid is aligned on absolute addresses)
 	const uintptr_t base_addr = reinterpret_cast<uintptr_t>(a.bin);
 	const uint8_t* bin_aligned = reinterpret_cast<const uint8_t*>(base_addr & ~(uintptr_t)15);
@@ -108,7 +194,7 @@ __global__ void __launch_bounds__(32 * kWalkWarpsPerBlock) walk_packs_kernel(con
 			a.sk_off[slot + j - 31 + lane] = my_off;
 			a.sk_kpre[slot + j - 31 + lane] = my_kpre;
 		}
-		if (nk + x + 1 > next_tile * (uint32_t)kExpandTile) {   // this super-k-mer holds k-mer number next_tile * tile of the pack
+		if (nk + x + 1 > next_tile * a.tile) {   // this super-k-mer holds k-mer number next_tile * tile of the pack
 			if (lane == 0) a.tile_first[tfb + next_tile] = j;
 			++next_tile;
 		}
@@ -140,7 +226,7 @@ __global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
 	for (uint32_t base = 0; base < a.n_packs; base += 1024) {
 		const uint32_t p = base + tid;
 		const uint32_t nk = p < a.n_packs ? a.pack_nk[p] : 0;
-		const uint32_t nt = (nk + kExpandTile - 1) / kExpandTile;
+		const uint32_t nt = (nk + a.tile - 1) / a.tile;
 		uint64_t ik = nk;
 		uint32_t it = nt;
 #pragma unroll
@@ -246,15 +332,15 @@ __device__ __forceinline__ uint32_t rec_top_digit(const Rec<WORDS>& r, uint32_t 
 }
 
 template <int WORDS>
-__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandArgs a)
+__global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(const ExpandArgs a)
 {
+	constexpr int kExpandTile = ExpandCfg<WORDS>::kTile, kExpandThreads = ExpandCfg<WORDS>::kThreads;
 	constexpr int IPT = kExpandTile / kExpandThreads;    // 8
 	__shared__ uint16_t head[kExpandTile];
 	__shared__ uint32_t warp_max[kExpandThreads / 32];
 	__shared__ uint32_t hist[256], htop[256];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	hist[tid] = 0;
-	htop[tid] = 0;
+	if (tid < 256) { hist[tid] = 0; htop[tid] = 0; }
 	const uint32_t total_tiles = a.status[1];
 	Rec<WORDS>* __restrict__ out = reinterpret_cast<Rec<WORDS>*>(a.recs);
 
@@ -267,7 +353,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandArgs
 		const uint32_t nk = a.pack_nk[p];
 		const uint32_t tile_start = t * kExpandTile;
 		const uint32_t cnt = min((uint32_t)kExpandTile, nk - tile_start);
-		const uint32_t j_lo = a.tile_first[tile_first_base(pstart, p) + t];
+		const uint32_t j_lo = a.tile_first[tile_first_base(pstart, p, kExpandTile) + t];
 		const uint32_t* __restrict__ kpre = a.sk_kpre + slot0;
 		const uint32_t* __restrict__ off = a.sk_off + slot0;
 
@@ -321,13 +407,17 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandArgs
 		}
 		__syncthreads();
 		// this tile is one work item of the level-1 partition: its digit counts go straight into the cell layout
-		a.cells1[(uint64_t)tid * total_tiles + g] = (uint16_t)htop[tid];
-		htop[tid] = 0;
+		if (tid < 256) {
+			a.cells1[(uint64_t)tid * total_tiles + g] = (uint16_t)htop[tid];
+			htop[tid] = 0;
+		}
 		if (tid == 0) { a.item_lo1[g] = obase; a.item_cnt1[g] = (uint16_t)cnt; }
 	}
 	__syncthreads();
-	const uint32_t c = hist[tid];
-	if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.hist0) + tid, (unsigned long long)c);
+	if (tid < 256) {
+		const uint32_t c = hist[tid];
+		if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.hist0) + tid, (unsigned long long)c);
+	}
 }
 
 }  // namespace kmcb

@@ -49,6 +49,7 @@ struct Slot {
 	uint64_t* d_pack_start = nullptr; size_t packs_cap = 0;
 	uint64_t* h_pack_start[kStageRing] = {}; cudaEvent_t ev_pack[kStageRing] = {}; int ring = 0;   // pinned staging of the pack offsets
 	uint32_t* pack_nsk = nullptr; uint32_t* pack_nk = nullptr; uint32_t* pack_tbase = nullptr; uint64_t* pack_kbase = nullptr;
+	uint32_t* pack_done = nullptr;
 	uint32_t* sk_off = nullptr; size_t sk_off_cap = 0;
 	uint32_t* sk_kpre = nullptr; size_t sk_kpre_cap = 0;
 	uint32_t* tile_first = nullptr; size_t tile_first_cap = 0;
@@ -164,7 +165,7 @@ int setup_kernels(kmcb200_ctx* ctx)
 {
 	CU(cudaFuncSetAttribute(radix_pass_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortSmem<WORDS>::kBytes));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_radix, radix_pass_kernel<WORDS>, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes));
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_expand, expand_kernel<WORDS>, kExpandThreads, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_expand, expand_kernel<WORDS>, ExpandCfg<WORDS>::kThreads, 0));
 	const size_t cs = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	CU(cudaFuncSetAttribute(count_emit_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
 	CU(cudaFuncSetAttribute(msd_partition_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MsdSmem<WORDS>::kBytes));
@@ -182,9 +183,9 @@ int setup_kernels(kmcb200_ctx* ctx)
 template <int WORDS>
 int launch_expand(kmcb200_ctx* ctx, const ExpandArgs& a, cudaStream_t st)
 {
-	const uint32_t max_tiles = (uint32_t)(a.n_rec / kExpandTile) + a.n_packs + 1;
+	const uint32_t max_tiles = (uint32_t)(a.n_rec / ExpandCfg<WORDS>::kTile) + a.n_packs + 1;
 	const uint32_t grid = std::min<uint32_t>(max_tiles, (uint32_t)(ctx->sm_count * ctx->occ_expand));
-	expand_kernel<WORDS><<<grid, kExpandThreads, 0, st>>>(a);
+	expand_kernel<WORDS><<<grid, ExpandCfg<WORDS>::kThreads, 0, st>>>(a);
 	ctx->launches++;
 	CU(cudaGetLastError());
 	return 0;
@@ -199,12 +200,12 @@ __global__ void msd_setup_kernel(uint64_t* seg1, uint32_t* item_base1, uint32_t*
 }
 
 // upper bound of the level-1 work items of a bin
-size_t msd_max_items1(uint64_t n_rec, uint32_t n_packs) { return (size_t)(n_rec / kExpandTile) + n_packs + 2; }
+size_t msd_max_items1(uint64_t n_rec, uint32_t n_packs) { return (size_t)(n_rec / kExpandMinTile) + n_packs + 2; }
 
 template <int WORDS>
 int ensure_msd(kmcb200_ctx* ctx, Slot& s, uint64_t n, uint32_t n_packs)
 {
-	static_assert(msd_tile<WORDS>() >= kExpandTile, "a partition tile must hold an expand tile");
+	static_assert(msd_tile<WORDS>() >= ExpandCfg<WORDS>::kTile, "a partition tile must hold an expand tile");
 	const size_t items1 = std::max(msd_max_items1(n, n_packs), (size_t)(n / msd_tile<WORDS>()) + 2);
 	const size_t items2 = (size_t)(n / msd_tile<WORDS>()) + 260;
 	const size_t cells = 256 * std::max(items1, items2);
@@ -339,7 +340,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			if (int rc = launch_cell_scan(ctx, s, items2.n_items, nd2, max_items2, flags, st)) return rc;
 			MsdBoundsArgs bb{};
 			bb.cell_scan = s.msd_cell_scan; bb.items = items2; bb.S = 256; bb.nd = nd2; bb.n = n; bb.start = s.msd_start3; bb.cap = cap; bb.flags = flags; bb.tile = 0;
-			msd_bounds_kernel<<<1, 1024, 0, st>>>(bb);
+			msd_bounds_flat_kernel<<<(256 * nd2 + 256) / 256 + 1, 256, 0, st>>>(bb);
 			ctx->launches++;
 			s.pass_names[iv] = "msd_count_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 			MsdPartArgs p2{};
@@ -439,6 +440,8 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_nk), cap * 4));
 		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_tbase), cap * 4));
 		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_kbase), cap * 8));
+		if (s.pack_done) CU(cudaFree(s.pack_done));
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_done), cap * 4));
 		s.packs_cap = cap;
 	}
 	// host prefix sum of the pack sizes into a pinned staging buffer (ring: the copy of an earlier bin may still be queued)
@@ -458,12 +461,13 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 
 	if (int rc = ensure(ctx, s.sk_off, s.sk_off_cap, size / min_rec + 2)) return rc;
 	if (int rc = ensure(ctx, s.sk_kpre, s.sk_kpre_cap, size / min_rec + 2)) return rc;
-	if (int rc = ensure(ctx, s.tile_first, s.tile_first_cap, size * 4 / kExpandTile + np + 2)) return rc;
-	if (int rc = ensure(ctx, s.tile_pack, s.tile_pack_cap, n_rec / kExpandTile + np + 2)) return rc;
+	if (int rc = ensure(ctx, s.tile_first, s.tile_first_cap, size * 4 / kExpandMinTile + np + 2)) return rc;
+	if (int rc = ensure(ctx, s.tile_pack, s.tile_pack_cap, n_rec / kExpandMinTile + np + 2)) return rc;
 
 	ExpandArgs a;
 	a.bin = d_bin; a.size = size; a.pack_start = s.d_pack_start; a.n_packs = np; a.k = k; a.min_rec_bytes = min_rec;
 	a.both_strands = ctx->prm.both_strands; a.n_rec = n_rec;
+	a.tile = ctx->words == 1 ? ExpandCfg<1>::kTile : ExpandCfg<2>::kTile;
 	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
 	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.status = s.zero->status;
 	a.recs = d_recs; a.hist0 = s.zero->hist[0];
@@ -473,7 +477,9 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	s.last_n_packs = np;
 
 	CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
-	walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a);
+	walk_packs_parallel_kernel<<<np, kWalkSegs, kWalkChunk + 32, st>>>(a, s.pack_done);
+	walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a, s.pack_done);
+	ctx->launches++;
 	scan_packs_kernel<<<1, 1024, 0, st>>>(a);
 	ctx->launches += 2;
 	CU(cudaGetLastError());
@@ -612,6 +618,9 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 		ctx->err = "leaf_count_kernel setup failed"; return bail(KMCB200_ERR_CUDA);
 	}
 	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
+	if (cudaFuncSetAttribute(walk_packs_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkChunk + 32) != cudaSuccess) {
+		ctx->err = "walk_packs_parallel_kernel setup failed"; return bail(KMCB200_ERR_CUDA);
+	}
 	if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(KMCB200_ERR_CUDA); }
 	for (auto& s : ctx->slots) {
 		bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -644,7 +653,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 	cudaDeviceSynchronize();
 	for (auto& s : ctx->slots) {
 		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
-				 (void*)s.pack_kbase, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
+				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
 				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off})

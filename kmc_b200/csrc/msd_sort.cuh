@@ -385,6 +385,25 @@ struct MsdBoundsArgs {
 	uint32_t* n_items;
 };
 
+// boundaries + oversize check only (any number of CTAs): used when no item table is needed
+__global__ void __launch_bounds__(256) msd_bounds_flat_kernel(const MsdBoundsArgs a)
+{
+	if (*a.flags & kMsdFlagFallback) return;
+	const uint32_t M = a.S * a.nd;
+	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m > M) return;
+	auto bound = [&](uint32_t q) -> uint64_t {
+		if (q >= M) return a.n;
+		const uint32_t seg = q / a.nd, d = q % a.nd;
+		if (a.items.item_lo) return a.cell_scan[(uint64_t)d * *a.items.n_items];
+		const uint32_t first = a.items.item_base[seg], nis = a.items.item_base[seg + 1] - first;
+		return nis ? (uint64_t)a.cell_scan[(uint64_t)a.nd * first + (uint64_t)d * nis] : a.items.seg_start[seg];
+	};
+	const uint64_t v = bound(m);
+	a.start[m] = v;
+	if (a.cap && m < M && bound(m + 1) - v > a.cap) atomicOr(a.flags, kMsdFlagFallback);
+}
+
 __global__ void __launch_bounds__(1024) msd_bounds_kernel(const MsdBoundsArgs a)
 {
 	__shared__ uint32_t s_i[32];
