@@ -66,7 +66,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -248,7 +248,6 @@ def main_ours(args, rank, world, local_rank):
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     st = ctx.stage_times(0)                      # CUDA events of the last timed step, recorded on the launching stream
     t_dev = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -288,6 +287,7 @@ def main_ours(args, rank, world, local_rank):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     t_e2e = float(t_e.item())
     e2e_value = world * n_rec * args.steps / t_e2e
+    clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions (device-resident and end-to-end)
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -337,7 +337,7 @@ def main_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-rec", type=int, default=1 << 26)
