@@ -109,7 +109,8 @@ int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, ui
 
 /* Expand + sort + count one bin that already lives in HBM.  d_superkmers must be 8-byte aligned and readable
  * up to the next multiple of 8 past size.  pack_bytes is a HOST array.  d_result receives 8 x uint64:
- * [0..3] stats, [4] emitted records, [5] capacity error flag, [6] bin-format error bits, [7] reserved. */
+ * [0..3] stats, [4] emitted records, [5] capacity error flag, [6] bin-format error bits,
+ * [7] 1 when the hybrid MSD / leaf-count path gave up (skew) and the LSD fallback produced the (identical) result. */
 int kmcb200_dev_process_bin(kmcb200_ctx* ctx, uint32_t slot,
 	const uint8_t* d_superkmers, uint64_t size, uint64_t n_rec,
 	const uint64_t* pack_bytes, uint32_t n_packs,

@@ -496,10 +496,11 @@ int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8
 	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, nullptr, st);
 }
 
-__global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uint32_t* status)
+__global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uint32_t* status, const uint32_t* msd_flags = nullptr)
 {
 	result[3] = n_rec;              // n_total = n_rec (kb_sorter.h:1166)
 	result[6] = status ? status[0] : 0;
+	result[7] = msd_flags ? msd_flags[0] : 0;       // 1: the hybrid MSD / leaf-count path gave up and the LSD fallback produced the result
 }
 
 // Expand -> Sort -> Compact on device buffers; records live in the slot workspace
@@ -569,7 +570,7 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 		const void* sorted = in_b ? s.recs_b : s.recs_a;
 		if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
 	}
-	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status);
+	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status, s.zero->msd_flags);
 	ctx->launches++;
 	CU(cudaEventRecord(s.ev_count, st));
 	s.ran_count = true;

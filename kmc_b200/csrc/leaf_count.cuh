@@ -40,6 +40,7 @@ struct LeafArgs {
 	uint32_t* flags;
 };
 
+constexpr int kLeafRoundRecords = 2560;              // records one round of a leaf is sized for
 constexpr int kLeafRetry = 2048;                    // copies of k-mers that lost their slot to another k-mer, handled in a dense second round
 constexpr int kLeafMaxEmit = kLeafSlots + kLeafSide;
 
@@ -54,7 +55,7 @@ struct LeafSmem {
 	uint32_t scnt[kLeafSide];        //  2 KB
 	uint16_t sslot[kLeafSide];       //  1 KB
 	uint16_t dense[kLeafSide];       //  1 KB   surviving side entries
-	uint16_t retry[kLeafRetry];      //  4 KB   indices (inside the leaf) of records whose slot was taken
+	uint32_t retry[kLeafRetry];      //  8 KB   indices (inside the leaf) of records whose slot was taken
 	uint16_t emit_src[kLeafMaxEmit]; //  5 KB   position -> main slot, or 0x8000 | side slot
 	uint32_t warp_tot[8];
 	uint32_t n_side, n_dense, n_allones, n_retry, leaf, total_emit;
@@ -84,7 +85,6 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 	if (*a.flags & kMsdFlagFallback) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t pad8 = (a.suffix_bytes + a.counter_bytes) > 8 ? 2u : 1u;          // temporary records: 8 or 16 bytes
-	const uint32_t slot_shift = a.low_bits > (uint32_t)kLeafSlotBits ? a.low_bits - kLeafSlotBits : 0;
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const bool one_prefix = prefix_shift >= a.low_bits;        // every k-mer of a leaf has the same LUT prefix
 	uint32_t n_unique = 0, n_min = 0, n_max = 0;
@@ -102,7 +102,16 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 		const uint64_t lo = a.start[leaf];
 		const uint32_t m = (uint32_t)(a.start[leaf + 1] - lo);
 		if (m == 0) { if (tid == 0) a.leaf_emit[leaf] = 0; continue; }
-
+		// A leaf with more records than the tables are made for (canonical k-mers crowd into the low prefixes: up to ~4x the average)
+		// is counted in 2^e rounds: round r takes the k-mers whose next e bits are r, so the rounds' outputs simply follow each other.
+		uint32_t e_bits = 0;
+		while ((m >> e_bits) > (uint32_t)kLeafRoundRecords && e_bits < 8 && e_bits < a.low_bits) ++e_bits;
+		if ((m >> e_bits) > (uint32_t)kLeafRoundRecords * 2) failed = true;
+		const uint32_t sub_shift = a.low_bits - e_bits;
+		const uint32_t slot_shift = sub_shift > (uint32_t)kLeafSlotBits ? sub_shift - kLeafSlotBits : 0;
+		uint32_t emit_base = 0;
+		for (uint32_t round = 0; round < (1u << e_bits); ++round) {
+		if (round) __syncthreads();
 		// ---- clear (16-byte stores)
 		{
 			uint4* k4 = reinterpret_cast<uint4*>(S.mkey);
@@ -130,13 +139,14 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 				const uint32_t j = j0 + u * kLeafThreads + tid;
 				if (j >= m) continue;
 				const uint64_t kk = key[u];
+				if (e_bits && ((uint32_t)(kk >> sub_shift) & ((1u << e_bits) - 1u)) != round) continue;      // another round's k-mer
 				if (kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
 				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
 				const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[b]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
 				if (old == kLeafEmpty || old == kk) atomicAdd(&S.mcnt[b], 1u);
 				else {
 					const uint32_t q = atomicAdd(&S.n_retry, 1u);
-					if (q < (uint32_t)kLeafRetry && j < 65536u) S.retry[q] = (uint16_t)j;
+					if (q < (uint32_t)kLeafRetry) S.retry[q] = j;
 					else failed = true;
 				}
 			}
@@ -269,14 +279,16 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 			const uint32_t value = c > a.counter_max ? a.counter_max : c;          // kb_sorter.h:1190
 			uint64_t rl; uint32_t rh;
 			leaf_record(kk, value, a, rl, rh);
-			tmp64[(lo + e) * pad8] = rl;
-			if (pad8 == 2) tmp64[(lo + e) * 2 + 1] = rh;
+			tmp64[(lo + emit_base + e) * pad8] = rl;
+			if (pad8 == 2) tmp64[(lo + emit_base + e) * 2 + 1] = rh;
 			if (!one_prefix) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kk >> prefix_shift), 1ull);     // kb_sorter.h:1203
 		}
+		emit_base += total_emit;
+		}      // rounds
 		if (tid == 0) {
-			a.leaf_emit[leaf] = total_emit;
-			if (one_prefix && total_emit)
-				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (((uint64_t)leaf << a.low_bits) >> prefix_shift), (unsigned long long)total_emit);
+			a.leaf_emit[leaf] = emit_base;
+			if (one_prefix && emit_base)
+				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (((uint64_t)leaf << a.low_bits) >> prefix_shift), (unsigned long long)emit_base);
 		}
 	}
 	// ---- statistics of this CTA
