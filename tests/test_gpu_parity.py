@@ -269,3 +269,17 @@ def test_skewed_keys_fall_back_to_lsd(oracle, kind):
     got = ctx.sort_records(recs, 8)
     assert np.array_equal(got, oracle.sort(recs, 8))
     ctx.close()
+
+
+def test_leaf_count_crowded_leaf_and_heavy_kmer(oracle):
+    """A leaf with far more distinct k-mers than one round of the leaf table holds (counted in several rounds), plus a k-mer
+    that occurs 50 000 times, inside a bin large enough for the hybrid MSD path."""
+    rng = np.random.default_rng(12)
+    k = 31
+    head = np.array([0, 1, 2, 3, 0, 1, 2, 3], dtype=np.uint8)                     # same first 8 symbols = same leaf (-b mode: no canonicalisation)
+    crowded = [np.concatenate([head, rng.integers(0, 4, k - 8)]) for _ in range(9000)]
+    heavy_one = np.concatenate([head[::-1], rng.integers(0, 4, k - 8)])
+    heavy = [heavy_one.copy() for _ in range(50000)]
+    rest = [rng.integers(0, 4, k + 40) for _ in range(3000)]
+    p = Params(k=k, both_strands=False, cutoff_min=1, lut_prefix_len=7)
+    _check_bin(oracle, pack_superkmers(k, crowded + heavy + rest), p)
