@@ -49,8 +49,7 @@ struct LeafSmem {
 	uint32_t mcnt[kLeafSlots];       //  8 KB   main table: multiplicities
 	uint32_t push[kLeafSlots / 4];   //  2 KB   surviving side entries that sort before the main entry of the slot, one byte each
 	uint32_t nside[kLeafSlots / 4];  //  2 KB   surviving side entries per slot, one byte each
-	uint16_t pre[kLeafSlots];        //  4 KB   position of the slot's first surviving k-mer
-	uint32_t mainpass[kLeafSlots / 32];
+	uint16_t pre[kLeafSlots];        //  4 KB   position of the slot's first surviving k-mer; bit 15: the slot's main entry survives
 	uint64_t skey[kLeafSide];        //  4 KB   side table
 	uint32_t scnt[kLeafSide];        //  2 KB
 	uint16_t sslot[kLeafSide];       //  1 KB
@@ -87,9 +86,9 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 	const uint32_t pad8 = (a.suffix_bytes + a.counter_bytes) > 8 ? 2u : 1u;          // temporary records: 8 or 16 bytes
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const bool one_prefix = prefix_shift >= a.low_bits;        // every k-mer of a leaf has the same LUT prefix
+	const bool maybe_allones = a.k == 32;
 	uint32_t n_unique = 0, n_min = 0, n_max = 0;
 	bool failed = false;
-	const uint8_t* const push8 = reinterpret_cast<const uint8_t*>(S.push);
 	const uint8_t* const nside8 = reinterpret_cast<const uint8_t*>(S.nside);
 	uint64_t* const tmp64 = reinterpret_cast<uint64_t*>(a.tmp);
 
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 				if (j >= m) continue;
 				const uint64_t kk = key[u];
 				if (e_bits && ((uint32_t)(kk >> sub_shift) & ((1u << e_bits) - 1u)) != round) continue;      // another round's k-mer
-				if (kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
+				if (maybe_allones && kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
 				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
 				const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[b]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
 				if (old == kLeafEmpty || old == kk) atomicAdd(&S.mcnt[b], 1u);
@@ -172,19 +171,7 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 		__syncthreads();
 		if (S.n_side > (uint32_t)kLeafSideMax) failed = true;
 
-		// ---- cutoffs.  Main slots striped over the threads (conflict-free): one ballot word per 32 slots says who survives.
-#pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			const uint32_t b = i * kLeafThreads + tid;
-			const uint32_t c = S.mcnt[b];
-			const uint32_t cl = leaf_class(c, a);
-			n_unique += c != 0;
-			n_min += (c != 0) & (cl == 0);
-			n_max += cl == 1;
-			const uint32_t bal = __ballot_sync(0xffffffffu, (c != 0) & (cl == 2));
-			if (lane == 0) S.mainpass[b >> 5] = bal;
-		}
-		// side entries: one or two per thread
+		// ---- side entries first (one or two per thread): cutoffs, survivors per slot, how many sort before the slot's main entry
 #pragma unroll
 		for (int i = 0; i < kLeafSide / kLeafThreads; ++i) {
 			const uint32_t h = i * kLeafThreads + tid;
@@ -203,22 +190,29 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 				}
 			}
 		}
-		uint32_t allones_cl = 0;
-		if (tid == 0 && S.n_allones) { ++n_unique; allones_cl = leaf_class(S.n_allones, a); n_min += allones_cl == 0; n_max += allones_cl == 1; }
+		if (tid == 0 && S.n_allones) { const uint32_t cl = leaf_class(S.n_allones, a); ++n_unique; n_min += cl == 0; n_max += cl == 1; }
 		__syncthreads();
 
-		// ---- exclusive prefix over the slots: thread t owns slots [8t, 8t+8): 8 ballot bits + 8 side-entry bytes
+		// ---- main slots: thread t owns the 8 consecutive slots [8t, 8t+8).  Cutoffs, survivors per slot (main + side), exclusive prefix
+		// over all slots = output position of every slot's first survivor, all in registers; one 16-byte store publishes the positions.
 		{
-			const uint32_t bits = (S.mainpass[tid >> 2] >> (8 * (tid & 3))) & 0xFFu;
-			const uint64_t spread = ((uint64_t)bits * 0x0101010101010101ull) & 0x8040201008040201ull;       // bit i -> byte i (non-zero)
-			const uint64_t mainb = ((spread + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;          // 0 / 1 per byte
-			const uint64_t v = mainb + reinterpret_cast<const uint64_t*>(S.nside)[tid];                       // survivors per slot (bytes <= 201)
-			// byte sums may exceed 255 over 8 slots only with absurd skew: use 16-bit lanes for the thread total
-			const uint32_t sum = (uint32_t)((((v & 0x00FF00FF00FF00FFull) + ((v >> 8) & 0x00FF00FF00FF00FFull)) * 0x0001000100010001ull) >> 48);
-			if (sum > 255) failed = true;
-			uint64_t x = v;
-			x += x << 8; x += x << 16; x += x << 32;               // inclusive byte prefix sums
-			uint32_t inc = sum;
+			const uint4 c0 = reinterpret_cast<const uint4*>(S.mcnt)[2 * tid], c1 = reinterpret_cast<const uint4*>(S.mcnt)[2 * tid + 1];
+			const uint32_t c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+			const uint64_t sv = reinterpret_cast<const uint64_t*>(S.nside)[tid], pv = reinterpret_cast<const uint64_t*>(S.push)[tid];
+			uint32_t passbits = 0, run = 0, pos[8];
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				const uint32_t cl = leaf_class(c[i], a);
+				const uint32_t occ = c[i] != 0;
+				n_unique += occ;
+				n_min += occ & (cl == 0);
+				n_max += cl == 1;
+				const uint32_t pass = occ & (cl == 2);
+				passbits |= pass << i;
+				pos[i] = run;
+				run += pass + (uint32_t)((sv >> (8 * i)) & 0xFF);
+			}
+			uint32_t inc = run;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
 				const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -226,42 +220,41 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 			}
 			if (lane == 31) S.warp_tot[warp] = inc;
 			__syncthreads();
-			uint32_t base = inc - sum, tot = 0;
+			uint32_t base = inc - run, tot = 0;
 #pragma unroll
 			for (int w = 0; w < 8; ++w) { const uint32_t t = S.warp_tot[w]; if ((uint32_t)w < warp) base += t; tot += t; }
-			const uint64_t excl = x - v;
+			if (tot > (uint32_t)kLeafMaxEmit) { failed = true; tot = 0; }
 			uint32_t p16[4];
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
-				const uint32_t e0 = base + (uint32_t)((excl >> (16 * q)) & 0xFF), e1 = base + (uint32_t)((excl >> (16 * q + 8)) & 0xFF);
-				p16[q] = e0 | (e1 << 16);
+				const uint32_t e0 = (base + pos[2 * q]) | (((passbits >> (2 * q)) & 1u) << 15), e1 = (base + pos[2 * q + 1]) | (((passbits >> (2 * q + 1)) & 1u) << 15);
+				p16[q] = (e0 & 0xFFFFu) | (e1 << 16);
 			}
-			reinterpret_cast<uint4*>(S.pre)[tid] = make_uint4(p16[0], p16[1], p16[2], p16[3]);
+			reinterpret_cast<uint4*>(S.pre)[tid] = make_uint4(p16[0], p16[1], p16[2], p16[3]);      // bit 15: the main entry of the slot survives
+			if (tot)
+#pragma unroll
+				for (int i = 0; i < 8; ++i)
+					if ((passbits >> i) & 1u) S.emit_src[min(base + pos[i] + (uint32_t)((pv >> (8 * i)) & 0xFF), (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)(8 * tid + i);
 			if (tid == 0) S.total_emit = tot;
 		}
 		__syncthreads();
 		const uint32_t total = S.total_emit;
-		if (total > (uint32_t)kLeafMaxEmit) failed = true;
 
-		// ---- who is at which position
-#pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			const uint32_t b = i * kLeafThreads + tid;
-			if ((S.mainpass[b >> 5] >> (b & 31)) & 1u) S.emit_src[min(S.pre[b] + push8[b], (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)b;
-		}
+		// ---- positions of the surviving side entries
 		{
 			const uint32_t n_dense = S.n_dense;
-			for (uint32_t e = tid; e < n_dense; e += kLeafThreads) {
+			for (uint32_t e = tid; e < n_dense && total; e += kLeafThreads) {
 				const uint32_t h = S.dense[e];
 				const uint64_t kk = S.skey[h];
 				const uint32_t b = S.sslot[h];
-				uint32_t r = (((S.mainpass[b >> 5] >> (b & 31)) & 1u) && S.mkey[b] < kk) ? 1u : 0u;
+				const uint32_t pb = S.pre[b];
+				uint32_t r = ((pb & 0x8000u) && S.mkey[b] < kk) ? 1u : 0u;
 				if (nside8[b] > 1)                                      // three or more k-mers in one slot: rank among the side entries
 					for (uint32_t f = 0; f < n_dense; ++f) {
 						const uint32_t h2 = S.dense[f];
 						if (S.sslot[h2] == b && S.skey[h2] < kk) ++r;
 					}
-				S.emit_src[min(S.pre[b] + r, (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)(0x8000u | h);
+				S.emit_src[min((pb & 0x7FFFu) + r, (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)(0x8000u | h);
 			}
 		}
 		__syncthreads();
