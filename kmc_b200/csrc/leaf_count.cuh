@@ -92,14 +92,19 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 	const uint8_t* const nside8 = reinterpret_cast<const uint8_t*>(S.nside);
 	uint64_t* const tmp64 = reinterpret_cast<uint64_t*>(a.tmp);
 
-	while (true) {
-		__syncthreads();
-		if (tid == 0) S.leaf = atomicAdd(a.ticket, 1u);
-		__syncthreads();
-		const uint32_t leaf = S.leaf;
-		if (leaf >= a.n_leaves) break;
-		const uint64_t lo = a.start[leaf];
-		const uint32_t m = (uint32_t)(a.start[leaf + 1] - lo);
+	// Leaves are dealt round-robin (leaf = blockIdx.x, + gridDim.x, ...): every CTA gets ~100 of them, so sizes average out, and
+	// knowing the next leaf in advance lets its boundaries be loaded and its records be pulled into L2 while the current one is counted.
+	uint32_t leaf = blockIdx.x;
+	uint64_t lo = 0, hi = 0;
+	if (leaf < a.n_leaves) { lo = a.start[leaf]; hi = a.start[leaf + 1]; }
+	for (; leaf < a.n_leaves; leaf += gridDim.x) {
+		const uint32_t m = (uint32_t)(hi - lo);
+		const uint64_t cur_lo = lo;
+		{       // next leaf of this CTA: boundaries now, L2 prefetch of its records a little later
+			const uint32_t nl = leaf + gridDim.x;
+			if (nl < a.n_leaves) { lo = a.start[nl]; hi = a.start[nl + 1]; }
+		}
+		__syncthreads();          // the previous leaf is completely done with the tables
 		if (m == 0) { if (tid == 0) a.leaf_emit[leaf] = 0; continue; }
 		// A leaf with more records than the tables are made for (canonical k-mers crowd into the low prefixes: up to ~4x the average)
 		// is counted in 2^e rounds: round r takes the k-mers whose next e bits are r, so the rounds' outputs simply follow each other.
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 		for (uint32_t j0 = 0; j0 < m; j0 += 4 * kLeafThreads) {
 			uint64_t key[4];
 #pragma unroll
-			for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * kLeafThreads + tid; key[u] = j < m ? a.recs[lo + j] : 0; }
+			for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * kLeafThreads + tid; key[u] = j < m ? a.recs[cur_lo + j] : 0; }
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				const uint32_t j = j0 + u * kLeafThreads + tid;
@@ -150,12 +155,16 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 				}
 			}
 		}
+		if (round == 0 && leaf + gridDim.x < a.n_leaves) {        // pull the next leaf towards L2 (128 bytes per thread and step)
+			const uint32_t nm = (uint32_t)(hi - lo);
+			for (uint32_t i = tid * 16; i < nm; i += kLeafThreads * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.recs + lo + i));
+		}
 		__syncthreads();
 		// ---- count, round 2 (dense): the noted records go to the side table (open addressing)
 		{
 			const uint32_t nr = min(S.n_retry, (uint32_t)kLeafRetry);
 			for (uint32_t q = tid; q < nr; q += kLeafThreads) {
-				const uint64_t kk = a.recs[lo + S.retry[q]];
+				const uint64_t kk = a.recs[cur_lo + S.retry[q]];
 				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
 				uint32_t h = (uint32_t)((kk * 0x9E3779B97F4A7C15ull) >> 55) & (kLeafSide - 1);
 				int probe = 0;
@@ -272,8 +281,8 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 			const uint32_t value = c > a.counter_max ? a.counter_max : c;          // kb_sorter.h:1190
 			uint64_t rl; uint32_t rh;
 			leaf_record(kk, value, a, rl, rh);
-			tmp64[(lo + emit_base + e) * pad8] = rl;
-			if (pad8 == 2) tmp64[(lo + emit_base + e) * 2 + 1] = rh;
+			tmp64[(cur_lo + emit_base + e) * pad8] = rl;
+			if (pad8 == 2) tmp64[(cur_lo + emit_base + e) * 2 + 1] = rh;
 			if (!one_prefix) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kk >> prefix_shift), 1ull);     // kb_sorter.h:1203
 		}
 		emit_base += total_emit;
