@@ -102,10 +102,14 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const R* __restrict__ g = reinterpret_cast<const R*>(a.recs);
 
+	// persistent CTAs: tiles are claimed from a ticket (the chained scan needs them started in order)
+	for (;;) {
+	__syncthreads();
 	if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
 	for (int i = tid; i < kLutWindow; i += THREADS) lutwin[i] = 0;
 	__syncthreads();
 	const uint32_t tile = s_tile;
+	if (tile >= a.n_tiles) break;
 	const uint64_t first = (uint64_t)tile * TILE;
 	const uint64_t rem = a.n - first;
 	const uint32_t cnt = rem < (uint64_t)TILE ? (uint32_t)rem : (uint32_t)TILE;
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 		const uint32_t c = lutwin[i];
 		if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + pfx0 + i, (unsigned long long)c);
 	}
+	}      // tiles
 }
 
 }  // namespace kmcb

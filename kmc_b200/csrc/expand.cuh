@@ -271,9 +271,10 @@ __device__ __forceinline__ uint64_t rev_symbols64(uint64_t x)
 	return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
 }
 
-// k-mer number `s` of the super-k-mer whose packed symbols start at global byte address `payload`
-template <int WORDS>
-__device__ __forceinline__ Rec<WORDS> extract_kmer(const uint8_t* payload, uint32_t s, uint32_t k, bool canonical)
+// k-mer number `s` of the super-k-mer whose packed symbols start at global byte address `payload`.
+// `load8(addr)` returns the 8 bytes at the 8-byte aligned absolute address addr (from global memory, or from a staged copy).
+template <int WORDS, typename Load8>
+__device__ __forceinline__ Rec<WORDS> extract_kmer(const uint8_t* payload, uint32_t s, uint32_t k, bool canonical, Load8 load8)
 {
 	const uint8_t* A = payload + (s >> 2);
 	const uint32_t sh = (s & 3u) * 2u;
@@ -284,7 +285,7 @@ __device__ __forceinline__ Rec<WORDS> extract_kmer(const uint8_t* payload, uint3
 #pragma unroll
 	for (int i = 0; i <= WORDS; ++i) {
 		const uintptr_t wa = a0 + 8u * i;
-		b[i] = wa < need_end ? bswap64(__ldg(reinterpret_cast<const unsigned long long*>(wa))) : 0ull;
+		b[i] = wa < need_end ? bswap64(load8(wa)) : 0ull;
 	}
 	// t = the WORDS-word big number (t[0] most significant) holding bits [bo, bo + 64*WORDS)
 	uint64_t t[WORDS];
@@ -336,8 +337,12 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 {
 	constexpr int kExpandTile = ExpandCfg<WORDS>::kTile, kExpandThreads = ExpandCfg<WORDS>::kThreads;
 	constexpr int IPT = kExpandTile / kExpandThreads;    // 8
+	constexpr int MAXSK = 1024, STAGE = 12288;          // per-tile staging of the super-k-mer index and bytes (typical tile: ~350 super-k-mers, ~4.5 KB)
 	__shared__ uint16_t head[kExpandTile];
 	__shared__ uint32_t warp_max[kExpandThreads / 32];
+	__shared__ uint32_t s_kpre[MAXSK], s_off[MAXSK];
+	__shared__ __align__(16) uint8_t s_bytes[STAGE];
+	__shared__ uint32_t s_jmax;
 	__shared__ uint32_t hist[256], htop[256];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid < 256) { hist[tid] = 0; htop[tid] = 0; }
@@ -360,14 +365,30 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 		__syncthreads();      // previous tile is done with head[]
 #pragma unroll
 		for (int i = 0; i < IPT; ++i) head[i * kExpandThreads + tid] = 0;
+		if (tid == 0) s_jmax = j_lo;
 		__syncthreads();
-		// head flags: super-k-mer j_lo + r starts at output slot kpre - tile_start
-		for (uint32_t j = j_lo + 1 + tid; j < nsk; j += kExpandThreads) {
-			const uint32_t kp = kpre[j];
-			if (kp >= tile_start + cnt) break;
-			head[kp - tile_start] = (uint16_t)(j - j_lo);
+		// head flags: super-k-mer j_lo + r starts at output slot kpre - tile_start; its index entry is staged in shared memory
+		{
+			uint32_t jm = j_lo;
+			for (uint32_t j = j_lo + tid; j < nsk; j += kExpandThreads) {
+				const uint32_t kp = kpre[j];
+				if (j > j_lo && kp >= tile_start + cnt) break;
+				const uint32_t rel = j - j_lo;
+				if (rel < (uint32_t)MAXSK) { s_kpre[rel] = kp; s_off[rel] = off[j]; }
+				if (j > j_lo) head[kp - tile_start] = (uint16_t)rel;
+				jm = j;
+			}
+			if (jm > j_lo) atomicMax(&s_jmax, jm);
 		}
 		__syncthreads();
+		// stage the tile's bytes of the bin (contiguous: from its first super-k-mer to the end of its last one) when they fit
+		const uint32_t j_hi = s_jmax;
+		const uint64_t b_lo = off[j_lo], b_hi = j_hi + 1 < nsk ? (uint64_t)off[j_hi + 1] : a.pack_start[p + 1];
+		const uintptr_t g0a = reinterpret_cast<uintptr_t>(a.bin + b_lo) & ~(uintptr_t)15;
+		const uint64_t span = reinterpret_cast<uintptr_t>(a.bin + b_hi) - g0a;
+		const bool staged = (j_hi - j_lo) < (uint32_t)MAXSK && span + 16 <= (uint64_t)STAGE;
+		if (staged)
+			for (uint32_t v = tid; v * 16 < span + 8; v += kExpandThreads) reinterpret_cast<uint4*>(s_bytes)[v] = __ldg(reinterpret_cast<const uint4*>(g0a) + v);
 		// inclusive max-scan (blocked: 8 consecutive slots per thread)
 		uint32_t v[IPT];
 		uint32_t m = 0;
@@ -397,9 +418,18 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 		for (int i = 0; i < IPT; ++i) {
 			const uint32_t slot = i * kExpandThreads + tid;
 			if (slot < cnt) {
-				const uint32_t j = j_lo + head[slot];
-				const uint32_t s = tile_start + slot - kpre[j];
-				const Rec<WORDS> r = extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0);
+				const uint32_t rel = head[slot];
+				Rec<WORDS> r;
+				if (staged) {
+					const uint32_t s = tile_start + slot - s_kpre[rel];
+					r = extract_kmer<WORDS>(a.bin + s_off[rel] + 1, s, a.k, a.both_strands != 0,
+						[&](uintptr_t wa) { return *reinterpret_cast<const unsigned long long*>(s_bytes + (wa - g0a)); });
+				} else {
+					const uint32_t j = j_lo + rel;
+					const uint32_t s = tile_start + slot - kpre[j];
+					r = extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0,
+						[](uintptr_t wa) { return __ldg(reinterpret_cast<const unsigned long long*>(wa)); });
+				}
 				out[obase + slot] = r;
 				atomicAdd(&hist[(uint32_t)r.w[0] & 0xFFu], 1u);
 				atomicAdd(&htop[rec_top_digit<WORDS>(r, a.top_shift)], 1u);

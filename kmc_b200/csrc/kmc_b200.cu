@@ -395,7 +395,7 @@ int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint
 	a.desc = s.cdesc; a.epoch = next_epoch(ctx); a.tile_counter = &s.zero->counters[kMaxPasses];
 	a.run_flag = run_flag;
 	const size_t smem = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
-	count_emit_kernel<WORDS><<<n_tiles, CountCfg<WORDS>::kThreads, smem, st>>>(a);
+	count_emit_kernel<WORDS><<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 6), CountCfg<WORDS>::kThreads, smem, st>>>(a);
 	ctx->launches++;
 	CU(cudaGetLastError());
 	return 0;

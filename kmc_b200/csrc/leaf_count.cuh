@@ -308,36 +308,32 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 	}
 }
 
-// exclusive scan of the per-leaf record counts (single CTA), total -> result[4]
+// exclusive scan of the per-leaf record counts (single CTA, every thread owns up to 64 consecutive leaves), total -> result[4]
 __global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_emit, uint32_t n_leaves, uint64_t* leaf_off, uint64_t* result, uint64_t out_capacity, uint32_t ob, const uint32_t* flags)
 {
 	__shared__ uint64_t s_w[32];
-	__shared__ uint64_t carry;
 	if (*flags & kMsdFlagFallback) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) carry = 0;
-	__syncthreads();
-	for (uint32_t b0 = 0; b0 < n_leaves; b0 += 1024) {
-		const uint32_t i = b0 + tid;
-		const uint64_t v = i < n_leaves ? leaf_emit[i] : 0;
-		uint64_t inc = v;
+	const uint32_t per = (n_leaves + 1023) / 1024;          // <= 64
+	const uint32_t i0 = tid * per;
+	uint64_t sum = 0;
+	for (uint32_t i = 0; i < per; ++i) sum += (i0 + i < n_leaves) ? leaf_emit[i0 + i] : 0u;
+	uint64_t inc = sum;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= (uint32_t)o) inc += t;
-		}
-		if (lane == 31) s_w[warp] = inc;
-		__syncthreads();
-		uint64_t base = carry;
-		for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
-		if (i < n_leaves) leaf_off[i] = base + inc - v;
-		__syncthreads();
-		if (tid == 1023) carry = base + inc;
-		__syncthreads();
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= (uint32_t)o) inc += t;
+	}
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads();
+	uint64_t base = inc - sum, tot = 0;
+	for (uint32_t w = 0; w < 32; ++w) { if (w < warp) base += s_w[w]; tot += s_w[w]; }
+	for (uint32_t i = 0; i < per; ++i) {
+		if (i0 + i < n_leaves) { leaf_off[i0 + i] = base; base += leaf_emit[i0 + i]; }
 	}
 	if (tid == 0) {
-		result[4] = carry;
-		if (carry * ob > out_capacity) result[5] = 1;
+		result[4] = tot;
+		if (tot * ob > out_capacity) result[5] = 1;
 	}
 }
 
