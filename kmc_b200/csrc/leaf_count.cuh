@@ -42,22 +42,25 @@ struct LeafArgs {
 
 constexpr int kLeafRoundRecords = 2560;              // records one round of a leaf is sized for
 constexpr int kLeafRetry = 2048;                    // copies of k-mers that lost their slot to another k-mer, handled in a dense second round
-constexpr int kLeafMaxEmit = kLeafSlots + kLeafSide;
+constexpr int kLeafWords = kLeafSlots / 32;
 
+// Everything after the counting works on DENSE lists (occupied main slots, side entries, survivors): only ~15 % of the slots
+// are occupied and ~3 % of the records end up in the output, and a warp that sweeps all slots or carries a rare path for one
+// active lane pays the full instruction count anyway.
 struct LeafSmem {
 	uint64_t mkey[kLeafSlots];       // 16 KB   main table: k-mers
 	uint32_t mcnt[kLeafSlots];       //  8 KB   main table: multiplicities
-	uint32_t push[kLeafSlots / 4];   //  2 KB   surviving side entries that sort before the main entry of the slot, one byte each
-	uint32_t nside[kLeafSlots / 4];  //  2 KB   surviving side entries per slot, one byte each
-	uint16_t pre[kLeafSlots];        //  4 KB   position of the slot's first surviving k-mer; bit 15: the slot's main entry survives
-	uint64_t skey[kLeafSide];        //  4 KB   side table
+	uint16_t occ[kLeafSlots];        //  4 KB   occupied main slots, in order of arrival
+	uint32_t surv[kLeafWords];       //         bitmap: the slot's main entry survives the cutoffs
+	uint32_t sidew[kLeafWords];      //         surviving side entries per 32 slots
+	uint32_t wpre[kLeafWords];       //         exclusive prefix of popc(surv) + sidew = position of the word's first survivor
+	uint64_t skey[kLeafSide];        //  4 KB   side table (open addressing)
 	uint32_t scnt[kLeafSide];        //  2 KB
-	uint16_t sslot[kLeafSide];       //  1 KB
+	uint16_t sslot[kLeafSide];       //  1 KB   main slot the side entry belongs to
+	uint16_t socc[kLeafSide];        //  1 KB   occupied side slots
 	uint16_t dense[kLeafSide];       //  1 KB   surviving side entries
 	uint32_t retry[kLeafRetry];      //  8 KB   indices (inside the leaf) of records whose slot was taken
-	uint16_t emit_src[kLeafMaxEmit]; //  5 KB   position -> main slot, or 0x8000 | side slot
-	uint32_t warp_tot[8];
-	uint32_t n_side, n_dense, n_allones, n_retry, leaf, total_emit;
+	uint32_t n_occ, n_side, n_dense, n_allones, n_retry, total_emit;
 };
 
 // record image: (k-p)/4 suffix bytes most significant first, then the counter least significant first (kb_sorter.h:1198-1201),
@@ -82,14 +85,13 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 	extern __shared__ __align__(16) uint8_t dsm[];
 	LeafSmem& S = *reinterpret_cast<LeafSmem*>(dsm);
 	if (*a.flags & kMsdFlagFallback) return;
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
 	const uint32_t pad8 = (a.suffix_bytes + a.counter_bytes) > 8 ? 2u : 1u;          // temporary records: 8 or 16 bytes
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const bool one_prefix = prefix_shift >= a.low_bits;        // every k-mer of a leaf has the same LUT prefix
 	const bool maybe_allones = a.k == 32;
 	uint32_t n_unique = 0, n_min = 0, n_max = 0;
 	bool failed = false;
-	const uint8_t* const nside8 = reinterpret_cast<const uint8_t*>(S.nside);
 	uint64_t* const tmp64 = reinterpret_cast<uint64_t*>(a.tmp);
 
 	// Leaves are dealt round-robin (leaf = blockIdx.x, + gridDim.x, ...): every CTA gets ~100 of them, so sizes average out, and
@@ -100,11 +102,10 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 	for (; leaf < a.n_leaves; leaf += gridDim.x) {
 		const uint32_t m = (uint32_t)(hi - lo);
 		const uint64_t cur_lo = lo;
-		{       // next leaf of this CTA: boundaries now, L2 prefetch of its records a little later
+		{
 			const uint32_t nl = leaf + gridDim.x;
 			if (nl < a.n_leaves) { lo = a.start[nl]; hi = a.start[nl + 1]; }
 		}
-		__syncthreads();          // the previous leaf is completely done with the tables
 		if (m == 0) { if (tid == 0) a.leaf_emit[leaf] = 0; continue; }
 		// A leaf with more records than the tables are made for (canonical k-mers crowd into the low prefixes: up to ~4x the average)
 		// is counted in 2^e rounds: round r takes the k-mers whose next e bits are r, so the rounds' outputs simply follow each other.
@@ -115,177 +116,160 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 		const uint32_t slot_shift = sub_shift > (uint32_t)kLeafSlotBits ? sub_shift - kLeafSlotBits : 0;
 		uint32_t emit_base = 0;
 		for (uint32_t round = 0; round < (1u << e_bits); ++round) {
-		if (round) __syncthreads();
-		// ---- clear (16-byte stores)
-		{
-			uint4* k4 = reinterpret_cast<uint4*>(S.mkey);
-			const uint4 e = make_uint4(~0u, ~0u, ~0u, ~0u), z = make_uint4(0, 0, 0, 0);
+			__syncthreads();          // the previous leaf / round is completely done with the tables
+			// ---- clear (16-byte stores)
+			{
+				uint4* k4 = reinterpret_cast<uint4*>(S.mkey);
+				const uint4 e = make_uint4(~0u, ~0u, ~0u, ~0u), z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-			for (int i = 0; i < kLeafSlots * 8 / 16 / kLeafThreads; ++i) k4[i * kLeafThreads + tid] = e;
-			uint4* c4 = reinterpret_cast<uint4*>(S.mcnt);
+				for (int i = 0; i < kLeafSlots * 8 / 16 / kLeafThreads; ++i) k4[i * kLeafThreads + tid] = e;
+				uint4* c4 = reinterpret_cast<uint4*>(S.mcnt);
 #pragma unroll
-			for (int i = 0; i < kLeafSlots * 4 / 16 / kLeafThreads; ++i) c4[i * kLeafThreads + tid] = z;
-			reinterpret_cast<uint4*>(S.skey)[tid] = e;                                  // 512 * 8 B = 256 * 16 B
-			reinterpret_cast<uint2*>(S.scnt)[tid] = make_uint2(0, 0);
-			reinterpret_cast<uint2*>(S.push)[tid] = make_uint2(0, 0);
-			reinterpret_cast<uint2*>(S.nside)[tid] = make_uint2(0, 0);
-			if (tid == 0) { S.n_side = 0; S.n_dense = 0; S.n_allones = 0; S.n_retry = 0; }
-		}
-		__syncthreads();
+				for (int i = 0; i < kLeafSlots * 4 / 16 / kLeafThreads; ++i) c4[i * kLeafThreads + tid] = z;
+				reinterpret_cast<uint4*>(S.skey)[tid] = e;                                  // 512 * 8 B = 256 * 16 B
+				reinterpret_cast<uint2*>(S.scnt)[tid] = make_uint2(0, 0);
+				if (tid < kLeafWords) { S.surv[tid] = 0; S.sidew[tid] = 0; }
+				if (tid == 0) { S.n_occ = 0; S.n_side = 0; S.n_dense = 0; S.n_allones = 0; S.n_retry = 0; }
+			}
+			__syncthreads();
 
-		// ---- count, round 1: slot = next 11 bits of the k-mer; a record whose slot belongs to another k-mer is only noted down
-		for (uint32_t j0 = 0; j0 < m; j0 += 4 * kLeafThreads) {
-			uint64_t key[4];
+			// ---- count, round 1: slot = next 11 bits of the k-mer.  First arrival claims the slot (and notes it in the occupied list),
+			// copies add one, a record whose slot belongs to another k-mer is only noted down.
+			for (uint32_t j0 = 0; j0 < m; j0 += 4 * kLeafThreads) {
+				uint64_t key[4];
 #pragma unroll
-			for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * kLeafThreads + tid; key[u] = j < m ? a.recs[cur_lo + j] : 0; }
+				for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * kLeafThreads + tid; key[u] = j < m ? a.recs[cur_lo + j] : 0; }
 #pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				const uint32_t j = j0 + u * kLeafThreads + tid;
-				if (j >= m) continue;
-				const uint64_t kk = key[u];
-				if (e_bits && ((uint32_t)(kk >> sub_shift) & ((1u << e_bits) - 1u)) != round) continue;      // another round's k-mer
-				if (maybe_allones && kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
-				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
-				const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[b]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
-				if (old == kLeafEmpty || old == kk) atomicAdd(&S.mcnt[b], 1u);
-				else {
-					const uint32_t q = atomicAdd(&S.n_retry, 1u);
-					if (q < (uint32_t)kLeafRetry) S.retry[q] = j;
-					else failed = true;
+				for (int u = 0; u < 4; ++u) {
+					const uint32_t j = j0 + u * kLeafThreads + tid;
+					if (j >= m) continue;
+					const uint64_t kk = key[u];
+					if (e_bits && ((uint32_t)(kk >> sub_shift) & ((1u << e_bits) - 1u)) != round) continue;      // another round's k-mer
+					if (maybe_allones && kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
+					const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
+					const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[b]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
+					if (old == kLeafEmpty) S.occ[atomicAdd(&S.n_occ, 1u)] = (uint16_t)b;
+					if (old == kLeafEmpty || old == kk) atomicAdd(&S.mcnt[b], 1u);
+					else {
+						const uint32_t q = atomicAdd(&S.n_retry, 1u);
+						if (q < (uint32_t)kLeafRetry) S.retry[q] = j;
+						else failed = true;
+					}
 				}
 			}
-		}
-		if (round == 0 && leaf + gridDim.x < a.n_leaves) {        // pull the next leaf towards L2 (128 bytes per thread and step)
-			const uint32_t nm = (uint32_t)(hi - lo);
-			for (uint32_t i = tid * 16; i < nm; i += kLeafThreads * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.recs + lo + i));
-		}
-		__syncthreads();
-		// ---- count, round 2 (dense): the noted records go to the side table (open addressing)
-		{
-			const uint32_t nr = min(S.n_retry, (uint32_t)kLeafRetry);
-			for (uint32_t q = tid; q < nr; q += kLeafThreads) {
-				const uint64_t kk = a.recs[cur_lo + S.retry[q]];
-				const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
-				uint32_t h = (uint32_t)((kk * 0x9E3779B97F4A7C15ull) >> 55) & (kLeafSide - 1);
-				int probe = 0;
-				for (; probe < kLeafSide; ++probe) {
-					const unsigned long long o2 = atomicCAS(reinterpret_cast<unsigned long long*>(&S.skey[h]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
-					if (o2 == kLeafEmpty) { S.sslot[h] = (uint16_t)b; atomicAdd(&S.n_side, 1u); }
-					if (o2 == kLeafEmpty || o2 == kk) { atomicAdd(&S.scnt[h], 1u); break; }
-					h = (h + 1) & (kLeafSide - 1);
-				}
-				if (probe == kLeafSide) failed = true;
+			if (round == 0 && leaf + gridDim.x < a.n_leaves) {        // pull the next leaf towards L2 (128 bytes per thread and step)
+				const uint32_t nm = (uint32_t)(hi - lo);
+				for (uint32_t i = tid * 16; i < nm; i += kLeafThreads * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.recs + lo + i));
 			}
-		}
-		__syncthreads();
-		if (S.n_side > (uint32_t)kLeafSideMax) failed = true;
+			__syncthreads();
+			// ---- count, round 2 (dense): the noted records go to the side table
+			{
+				const uint32_t nr = min(S.n_retry, (uint32_t)kLeafRetry);
+				for (uint32_t q = tid; q < nr; q += kLeafThreads) {
+					const uint64_t kk = a.recs[cur_lo + S.retry[q]];
+					const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
+					uint32_t h = (uint32_t)((kk * 0x9E3779B97F4A7C15ull) >> 55) & (kLeafSide - 1);
+					int probe = 0;
+					for (; probe < kLeafSide; ++probe) {
+						const unsigned long long o2 = atomicCAS(reinterpret_cast<unsigned long long*>(&S.skey[h]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
+						if (o2 == kLeafEmpty) {
+							S.sslot[h] = (uint16_t)b;
+							const uint32_t i = atomicAdd(&S.n_side, 1u);
+							if (i < (uint32_t)kLeafSide) S.socc[i] = (uint16_t)h;
+						}
+						if (o2 == kLeafEmpty || o2 == kk) { atomicAdd(&S.scnt[h], 1u); break; }
+						h = (h + 1) & (kLeafSide - 1);
+					}
+					if (probe == kLeafSide) failed = true;
+				}
+			}
+			__syncthreads();
+			const uint32_t n_occ = S.n_occ, n_side = min(S.n_side, (uint32_t)kLeafSide);
+			if (S.n_side > (uint32_t)kLeafSideMax) failed = true;
 
-		// ---- side entries first (one or two per thread): cutoffs, survivors per slot, how many sort before the slot's main entry
-#pragma unroll
-		for (int i = 0; i < kLeafSide / kLeafThreads; ++i) {
-			const uint32_t h = i * kLeafThreads + tid;
-			const uint64_t kk = S.skey[h];
-			if (kk != kLeafEmpty) {
-				++n_unique;
+			// ---- cutoffs (dense): survivors of the main table as a bitmap, surviving side entries as a list + a count per 32 slots
+			for (uint32_t q = tid; q < n_occ; q += kLeafThreads) {
+				const uint32_t b = S.occ[q];
+				const uint32_t cl = leaf_class(S.mcnt[b], a);
+				n_min += cl == 0;
+				n_max += cl == 1;
+				if (cl == 2) atomicOr(&S.surv[b >> 5], 1u << (b & 31));
+			}
+			for (uint32_t q = tid; q < n_side; q += kLeafThreads) {
+				const uint32_t h = S.socc[q];
 				const uint32_t cl = leaf_class(S.scnt[h], a);
 				n_min += cl == 0;
 				n_max += cl == 1;
 				if (cl == 2) {
 					S.dense[atomicAdd(&S.n_dense, 1u)] = (uint16_t)h;
-					const uint32_t b = S.sslot[h];
-					const uint32_t before = atomicAdd(&S.nside[b >> 2], 1u << (8 * (b & 3)));
-					if (((before >> (8 * (b & 3))) & 0xFFu) >= 200u) failed = true;        // byte counters: absurdly many k-mers share 11 bits
-					if (kk < S.mkey[b]) atomicAdd(&S.push[b >> 2], 1u << (8 * (b & 3)));
+					atomicAdd(&S.sidew[S.sslot[h] >> 5], 1u);
 				}
 			}
-		}
-		if (tid == 0 && S.n_allones) { const uint32_t cl = leaf_class(S.n_allones, a); ++n_unique; n_min += cl == 0; n_max += cl == 1; }
-		__syncthreads();
-
-		// ---- main slots: thread t owns the 8 consecutive slots [8t, 8t+8).  Cutoffs, survivors per slot (main + side), exclusive prefix
-		// over all slots = output position of every slot's first survivor, all in registers; one 16-byte store publishes the positions.
-		{
-			const uint4 c0 = reinterpret_cast<const uint4*>(S.mcnt)[2 * tid], c1 = reinterpret_cast<const uint4*>(S.mcnt)[2 * tid + 1];
-			const uint32_t c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-			const uint64_t sv = reinterpret_cast<const uint64_t*>(S.nside)[tid], pv = reinterpret_cast<const uint64_t*>(S.push)[tid];
-			uint32_t passbits = 0, run = 0, pos[8];
-#pragma unroll
-			for (int i = 0; i < 8; ++i) {
-				const uint32_t cl = leaf_class(c[i], a);
-				const uint32_t occ = c[i] != 0;
-				n_unique += occ;
-				n_min += occ & (cl == 0);
-				n_max += cl == 1;
-				const uint32_t pass = occ & (cl == 2);
-				passbits |= pass << i;
-				pos[i] = run;
-				run += pass + (uint32_t)((sv >> (8 * i)) & 0xFF);
+			if (tid == 0) {
+				n_unique += n_occ + n_side;
+				if (S.n_allones) { const uint32_t cl = leaf_class(S.n_allones, a); ++n_unique; n_min += cl == 0; n_max += cl == 1; }
 			}
-			uint32_t inc = run;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-				if (lane >= (uint32_t)o) inc += t;
-			}
-			if (lane == 31) S.warp_tot[warp] = inc;
 			__syncthreads();
-			uint32_t base = inc - run, tot = 0;
-#pragma unroll
-			for (int w = 0; w < 8; ++w) { const uint32_t t = S.warp_tot[w]; if ((uint32_t)w < warp) base += t; tot += t; }
-			if (tot > (uint32_t)kLeafMaxEmit) { failed = true; tot = 0; }
-			uint32_t p16[4];
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				const uint32_t e0 = (base + pos[2 * q]) | (((passbits >> (2 * q)) & 1u) << 15), e1 = (base + pos[2 * q + 1]) | (((passbits >> (2 * q + 1)) & 1u) << 15);
-				p16[q] = (e0 & 0xFFFFu) | (e1 << 16);
-			}
-			reinterpret_cast<uint4*>(S.pre)[tid] = make_uint4(p16[0], p16[1], p16[2], p16[3]);      // bit 15: the main entry of the slot survives
-			if (tot)
-#pragma unroll
-				for (int i = 0; i < 8; ++i)
-					if ((passbits >> i) & 1u) S.emit_src[min(base + pos[i] + (uint32_t)((pv >> (8 * i)) & 0xFF), (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)(8 * tid + i);
-			if (tid == 0) S.total_emit = tot;
-		}
-		__syncthreads();
-		const uint32_t total = S.total_emit;
 
-		// ---- positions of the surviving side entries
-		{
+			// ---- exclusive prefix over the 64 bitmap words (two warps)
+			if (tid < kLeafWords) {
+				const uint32_t v = __popc(S.surv[tid]) + S.sidew[tid];
+				uint32_t inc = v;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+					if (lane >= (uint32_t)o) inc += t;
+				}
+				S.wpre[tid] = inc - v;                       // per-warp exclusive prefix; the second warp adds the first warp's total below
+				if (tid == 31) S.total_emit = inc;
+				__syncwarp();
+			}
+			__syncthreads();
+			if (tid >= 32 && tid < kLeafWords) S.wpre[tid] += S.total_emit;
+			__syncthreads();
 			const uint32_t n_dense = S.n_dense;
-			for (uint32_t e = tid; e < n_dense && total; e += kLeafThreads) {
-				const uint32_t h = S.dense[e];
-				const uint64_t kk = S.skey[h];
-				const uint32_t b = S.sslot[h];
-				const uint32_t pb = S.pre[b];
-				uint32_t r = ((pb & 0x8000u) && S.mkey[b] < kk) ? 1u : 0u;
-				if (nside8[b] > 1)                                      // three or more k-mers in one slot: rank among the side entries
-					for (uint32_t f = 0; f < n_dense; ++f) {
-						const uint32_t h2 = S.dense[f];
-						if (S.sslot[h2] == b && S.skey[h2] < kk) ++r;
-					}
-				S.emit_src[min((pb & 0x7FFFu) + r, (uint32_t)kLeafMaxEmit - 1)] = (uint16_t)(0x8000u | h);
-			}
-		}
-		__syncthreads();
+			const uint32_t total = S.wpre[kLeafWords - 1] + __popc(S.surv[kLeafWords - 1]) + S.sidew[kLeafWords - 1];
+			const uint32_t allones_emit = (S.n_allones && leaf_class(S.n_allones, a) == 2) ? 1u : 0u;
 
-		// ---- dense emission: one thread per surviving k-mer, one aligned 8-byte store each into the leaf's region of the temporary buffer
-		const uint32_t allones_emit = (S.n_allones && leaf_class(S.n_allones, a) == 2) ? 1u : 0u;
-		const uint32_t total_emit = total + allones_emit;
-		for (uint32_t e = tid; e < total_emit && !failed; e += kLeafThreads) {
-			uint64_t kk; uint32_t c;
-			if (e < total) {
-				const uint32_t src = S.emit_src[e];
-				if (src & 0x8000u) { kk = S.skey[src & 0x7FFFu]; c = S.scnt[src & 0x7FFFu]; }
-				else { kk = S.mkey[src]; c = S.mcnt[src]; }
-			} else { kk = kLeafEmpty; c = S.n_allones; }
-			const uint32_t value = c > a.counter_max ? a.counter_max : c;          // kb_sorter.h:1190
-			uint64_t rl; uint32_t rh;
-			leaf_record(kk, value, a, rl, rh);
-			tmp64[(cur_lo + emit_base + e) * pad8] = rl;
-			if (pad8 == 2) tmp64[(cur_lo + emit_base + e) * 2 + 1] = rh;
-			if (!one_prefix) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kk >> prefix_shift), 1ull);     // kb_sorter.h:1203
-		}
-		emit_base += total_emit;
+			// ---- emission (dense): every survivor computes its own position and stores its record (one aligned 8-byte store)
+			auto emit = [&](uint32_t pos, uint64_t kk, uint32_t c) {
+				const uint32_t value = c > a.counter_max ? a.counter_max : c;          // kb_sorter.h:1190
+				uint64_t rl; uint32_t rh;
+				leaf_record(kk, value, a, rl, rh);
+				tmp64[(cur_lo + emit_base + pos) * pad8] = rl;
+				if (pad8 == 2) tmp64[(cur_lo + emit_base + pos) * 2 + 1] = rh;
+				if (!one_prefix) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (kk >> prefix_shift), 1ull);     // kb_sorter.h:1203
+			};
+			if (!failed) {
+				for (uint32_t q = tid; q < n_occ; q += kLeafThreads) {
+					const uint32_t b = S.occ[q], w = b >> 5;
+					const uint32_t bits = S.surv[w];
+					if (!((bits >> (b & 31)) & 1u)) continue;
+					const uint64_t kk = S.mkey[b];
+					uint32_t pos = S.wpre[w] + __popc(bits & ((1u << (b & 31)) - 1u));
+					if (S.sidew[w])                               // surviving side entries in this word: those that sort before this k-mer
+						for (uint32_t f = 0; f < n_dense; ++f) {
+							const uint32_t h2 = S.dense[f], b2 = S.sslot[h2];
+							if ((b2 >> 5) == w && (b2 < b || (b2 == b && S.skey[h2] < kk))) ++pos;
+						}
+					emit(pos, kk, S.mcnt[b]);
+				}
+				for (uint32_t e = tid; e < n_dense; e += kLeafThreads) {
+					const uint32_t h = S.dense[e], b = S.sslot[h], w = b >> 5;
+					const uint64_t kk = S.skey[h];
+					const uint32_t bits = S.surv[w];
+					uint32_t pos = S.wpre[w] + __popc(bits & ((1u << (b & 31)) - 1u));
+					if (((bits >> (b & 31)) & 1u) && S.mkey[b] < kk) ++pos;          // the main entry of the own slot
+					if (S.sidew[w] > 1)
+						for (uint32_t f = 0; f < n_dense; ++f) {
+							const uint32_t h2 = S.dense[f], b2 = S.sslot[h2];
+							if ((b2 >> 5) == w && (b2 < b || (b2 == b && S.skey[h2] < kk))) ++pos;
+						}
+					emit(pos, kk, S.scnt[h]);
+				}
+				if (tid == 0 && allones_emit) emit(total, kLeafEmpty, S.n_allones);
+			}
+			emit_base += total + allones_emit;
 		}      // rounds
 		if (tid == 0) {
 			a.leaf_emit[leaf] = emit_base;
