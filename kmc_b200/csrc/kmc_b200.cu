@@ -319,6 +319,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			ctx->launches += 2;
 		}
 		if (int rc = launch_cell_scan(ctx, s, items1.n_items, 256, max_items1, never, st)) return rc;
+		s.pass_names[iv] = "msd_scan_L1"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		MsdBoundsArgs b1{};
 		b1.cell_scan = s.msd_cell_scan; b1.items = items1; b1.S = 1; b1.nd = 256; b1.n = n; b1.start = s.msd_start2;
 		b1.cap = b2 == 0 ? cap : 0; b1.flags = flags;
@@ -328,9 +329,9 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		p1.tile_counter = &s.zero->msd_counters[0]; p1.flags = never;
 		// (the item_seg table of the level-2 items shares its buffer with the all-zero level-1 table: partition first, bounds after)
 		msd_partition_kernel<WORDS><<<pgrid1, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p1);
+		s.pass_names[iv] = "msd_partition_L1"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		msd_bounds_kernel<<<1, 1024, 0, st>>>(b1);
 		ctx->launches += 2;
-		s.pass_names[iv] = "msd_partition_L1"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		if (b2 > 0) {
 			MsdItems items2{};
 			items2.seg_start = s.msd_start2; items2.item_base = s.msd_item_base2; items2.item_seg = s.msd_item_seg2; items2.n_items = &s.zero->msd_n_items[1];

@@ -37,6 +37,13 @@ __global__ void k(uint32_t* out, int unused)
 		if (MODE == 10) acc += __popc(__ballot_sync(0xffffffffu, d & 1));            // single ballot
 		if (MODE == 11) { uint32_t dd = (d & 0xF0u) | (lane & 15u); atomicAdd(&sh[dd], 1u); }  // 2 lanes per address
 		if (MODE == 12) { atomicAdd(&sh[lane * 8 + (d & 7)], 1u); }                  // conflict-free banks, distinct addresses
+		if (MODE == 13) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((d * 3 + lane) & 1023); acc += (uint32_t)atomicCAS(p, 0xFFFFFFFFFFFFFFFFull, (unsigned long long)d); }   // CAS.64 random
+		if (MODE == 14) { acc += atomicCAS(&sh[(d * 3 + lane) & 2047], 0xFFFFFFFFu, d); }                              // CAS.32 random
+		if (MODE == 15) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((d * 3 + lane) & 1023); acc += (uint32_t)atomicMin(p, (unsigned long long)d * 7919ull); }      // MIN.64
+		if (MODE == 16) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((d * 3 + lane) & 1023); atomicAdd(p, 1ull); }      // ADD.64
+		if (MODE == 17) { acc += atomicMin(&sh[(d * 3 + lane) & 2047], d * 7919u); }                                    // MIN.32
+		if (MODE == 18) { acc += atomicExch(&sh[(d * 3 + lane) & 2047], d); }                                           // EXCH.32
+		if (MODE == 19) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((d * 3 + lane) & 1023); acc += (uint32_t)atomicExch(p, (unsigned long long)d); }  // EXCH.64
 	}
 	long long t1 = clock64();
 	if (threadIdx.x == 0) out[blockIdx.x * 2] = (uint32_t)(t1 - t0);
@@ -64,7 +71,7 @@ void run(const char* name, int threads, int blocks_per_sm)
 
 int main()
 {
-	for (int cfg = 0; cfg < 2; ++cfg) {
+	for (int cfg = 0; cfg < 1; ++cfg) {
 		const int thr = cfg == 0 ? 512 : 1024, bps = cfg == 0 ? 2 : 2;
 		run<0>("baseline lcg", thr, bps);
 		run<1>("atomicAdd smem CTA-shared random (no ret)", thr, bps);
@@ -77,6 +84,13 @@ int main()
 		run<5>("8 ballots emulating match", thr, bps);
 		run<10>("single ballot + popc", thr, bps);
 		run<6>("shfl", thr, bps);
+		run<13>("atomicCAS 64 smem random", thr, bps);
+		run<14>("atomicCAS 32 smem random", thr, bps);
+		run<15>("atomicMin 64 smem random", thr, bps);
+		run<16>("atomicAdd 64 smem random", thr, bps);
+		run<17>("atomicMin 32 smem random", thr, bps);
+		run<18>("atomicExch 32 smem random", thr, bps);
+		run<19>("atomicExch 64 smem random", thr, bps);
 		run<8>("match + leader LDS/STS RMW + syncwarp", thr, bps);
 		run<9>("plain smem RMW (LDS+IADD+STS)", thr, bps);
 	}
