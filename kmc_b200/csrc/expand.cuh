@@ -64,16 +64,17 @@ __device__ __forceinline__ uint64_t tile_first_base(uint64_t pack_start, uint32_
 // ---------------------------------------------------------------------------------------------------------------------
 // Walking a pack is a serial chain (the length byte of a record says where the next record starts).  For the usual pack
 // (one collector flush, <= 64 KiB) the chain is cut into 256 segments of 256 bytes that are walked IN PARALLEL, one thread each,
-// from shared memory: thread t does not know where the first record of its segment begins, so it starts 8 KB earlier at an
+// from shared memory: thread t does not know where the first record of its segment begins, so it starts 1 KB earlier at an
 // arbitrary byte and follows the chain from there.  Any chain that ever lands on a true record start stays on the true chain,
-// and a landing hits a true start with probability ~1/12, so after 8 KB (>= 200 landings) the two have merged
-// (miss probability ~ (11/12)^200 ~ 3e-8 per segment).  This is then VERIFIED, not assumed: the entry of segment t must be
-// exactly the exit of segment t-1 (thread 0 starts on the true start); one mismatch and the pack is left to the exact
-// warp-per-pack walker below.  A step costs one shared-memory load (~45 cycles); 8 KB + 2 x 256 B = ~750 steps per thread.
+// and a landing hits a true start with probability ~1/12, so after 1 KB the two have merged for ~9 segments out of 10.
+// The rest is repaired, not assumed: the entry of segment t must be exactly the exit of segment t-1 (segment 0 starts on the
+// true start); a segment whose entry is off re-walks from the true one, round after round until nothing changes (chains merge,
+// so exits rarely move: one or two rounds).  A final check of the whole chain guards the result; a pack that fails it is left
+// to the exact warp-per-pack walker below.  A step costs one shared-memory load (~45 cycles); ~150 steps per thread.
 constexpr int kWalkSegBytes = 256;
 constexpr int kWalkSegs = 256;                                   // threads per CTA = segments per pack
 constexpr int kWalkChunk = kWalkSegBytes * kWalkSegs;            // 64 KiB
-constexpr int kWalkSpec = 8192;
+constexpr int kWalkSpec = 1024;
 
 __global__ void __launch_bounds__(kWalkSegs) walk_packs_parallel_kernel(const ExpandArgs a, uint32_t* pack_done)
 {
@@ -97,17 +98,32 @@ __global__ void __launch_bounds__(kWalkSegs) walk_packs_parallel_kernel(const Ex
 		const uint8_t* pk = wsm + shift;
 		const uint32_t k3 = a.k + 3;
 		const uint32_t seg_lo = tid * kWalkSegBytes, seg_hi = min(seg_lo + (uint32_t)kWalkSegBytes, len);
-		uint32_t pos = seg_lo > (uint32_t)kWalkSpec ? seg_lo - kWalkSpec : 0;       // speculative start (exact for the first 32 segments)
+		uint32_t pos = seg_lo > (uint32_t)kWalkSpec ? seg_lo - kWalkSpec : 0;       // speculative start (exact for the first segments)
 		if (seg_lo < len) {
 			while (pos < seg_lo) pos += 1 + ((pk[pos] + k3) >> 2);
 		} else pos = len;
-		const uint32_t entry = min(pos, len);
+		uint32_t entry = min(pos, len);
 		uint32_t nrec = 0, nk = 0;
 		pos = entry;
 		while (pos < seg_hi) { const uint32_t x = pk[pos]; nk += x + 1; ++nrec; pos += 1 + ((x + k3) >> 2); }
-		s_entry[tid] = entry; s_exit[tid] = seg_lo < len ? pos : len; s_nrec[tid] = nrec; s_nk[tid] = nk;
+		s_entry[tid] = entry; s_exit[tid] = seg_lo < len ? pos : len;
+		// ---- make the chain of segments consistent: the entry of segment t must be the exit of segment t-1 (segment 0 starts on the true
+		// start).  A segment whose speculative entry was off re-walks from the true one; since chains merge, its exit rarely changes,
+		// so one or two rounds settle a pack (at most one round per segment: every round fixes at least the first wrong segment).
+		for (int it = 0; it < kWalkSegs; ++it) {
+			__syncthreads();
+			const uint32_t want = tid > 0 ? min(s_exit[tid - 1], len) : 0u;
+			const bool fix = tid > 0 && seg_lo < len && entry != want;
+			if (!__syncthreads_or(fix)) break;
+			if (fix) {
+				entry = want; nrec = 0; nk = 0; pos = entry;
+				while (pos < seg_hi) { const uint32_t x = pk[pos]; nk += x + 1; ++nrec; pos += 1 + ((x + k3) >> 2); }
+				s_entry[tid] = entry; s_exit[tid] = pos;
+			}
+		}
+		s_nrec[tid] = nrec; s_nk[tid] = nk;
 		__syncthreads();
-		// ---- verify the chain of segments
+		// ---- verify (cheap, and the only thing correctness rests on)
 		bool bad = false;
 		if (tid > 0 && seg_lo < len && s_entry[tid] != min(s_exit[tid - 1], len)) bad = true;
 		if (tid == kWalkSegs - 1 || seg_hi == len) { if (seg_lo < len && s_exit[tid] != len) bad = true; }     // the last record must end with the pack
