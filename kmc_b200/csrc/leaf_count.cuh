@@ -139,20 +139,34 @@ __global__ void __launch_bounds__(kLeafThreads, 4) leaf_count_kernel(const LeafA
 				uint64_t key[4];
 #pragma unroll
 				for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * kLeafThreads + tid; key[u] = j < m ? a.recs[cur_lo + j] : 0; }
+				// all four claims are issued before any result is looked at: their latencies overlap
+				uint32_t slot[4];
+				unsigned long long old[4];
+				uint32_t live = 0;
 #pragma unroll
 				for (int u = 0; u < 4; ++u) {
 					const uint32_t j = j0 + u * kLeafThreads + tid;
-					if (j >= m) continue;
 					const uint64_t kk = key[u];
-					if (e_bits && ((uint32_t)(kk >> sub_shift) & ((1u << e_bits) - 1u)) != round) continue;      // another round's k-mer
-					if (maybe_allones && kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); continue; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
-					const uint32_t b = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
-					const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[b]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
-					if (old == kLeafEmpty) S.occ[atomicAdd(&S.n_occ, 1u)] = (uint16_t)b;
-					if (old == kLeafEmpty || old == kk) atomicAdd(&S.mcnt[b], 1u);
+					bool ok = j < m;
+					if (e_bits && ((uint32_t)(kk >> sub_shift) & ((1u << e_bits) - 1u)) != round) ok = false;      // another round's k-mer
+					if (ok && maybe_allones && kk == kLeafEmpty) { atomicAdd(&S.n_allones, 1u); ok = false; }       // TTT..T (k = 32, -b): cannot live in the table, sorts last
+					slot[u] = (uint32_t)(kk >> slot_shift) & (kLeafSlots - 1);
+					old[u] = kk;
+					if (ok) {
+						old[u] = atomicCAS(reinterpret_cast<unsigned long long*>(&S.mkey[slot[u]]), (unsigned long long)kLeafEmpty, (unsigned long long)kk);
+						live |= 1u << u;
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					if (!((live >> u) & 1u)) continue;
+					const uint64_t kk = key[u];
+					const uint32_t b = slot[u];
+					if (old[u] == kLeafEmpty) S.occ[atomicAdd(&S.n_occ, 1u)] = (uint16_t)b;
+					if (old[u] == kLeafEmpty || old[u] == kk) atomicAdd(&S.mcnt[b], 1u);
 					else {
 						const uint32_t q = atomicAdd(&S.n_retry, 1u);
-						if (q < (uint32_t)kLeafRetry) S.retry[q] = j;
+						if (q < (uint32_t)kLeafRetry) S.retry[q] = j0 + u * kLeafThreads + tid;
 						else failed = true;
 					}
 				}
