@@ -291,8 +291,11 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 	const uint32_t* lsd_flag = nullptr;
 	if (msd) {
 		// leaves of ~1 K records: b2 = bits of the second partition level
+		// counted leaves (k <= 32) are streamed and may be any size; sorted leaves must fit on chip, and canonical k-mers crowd
+		// into the low prefixes (largest leaf ~4.4x the mean): aim at a fifth of the capacity
+		const uint64_t target = (plan && WORDS == 1) ? 1024 : std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64);
 		uint32_t lg = 0;
-		while ((1ull << lg) < (n + 1023) / 1024) ++lg;
+		while ((1ull << lg) < (n + target - 1) / target) ++lg;
 		const uint32_t b2 = lg > 8 ? std::min(lg - 8, 8u) : 0;
 		const uint32_t nd2 = 1u << b2;
 		const uint32_t cap = (plan && WORDS == 1) ? 0u : (uint32_t)msd_local_cap<WORDS>();      // counted leaves are streamed: no size limit
