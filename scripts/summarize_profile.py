@@ -44,13 +44,13 @@ if os.path.exists(rp):
             except ValueError: pass
             vals.append(v + (" " + u if u and u not in ("%",) else ""))
         out.append("| %s | `%s` | " % (r[0], name) + " | ".join(vals) + " |")
-        if ("radix_pass" in name or "partition" in name) and traffic is None:
+        if "msd_partition" in name and traffic is None:          # the kernel bench.py's roofline names (radix_pass launches are no-op fallbacks)
             def tobytes(x, unit):
                 return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
             traffic = tobytes(r[idx["dram__bytes_read.sum"]], rows[1][idx["dram__bytes_read.sum"]]) + tobytes(r[idx["dram__bytes_write.sum"]], rows[1][idx["dram__bytes_write.sum"]])
     out.append("")
     if traffic:
-        json.dump({"dram_bytes_per_launch": traffic, "source": "ncu --set full, %s, first sort-pass kernel instance" % os.path.basename(rp)},
+        json.dump({"dram_bytes_per_launch": traffic, "source": "ncu --set full, %s, first msd_partition_kernel instance" % os.path.basename(rp)},
                   open(os.path.join(P, "radix_pass_traffic.json"), "w"))
         out.append("dominant-kernel DRAM traffic per launch: %.4g bytes (algorithmic 2*N*W = %.4g)\n" % (traffic, 2.0 * (1 << 26) * 8))
 
