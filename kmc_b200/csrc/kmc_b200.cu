@@ -7,7 +7,7 @@
 #include "radix_sort.cuh"
 #include "count.cuh"
 #include "msd_sort.cuh"
-#include "leaf_count.cuh"
+#include "leaf_warp.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -101,6 +101,7 @@ struct kmcb200_ctx {
 	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
+	int leaf_slot_bits = 9;                                 // KMCB200_LEAF_SLOT_BITS = 8 | 9 | 10: slots of a warp's leaf table
 	uint32_t epoch = 1;
 	uint64_t launches = 0;
 	// All kernels of a context run on ONE stream: the persistent radix passes size their grids to fill the GPU and two of
@@ -293,12 +294,12 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		// leaves of ~1 K records: b2 = bits of the second partition level
 		// counted leaves (k <= 32) are streamed and may be any size; sorted leaves must fit on chip, and canonical k-mers crowd
 		// into the low prefixes (largest leaf ~4.4x the mean): aim at a fifth of the capacity
-		const uint64_t target = (plan && WORDS == 1) ? 1024 : std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64);
+		const uint64_t target = plan ? 1024 : std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64);
 		uint32_t lg = 0;
 		while ((1ull << lg) < (n + target - 1) / target) ++lg;
 		const uint32_t b2 = lg > 8 ? std::min(lg - 8, 8u) : 0;
 		const uint32_t nd2 = 1u << b2;
-		const uint32_t cap = (plan && WORDS == 1) ? 0u : (uint32_t)msd_local_cap<WORDS>();      // counted leaves are streamed: no size limit
+		const uint32_t cap = plan ? kLwMaxLeaf : (uint32_t)msd_local_cap<WORDS>();      // counted leaves are streamed by one warp: only a very loose limit
 		const bool final_in_b = (key_bytes % 2) == 0;                 // where the LSD passes (started from b) end; the leaves go to the same place
 		void* fin = final_in_b ? b : a;
 		uint32_t* flags = s.zero->msd_flags;
@@ -354,7 +355,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			ctx->launches++;
 			s.pass_names[iv] = "msd_partition_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		}
-		if (plan && WORDS == 1) {          // the caller counts the leaves (no sort of the duplicates)
+		if (plan) {          // the caller counts the leaves (no sort of the duplicates)
 			plan->active = true;
 			plan->recs = b2 > 0 ? a : b; plan->start = b2 > 0 ? s.msd_start3 : s.msd_start2; plan->n_leaves = 256 * nd2; plan->low_bits = top_shift - b2;
 		} else {
@@ -507,6 +508,76 @@ __global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uin
 	result[7] = msd_flags ? msd_flags[0] : 0;       // 1: the hybrid MSD / leaf-count path gave up and the LSD fallback produced the result
 }
 
+template <int WORDS, int SLOT_BITS>
+int launch_leaves(kmcb200_ctx* ctx, const LeafArgs& la, cudaStream_t st)
+{
+	const size_t smem = sizeof(LwSmem<SLOT_BITS>) * kLwWarps;
+	const uint32_t lgrid = std::min<uint32_t>((la.n_leaves + kLwWarps - 1) / kLwWarps, (uint32_t)(ctx->sm_count * ctx->occ_leaf));
+	leaf_warp_kernel<WORDS, SLOT_BITS><<<lgrid, 32 * kLwWarps, smem, st>>>(la);
+	ctx->launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+template <int WORDS, int SLOT_BITS>
+int setup_leaves(kmcb200_ctx* ctx)
+{
+	const int smem = (int)(sizeof(LwSmem<SLOT_BITS>) * kLwWarps);
+	CU(cudaFuncSetAttribute(leaf_warp_kernel<WORDS, SLOT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	CU(cudaFuncSetAttribute(leaf_warp_kernel<WORDS, SLOT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf, leaf_warp_kernel<WORDS, SLOT_BITS>, 32 * kLwWarps, smem));
+	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
+	return 0;
+}
+
+#define DISPATCH_SLOTS(ctx, fn, W, ...) ((ctx)->leaf_slot_bits == 8 ? fn<W, 8>(__VA_ARGS__) : (ctx)->leaf_slot_bits == 10 ? fn<W, 10>(__VA_ARGS__) : fn<W, 9>(__VA_ARGS__))
+
+template <int WORDS> int setup_leaves_w(kmcb200_ctx* ctx) { return DISPATCH_SLOTS(ctx, setup_leaves, WORDS, ctx); }
+
+// Partition (two MSD levels), then COUNT the leaves (leaf_warp.cuh) instead of sorting them; the LSD passes + count_emit_kernel
+// stand behind as the device-flagged fallback (they return at once unless a leaf could not be counted).
+template <int WORDS>
+int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np_eff, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+{
+	bool in_b = false;
+	LeafPlan plan;
+	if (int rc = launch_sort<WORDS>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b, &plan)) return rc;
+	if (!plan.active) {          // small bin: plain LSD passes, classic count
+		CU(cudaEventRecord(s.ev_sort, st));
+		s.ran_sort = true;
+		const void* sorted = in_b ? s.recs_b : s.recs_a;
+		return stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st);
+	}
+	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
+	const size_t pad = (size_t)((ob + 7) / 8) * 8;
+	if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * pad + 64)) return rc;
+	CU(cudaMemsetAsync(d_lut, 0, ctx->lut_entries * 8, st));
+	CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
+	uint32_t* flags = s.zero->msd_flags;
+	LeafArgs la{};
+	la.recs = plan.recs; la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
+	la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
+	la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
+	la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
+	if (int rc = DISPATCH_SLOTS(ctx, launch_leaves, WORDS, ctx, la, st)) return rc;
+	leaf_scan_kernel<<<1, 1024, 0, st>>>(s.leaf_emit, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags);
+	leaf_gather_kernel<<<(plan.n_leaves + 7) / 8, 256, 0, st>>>(s.leaf_tmp, plan.start, s.leaf_emit, s.leaf_off, plan.n_leaves, ob, d_out, d_result, flags);
+	ctx->launches += 2;
+	int iv = s.n_passes_run;
+	s.pass_names[iv] = "leaf_count"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+	// fallback (returns at once unless a leaf could not be counted): LSD passes from the level-1 output, then the classic count
+	if (int rc = launch_lsd_passes<WORDS>(ctx, s, s.recs_b, s.recs_a, n_rec, ctx->key_bytes, flags, false, iv, st)) return rc;
+	leaf_reset_kernel<<<64, 256, 0, st>>>(d_lut, ctx->lut_entries, d_result, flags);
+	ctx->launches++;
+	s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st));
+	s.n_passes_run = iv;
+	CU(cudaEventRecord(s.ev_sort, st));
+	s.ran_sort = true;
+	const void* sorted = (ctx->key_bytes % 2 == 0) ? s.recs_b : s.recs_a;
+	CU(cudaMemsetAsync(&s.zero->counters[kMaxPasses], 0, sizeof(uint32_t), st));
+	return launch_count<WORDS>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, st);
+}
+
 // Expand -> Sort -> Compact on device buffers; records live in the slot workspace
 int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
 	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
@@ -528,45 +599,8 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	s.ran_expand = true;
 	bool in_b = false;
 	const uint32_t np_eff = (n_packs && pack_bytes) ? n_packs : 1u;
-	if (ctx->words == 1 && ctx->use_leaf) {
-		// ---- k <= 32: partition, then COUNT the leaves (leaf_count.cuh); LSD passes + count_emit_kernel stand behind as the flagged fallback
-		LeafPlan plan;
-		if (int rc = launch_sort<1>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b, &plan)) return rc;
-		if (plan.active) {
-			const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
-			if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * (ob > 8 ? 16 : 8) + 64)) return rc;
-			CU(cudaMemsetAsync(d_lut, 0, ctx->lut_entries * 8, st));
-			CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
-			uint32_t* flags = s.zero->msd_flags;
-			LeafArgs la{};
-			la.recs = reinterpret_cast<const uint64_t*>(plan.recs); la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
-			la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
-			la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
-			la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
-			const uint32_t lgrid = std::min<uint32_t>(plan.n_leaves, (uint32_t)(ctx->sm_count * ctx->occ_leaf));
-			leaf_count_kernel<<<lgrid, kLeafThreads, sizeof(LeafSmem), st>>>(la);
-			leaf_scan_kernel<<<1, 1024, 0, st>>>(s.leaf_emit, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags);
-			leaf_gather_kernel<<<(plan.n_leaves + 7) / 8, 256, 0, st>>>(s.leaf_tmp, plan.start, s.leaf_emit, s.leaf_off, plan.n_leaves, ob, d_out, d_result, flags);
-			ctx->launches += 3;
-			int iv = s.n_passes_run;
-			s.pass_names[iv] = "leaf_count"; CU(cudaEventRecord(s.ev_pass[++iv], st));
-			// fallback (returns at once unless a leaf overflowed): LSD passes from the level-1 output, then the classic count
-			if (int rc = launch_lsd_passes<1>(ctx, s, s.recs_b, s.recs_a, n_rec, ctx->key_bytes, flags, false, iv, st)) return rc;
-			leaf_reset_kernel<<<64, 256, 0, st>>>(d_lut, ctx->lut_entries, d_result, flags);
-			ctx->launches++;
-			s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st));
-			s.n_passes_run = iv;
-			CU(cudaEventRecord(s.ev_sort, st));
-			s.ran_sort = true;
-			const void* sorted = (ctx->key_bytes % 2 == 0) ? s.recs_b : s.recs_a;
-			CU(cudaMemsetAsync(&s.zero->counters[kMaxPasses], 0, sizeof(uint32_t), st));
-			if (int rc = launch_count<1>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, st)) return rc;
-		} else {
-			CU(cudaEventRecord(s.ev_sort, st));
-			s.ran_sort = true;
-			const void* sorted = in_b ? s.recs_b : s.recs_a;
-			if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
-		}
+	if (ctx->use_leaf) {
+		if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, n_rec, np_eff, d_out, out_capacity, d_lut, d_result, st)) return rc;
 	} else {
 		if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b)) return rc;
 		CU(cudaEventRecord(s.ev_sort, st));
@@ -614,15 +648,12 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	ctx->sm_count = dp.multiProcessorCount;
 	if (const char* e = getenv("KMCB200_SORT")) ctx->use_msd = std::string(e) != "lsd";
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
+	if (const char* e = getenv("KMCB200_LEAF_SLOT_BITS")) { const int b = atoi(e); if (b == 8 || b == 9 || b == 10) ctx->leaf_slot_bits = b; }
 	ctx->slots.resize(prm->n_slots);
 	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };
 	if (cudaSetDevice(prm->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(KMCB200_ERR_CUDA); }
 	if (int rc = DISPATCH_WORDS(ctx, setup_kernels, ctx)) return bail(rc);
-	if (cudaFuncSetAttribute(leaf_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeafSmem)) != cudaSuccess ||
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf, leaf_count_kernel, kLeafThreads, sizeof(LeafSmem)) != cudaSuccess) {
-		ctx->err = "leaf_count_kernel setup failed"; return bail(KMCB200_ERR_CUDA);
-	}
-	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
+	if (int rc = DISPATCH_WORDS(ctx, setup_leaves_w, ctx)) return bail(rc);
 	if (cudaFuncSetAttribute(walk_packs_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkChunk + 32) != cudaSuccess) {
 		ctx->err = "walk_packs_parallel_kernel setup failed"; return bail(KMCB200_ERR_CUDA);
 	}

@@ -61,6 +61,28 @@ def test_bin_parity_multi_word(oracle, k, both, cmin):
     _check_bin(oracle, synth_bin(11, k, 8000, genome_len=12000, err=0.02), p)
 
 
+@pytest.mark.parametrize("slot_bits", [8, 9, 10])
+@pytest.mark.parametrize("k,both,cmin,p_len", [(31, True, 2, 7), (55, True, 2, 7), (55, False, 1, 3), (33, True, 1, 5), (64, True, 2, 8), (70, True, 1, 6),
+                                               (96, False, 2, 8), (128, True, 1, 8), (32, False, 1, 4), (17, True, 1, 5)])
+def test_leaf_path_all_widths(oracle, monkeypatch, slot_bits, k, both, cmin, p_len):
+    """~170 K k-mers (the hybrid MSD path + warp-counted leaves) for every record width and every table size."""
+    monkeypatch.setenv("KMCB200_LEAF_SLOT_BITS", str(slot_bits))
+    p = Params(k=k, both_strands=both, cutoff_min=cmin, lut_prefix_len=p_len)
+    _check_bin(oracle, synth_bin(31 + k, k, 14000, genome_len=9000, err=0.01), p)
+
+
+@pytest.mark.parametrize("k,p_len", [(31, 7), (55, 7), (100, 8)])
+def test_leaf_path_without_duplicates(oracle, k, p_len):
+    """Every k-mer distinct (no coverage): the rounds of a leaf overflow their tables and are split on further bits."""
+    p = Params(k=k, cutoff_min=1, lut_prefix_len=p_len)
+    b = synth_bin(5, k, 20000, genome_len=4_000_000, err=0.0)
+    ctx = _ctx(p)
+    r = ctx.process_bin(_to_skb(b))
+    e = oracle.process_bin(b, p)
+    assert r.stats == e.stats and np.array_equal(r.lut, e.lut) and r.payload.tobytes() == e.payload
+    ctx.close()
+
+
 def test_expand_matches_oracle(oracle):
     import torch
     for k, both in [(31, True), (31, False), (55, True), (100, True), (9, True)]:
