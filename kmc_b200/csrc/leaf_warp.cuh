@@ -4,23 +4,28 @@
 // DISTINCT k-mers with their multiplicities (CompactKmers, kmc_core/kb_sorter.h:1128-1281; for k % 32 != 0 the same result
 // comes out of CompactKxmers :937-1122 + kxmer_set.h).  With sequencing coverage c a k-mer occurs ~c times, so sorting every
 // copy (RADULS' lower levels and small sorts, raduls_impl.h:77-141,493-519) does ~c times the necessary work.  A leaf is
-// therefore counted in an ORDER-PRESERVING table:
-//   * slot = the next SLOT_BITS bits of the k-mer (monotone in the k-mer: slot order is key order, nothing is sorted);
-//     the first copy claims the slot with one 64-bit atomicCAS, every other copy is one 32-bit atomicAdd on the count;
-//   * a different k-mer that maps to a taken slot is noted and goes, in a dense second step, to a small open-addressing side
-//     table; surviving side entries are ranked against the few entries of their own slot only;
-//   * cutoffs / clamp / record bytes / lut[prefix]++ exactly as kb_sorter.h:1174-1203; one sweep over the slots gives every
-//     surviving k-mer its position; records are written lane-dense (coalesced) into the leaf's region of a temporary buffer,
-//     leaf_scan_kernel + leaf_gather_kernel pack the regions into the output.
+// therefore counted in a hash table whose GROUPS are ordered:
+//   * the table is groups of 64 slots; the group of a k-mer is its next bits (monotone: group order is k-mer order),
+//     the slot inside the group is a hash of the remaining bits, linear probing stays inside the group.  (A fully
+//     order-preserving table does not work: a sequencing error late in a k-mer leaves its leading bits untouched, so a real
+//     k-mer and its error variants would all fight for one slot - measured: 1/3 of the records collided.)
+//     The first copy claims a slot with one 64-bit atomicCAS, every other copy is one 32-bit atomicAdd on the count;
+//   * the cutoffs (kb_sorter.h:1174-1191) are applied ON THE WAY: the add that lifts a count to cutoff_min sets the entry's bit in
+//     a bitmap (one word per group), the add that lifts it past cutoff_max sets it in a second one.  When the last record is in,
+//     reached & ~over IS the set of survivors: prefix popcounts of the words are the output positions of the groups, and inside
+//     a group (a handful of survivors) a k-mer is placed by comparing it with the other survivors of its word;
+//   * survivors are emitted lane-dense: record bytes / clamp / lut[prefix]++ as kb_sorter.h:1190-1203, into the leaf's region of a
+//     temporary buffer; leaf_scan_kernel + leaf_gather_kernel pack the regions into the output.
 // Everything is private to ONE WARP (its own table in shared memory, __syncwarp only): no CTA barrier, no inter-warp
 // dependency, so the short latency-bound phases of one leaf overlap with those of ~30 other leaves per SM.
 // A leaf larger than a round of the table (canonical k-mers crowd into the low prefixes: up to ~4.4x the mean) is counted in
-// 2^e rounds over sub-ranges of its next e bits; a round whose tables overflow anyway is split in two on the next bit (binary
-// descent, nothing has been emitted for it yet).  Only a leaf beyond kLwMaxLeaf records (or one k-mer-range that cannot be
-// split any further) raises the device flag: the LSD passes + count_emit_kernel behind then redo the bin.
+// 2^e rounds over sub-ranges of its next e bits (a cheap scan compacts the round's k-mers into a ring in shared memory, the
+// ring is inserted densely); a round in which a group fills up is split in two on the next bit (binary descent, nothing of
+// it has been emitted yet).  Only a leaf beyond kLwMaxLeaf records (or a k-mer range that cannot be split any further) raises
+// the device flag: the LSD passes + count_emit_kernel behind then redo the bin.
 //
 // Entry formats (64 bit, EMPTY = all ones):
-//   WORDS == 1   [ key bits below the slot bits (<= 47) | count ]      the k-mer is rebuilt from leaf, slot and entry
+//   WORDS == 1   [ key bits below the group bits (<= 47) | count ]     the k-mer is rebuilt from leaf, round, group and entry
 //   WORDS >= 2   [ index of the first copy inside the leaf (32) | count (32) ]   equality is checked against that record
 #pragma once
 #include "common.cuh"
@@ -31,11 +36,11 @@
 namespace kmcb {
 
 constexpr int kLwWarps = 4;                      // warps per CTA (independent of each other)
-constexpr int kLwSide = 128;                     // side table (open addressing)
-constexpr int kLwSideMax = 100;
-constexpr int kLwRetry = 256;                    // records whose slot was taken, per round
-constexpr uint32_t kLwMaxLeaf = 65534;           // records of a warp-counted leaf (u16 indices; count field >= 16 bits)
-constexpr uint32_t kLwMaxSplit = 10;             // extra split bits a round may descend
+constexpr uint32_t kLwGroupBits = 6;              // slots per group = 64: a real k-mer and its error variants share a group, groups must absorb such clumps
+constexpr int kLwList = 256;                     // u16 list of survivors, one step of the emission
+constexpr uint32_t kLwRing = 128;                // ring of compacted k-mers (WORDS == 1, multi-round leaves)
+constexpr uint32_t kLwMaxLeaf = 65534;           // records of a warp-counted leaf (count field >= 16 bits)
+constexpr uint32_t kLwMaxSplit = 12;             // extra split bits a round may descend
 constexpr uint64_t kLwEmpty = ~0ull;
 
 struct LeafArgs {
@@ -55,14 +60,13 @@ struct LeafArgs {
 template <int SLOT_BITS>
 struct LwSmem {
 	static constexpr int kSlots = 1 << SLOT_BITS;
-	uint64_t main[kSlots];           // main table
-	uint64_t skey[kLwSide];          // side table: the k-mer (WORDS == 1) or the index of its first copy
-	uint32_t scnt[kLwSide];
-	uint32_t extra[kSlots / 4];      // surviving side entries per slot, one byte each
-	uint16_t gbase[kSlots / 4];      // output position of the first survivor of a group of 4 slots (written where side entries exist)
-	uint16_t list[kLwRetry];         // insertion: records whose slot was taken; emission: survivors in output order
-	uint8_t dense[kLwSide];          // surviving side entries
+	uint64_t main[kSlots];           // the table: ordered groups of 64 hashed slots
+	uint64_t ring[kLwRing];          // WORDS == 1: k-mers of the current round, compacted; during the emission the u16 list lives here
+	uint32_t surv[kSlots / 32];      // per group: entries whose count reached cutoff_min (later: the survivors) ...
+	uint32_t over[kSlots / 32];      // ... whose count went past cutoff_max (later: survivors in earlier groups)
+	__device__ __forceinline__ uint16_t* list() { return reinterpret_cast<uint16_t*>(ring); }       // [kLwList]
 };
+static_assert(kLwRing * 8 >= kLwList * 2, "the u16 list lives in the ring");
 
 template <int WORDS>
 __device__ __forceinline__ Rec<WORDS> lw_load(const Rec<WORDS>* p)
@@ -119,17 +123,77 @@ __device__ __forceinline__ uint32_t lw_hash(const Rec<WORDS>& r)
 	return (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> 40);
 }
 
-__device__ __forceinline__ uint32_t lw_bytesum(uint32_t x) { return (x * 0x01010101u) >> 24; }
+
+// cutoffs applied on the way (kb_sorter.h:1174-1191): what happens when a count goes from c-1 to c
+struct LwCut {
+	uint32_t cmin;               // max(cutoff_min, 1): reaching it makes a survivor ...
+	uint32_t cmax;               // ... exceeding cutoff_max unmakes it
+	bool never;                  // cutoff_max < cutoff_min: nothing survives, whatever reaches cmin counts as n_cutoff_max
+};
+// (two bitmaps, both only ever OR-ed: the result does not depend on the order in which lanes get to run)
+__device__ __forceinline__ void lw_transition(const LwCut& c, uint32_t newc, uint32_t* reached, uint32_t* over, uint32_t idx, uint32_t& r_max)
+{
+	if (newc == c.cmin) {
+		if (c.never) ++r_max;
+		else atomicOr(&reached[idx >> 5], 1u << (idx & 31u));
+	}
+	if (newc - 1u == c.cmax && !c.never) { atomicOr(&over[idx >> 5], 1u << (idx & 31u)); ++r_max; }
+}
+
+// ---- WORDS == 1: V k-mers per lane into the warp's table.  The first probes of all V are issued before any result is looked at
+// (their latencies overlap); further probes (the slot belongs to another k-mer) walk the 32 slots of the group.
+struct LwRound {
+	uint64_t* main; uint32_t* surv; uint32_t* over;
+	uint32_t gshift, gmask, cb, cmask;
+	uint64_t rem_mask;
+	LwCut cut;
+};
+
+template <int V>
+__device__ __forceinline__ void lw_insert1(const LwRound& t, const uint64_t (&kk)[V], uint32_t vmask, uint32_t& r_claim, uint32_t& r_max, bool& ok)
+{
+	uint32_t slot[V];
+	unsigned long long old[V], ent[V];
+#pragma unroll
+	for (int v = 0; v < V; ++v) {
+		const uint64_t rem = kk[v] & t.rem_mask;
+		slot[v] = ((((uint32_t)(kk[v] >> t.gshift)) & t.gmask) << kLwGroupBits) | (uint32_t)((rem * 0x9E3779B97F4A7C15ull) >> (64 - kLwGroupBits));
+		ent[v] = (rem << t.cb) | 1ull;
+		old[v] = 0;
+		if ((vmask >> v) & 1u) old[v] = atomicCAS(reinterpret_cast<unsigned long long*>(&t.main[slot[v]]), (unsigned long long)kLwEmpty, ent[v]);
+	}
+#pragma unroll
+	for (int v = 0; v < V; ++v) {
+		if (!((vmask >> v) & 1u)) continue;
+		uint32_t s = slot[v];
+		unsigned long long o = old[v];
+		int probe = 0;
+		while (true) {
+			if (o == kLwEmpty) { ++r_claim; lw_transition(t.cut, 1u, t.surv, t.over, s, r_max); break; }
+			if ((o >> t.cb) == (ent[v] >> t.cb)) {
+				const uint32_t oc = atomicAdd(reinterpret_cast<uint32_t*>(&t.main[s]), 1u) & t.cmask;      // low word = count
+				lw_transition(t.cut, oc + 1u, t.surv, t.over, s, r_max);
+				break;
+			}
+			if (++probe == (1 << kLwGroupBits)) { ok = false; break; }      // the group is full
+			s = (s & ~((1u << kLwGroupBits) - 1u)) | ((s + 1u) & ((1u << kLwGroupBits) - 1u));
+			o = atomicCAS(reinterpret_cast<unsigned long long*>(&t.main[s]), (unsigned long long)kLwEmpty, ent[v]);
+		}
+	}
+}
 
 template <int WORDS, int SLOT_BITS>
-__global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafArgs a)
+__global__ void __launch_bounds__(32 * kLwWarps, 8) leaf_warp_kernel(const LeafArgs a)
 {
 	using R = Rec<WORDS>;
 	using SM = LwSmem<SLOT_BITS>;
 	constexpr int SLOTS = SM::kSlots;
-	constexpr uint32_t ROUND = SLOTS + SLOTS / 4;        // records a round is sized for
-	constexpr int U = WORDS == 1 ? 4 : 2;                // records per lane and step
+	constexpr int NW = SLOTS / 32;                       // groups = bitmap words (<= 32)
+	constexpr int NG = SLOTS >> kLwGroupBits;           // groups
+	constexpr uint32_t GB = SLOT_BITS - kLwGroupBits;    // group bits
+	constexpr uint32_t ROUND = SLOTS + SLOTS / 2;        // records a round is sized for (30x coverage: ~0.3 distinct k-mers per record)
 	constexpr uint32_t FULL = 0xffffffffu;
+	static_assert(NW <= 32 && NW >= 4, "one bitmap word per lane");
 	extern __shared__ __align__(16) uint8_t lw_dsm[];
 	SM& S = reinterpret_cast<SM*>(lw_dsm)[threadIdx.x >> 5];
 	if (*a.flags & kMsdFlagFallback) return;
@@ -139,10 +203,10 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 	const uint32_t padw = (ob + 7) >> 3;                                   // temporary records: padw 64-bit words
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const bool one_prefix = prefix_shift >= a.low_bits;                    // every k-mer of a leaf has the same LUT prefix
-	const uint32_t span = a.cutoff_max - a.cutoff_min;                     // survivor <=> count - cutoff_min <= span (cutoff_max >= cutoff_min) ...
-	const bool never = a.cutoff_max < a.cutoff_min;                        // ... unless nothing can survive
+	const LwCut cut{a.cutoff_min > 1u ? a.cutoff_min : 1u, a.cutoff_max, a.cutoff_max < (a.cutoff_min > 1u ? a.cutoff_min : 1u)};
 	uint64_t* const tmp64 = reinterpret_cast<uint64_t*>(a.tmp);
-	uint32_t n_unique = 0, n_min = 0, n_max = 0;
+	uint16_t* const list = S.list();
+	uint32_t t_unique = 0, t_max = 0, t_emit = 0;        // per lane; n_cutoff_min = unique - emitted - n_cutoff_max
 	bool failed = false;
 
 	uint32_t leaf = 0;
@@ -158,78 +222,128 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 		if (m > kLwMaxLeaf) failed = true;
 		else if (m > 0) {
 			uint32_t e0 = 0;
-			while ((m >> e0) > ROUND && e0 < 8 && e0 < a.low_bits) ++e0;
+			while (((m >> e0) > ROUND && e0 < 8 && e0 < a.low_bits) || (WORDS == 1 && a.low_bits - e0 > GB + 47u)) ++e0;      // (an entry holds <= 47 key bits)
 			uint32_t e = e0, r = 0;
 			while (true) {
 				// ================================================================ one round: the k-mers whose next e bits are r
 				const uint32_t sub_shift = a.low_bits - e;
-				const uint32_t slot_shift = sub_shift > (uint32_t)SLOT_BITS ? sub_shift - SLOT_BITS : 0;
-				const uint32_t cb = WORDS == 1 ? min(64u - slot_shift, 32u) : 32u;              // bits of the count field
-				const uint64_t rem_mask = (1ull << slot_shift) - 1ull;                           // slot_shift <= 47
+				const uint32_t gshift = sub_shift > GB ? sub_shift - GB : 0;                      // bits below the group bits
+				const uint32_t cb = WORDS == 1 ? min(64u - gshift, 32u) : 32u;                   // bits of the count field
+				const uint64_t rem_mask = (1ull << gshift) - 1ull;                                // gshift <= 47
 				const uint32_t cmask = cb >= 32 ? 0xffffffffu : ((1u << cb) - 1u);
 				const uint32_t emask = (1u << e) - 1u;
 				// ---- clear
 				{
-					uint4* m4 = reinterpret_cast<uint4*>(S.main);
-					const uint4 ev = make_uint4(~0u, ~0u, ~0u, ~0u);
+					const uint4 ev = make_uint4(~0u, ~0u, ~0u, ~0u), zv = make_uint4(0, 0, 0, 0);
 #pragma unroll
-					for (int i = 0; i < SLOTS * 8 / 16 / 32; ++i) m4[i * 32 + lane] = ev;
-#pragma unroll
-					for (int i = 0; i < kLwSide * 8 / 16 / 32; ++i) reinterpret_cast<uint4*>(S.skey)[i * 32 + lane] = ev;
-					reinterpret_cast<uint4*>(S.scnt)[lane] = make_uint4(0, 0, 0, 0);              // 128 * 4 B
-#pragma unroll
-					for (int i = 0; i < SLOTS / 4 * 4 / 16 / 32; ++i) reinterpret_cast<uint4*>(S.extra)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
-					if (SLOTS / 4 * 4 / 16 < 32) { if (lane < SLOTS / 4 * 4 / 16) reinterpret_cast<uint4*>(S.extra)[lane] = make_uint4(0, 0, 0, 0); }
+					for (int i = 0; i < SLOTS * 8 / 16 / 32; ++i) reinterpret_cast<uint4*>(S.main)[i * 32 + lane] = ev;
+					if (lane < 2 * NW / 4) reinterpret_cast<uint4*>(S.surv)[lane] = zv;            // surv, over (contiguous)
 				}
 				__syncwarp();
-				// ---- insertion: first copy claims the slot, other copies add one, k-mers that find their slot taken are noted
-				uint32_t n_retry = 0;
+				// ---- insertion
+				uint32_t r_claim = 0, r_max = 0;
 				bool ok = true;
-				for (uint32_t j0 = 0; j0 < m; j0 += U * 32) {
-					R key[U];
+				if constexpr (WORDS == 1) {
+					const LwRound T{S.main, S.surv, S.over, gshift, (uint32_t)NG - 1u, cb, cmask, rem_mask, cut};
+					const unsigned long long* __restrict__ g = reinterpret_cast<const unsigned long long*>(recs) + lo;
+					if (e == 0) {
+						// the whole leaf: straight from registers, the next step's loads in flight while this one is inserted
+						uint64_t nx[4];
 #pragma unroll
-					for (int u = 0; u < U; ++u) {
-						const uint32_t j = j0 + u * 32 + lane;
-						if (j < m) key[u] = lw_load<WORDS>(recs + lo + j);
-						else {
+						for (int u = 0; u < 4; ++u) { const uint32_t j = u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+						for (uint32_t j0 = 0; j0 < m; j0 += 128) {
+							uint64_t cur[4];
+							uint32_t vmask = 0;
 #pragma unroll
-							for (int i = 0; i < WORDS; ++i) key[u].w[i] = 0;
+							for (int u = 0; u < 4; ++u) { cur[u] = nx[u]; vmask |= (j0 + u * 32 + lane < m) ? (1u << u) : 0u; }
+#pragma unroll
+							for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + 128 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+							lw_insert1<4>(T, cur, vmask, r_claim, r_max, ok);
+							if (!__all_sync(FULL, ok)) break;            // a group is full: the round is split
+						}
+					} else {
+						// one of several rounds: a cheap scan compacts this round's k-mers into a ring, the ring is inserted 64 at a time
+						uint32_t head = 0, tail = 0;
+						uint64_t nx[2];
+#pragma unroll
+						for (int u = 0; u < 2; ++u) { const uint32_t j = u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+						for (uint32_t j0 = 0;; j0 += 64) {
+							if (j0 < m) {
+								uint64_t cur[2];
+								bool in[2];
+#pragma unroll
+								for (int u = 0; u < 2; ++u) { cur[u] = nx[u]; in[u] = (j0 + u * 32 + lane < m) && ((uint32_t)(cur[u] >> sub_shift) & emask) == r; }
+#pragma unroll
+								for (int u = 0; u < 2; ++u) { const uint32_t j = j0 + 64 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+#pragma unroll
+								for (int u = 0; u < 2; ++u) {
+									const uint32_t bal = __ballot_sync(FULL, in[u]);
+									if (in[u]) S.ring[(tail + __popc(bal & lt)) & (kLwRing - 1)] = cur[u];
+									tail += __popc(bal);
+								}
+							}
+							const uint32_t avail = tail - head;
+							if (avail >= 64 || (j0 + 64 >= m && avail)) {
+								__syncwarp();
+								const uint64_t kk[2] = {S.ring[(head + lane) & (kLwRing - 1)], S.ring[(head + 32 + lane) & (kLwRing - 1)]};
+								__syncwarp();
+								head += min(avail, 64u);
+								lw_insert1<2>(T, kk, (lane < avail ? 1u : 0u) | (32 + lane < avail ? 2u : 0u), r_claim, r_max, ok);
+								if (!__all_sync(FULL, ok)) break;
+							}
+							if (j0 + 64 >= m && tail == head) break;
 						}
 					}
-					uint32_t slot[U];
-					unsigned long long old[U];
-					uint32_t live = 0;
+				} else {
+					// ---- wide records: the entry holds the index of the first copy, equality is checked against that record
+					constexpr int U = 2;
+					for (uint32_t j0 = 0; j0 < m; j0 += U * 32) {
+						R key[U];
 #pragma unroll
-					for (int u = 0; u < U; ++u) {              // all claims are issued before any result is looked at
-						const uint32_t j = j0 + u * 32 + lane;
-						bool in = j < m;
-						if (e && rec_bits<WORDS>(key[u], sub_shift, emask) != r) in = false;      // another round's k-mer
-						slot[u] = rec_bits<WORDS>(key[u], slot_shift, SLOTS - 1);
-						old[u] = 0;
-						if (in) {
-							const unsigned long long ent = WORDS == 1 ? (((key[u].w[0] & rem_mask) << cb) | 1ull) : (((unsigned long long)j << 32) | 1ull);
-							old[u] = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[slot[u]]), (unsigned long long)kLwEmpty, ent);
-							live |= 1u << u;
-						}
-					}
+						for (int u = 0; u < U; ++u) {
+							const uint32_t j = j0 + u * 32 + lane;
+							if (j < m) key[u] = lw_load<WORDS>(recs + lo + j);
+							else {
 #pragma unroll
-					for (int u = 0; u < U; ++u) {
-						bool coll = false;
-						if (((live >> u) & 1u) && old[u] != kLwEmpty) {
-							bool same;
-							if (WORDS == 1) same = (old[u] >> cb) == (key[u].w[0] & rem_mask);
-							else same = rec_equal<WORDS>(lw_load<WORDS>(recs + lo + (uint32_t)(old[u] >> 32)), key[u]);
-							if (same) atomicAdd(reinterpret_cast<uint32_t*>(&S.main[slot[u]]), 1u);       // low word = count
-							else coll = true;
+								for (int i = 0; i < WORDS; ++i) key[u].w[i] = 0;
+							}
 						}
-						const uint32_t cm = __ballot_sync(FULL, coll);
-						if (cm) {
-							const uint32_t q = n_retry + __popc(cm & lt);
-							if (coll && q < (uint32_t)kLwRetry) S.list[q] = (uint16_t)(j0 + u * 32 + lane);
-							n_retry += __popc(cm);
+						uint32_t slot[U];
+						unsigned long long old[U];
+						uint32_t live = 0;
+#pragma unroll
+						for (int u = 0; u < U; ++u) {              // both first probes are issued before any result is looked at
+							const uint32_t j = j0 + u * 32 + lane;
+							bool in = j < m;
+							if (e && rec_bits<WORDS>(key[u], sub_shift, emask) != r) in = false;      // another round's k-mer
+							slot[u] = (rec_bits<WORDS>(key[u], gshift, NG - 1) << kLwGroupBits) | (lw_hash<WORDS>(key[u]) & ((1u << kLwGroupBits) - 1u));
+							old[u] = 0;
+							if (in) {
+								old[u] = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[slot[u]]), (unsigned long long)kLwEmpty, ((unsigned long long)j << 32) | 1ull);
+								live |= 1u << u;
+							}
 						}
+#pragma unroll
+						for (int u = 0; u < U; ++u) {
+							if (!((live >> u) & 1u)) continue;
+							const uint32_t j = j0 + u * 32 + lane;
+							uint32_t s = slot[u];
+							unsigned long long o = old[u];
+							int probe = 0;
+							while (true) {
+								if (o == kLwEmpty) { ++r_claim; lw_transition(cut, 1u, S.surv, S.over, s, r_max); break; }
+								if (rec_equal<WORDS>(lw_load<WORDS>(recs + lo + (uint32_t)(o >> 32)), key[u])) {
+									const uint32_t oc = atomicAdd(reinterpret_cast<uint32_t*>(&S.main[s]), 1u);       // low word = count
+									lw_transition(cut, oc + 1u, S.surv, S.over, s, r_max);
+									break;
+								}
+								if (++probe == (1 << kLwGroupBits)) { ok = false; break; }
+								s = (s & ~((1u << kLwGroupBits) - 1u)) | ((s + 1u) & ((1u << kLwGroupBits) - 1u));
+								o = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[s]), (unsigned long long)kLwEmpty, ((unsigned long long)j << 32) | 1ull);
+							}
+						}
+						if (!__all_sync(FULL, ok)) break;
 					}
-					if (n_retry > (uint32_t)kLwRetry) { ok = false; break; }
 				}
 				if (!prefetched) {        // the next leaf: towards L2 while this one is counted
 					prefetched = true;
@@ -241,172 +355,74 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 					}
 				}
 				__syncwarp();
-				// ---- the noted records go to the side table
-				uint32_t n_side = 0;
-				if (ok && n_retry) {
-					for (uint32_t q = lane; q < n_retry; q += 32) {
-						const uint32_t j = S.list[q];
-						const R kk = lw_load<WORDS>(recs + lo + j);
-						uint32_t h = lw_hash<WORDS>(kk) & (kLwSide - 1);
-						const unsigned long long mine = WORDS == 1 ? (unsigned long long)kk.w[0] : (unsigned long long)j;
-						int probe = 0;
-						for (; probe < kLwSide; ++probe) {
-							const unsigned long long o2 = atomicCAS(reinterpret_cast<unsigned long long*>(&S.skey[h]), (unsigned long long)kLwEmpty, mine);
-							bool hit = o2 == kLwEmpty;
-							if (hit) ++n_side;
-							else if (WORDS == 1) hit = o2 == mine;
-							else hit = rec_equal<WORDS>(lw_load<WORDS>(recs + lo + (uint32_t)o2), kk);
-							if (hit) { atomicAdd(&S.scnt[h], 1u); break; }
-							h = (h + 1) & (kLwSide - 1);
-						}
-						if (probe == kLwSide) ok = false;
-					}
-#pragma unroll
-					for (int o = 16; o > 0; o >>= 1) n_side += __shfl_xor_sync(FULL, n_side, o);
-					if (n_side > (uint32_t)kLwSideMax) ok = false;
-					__syncwarp();
-				}
 				ok = __all_sync(FULL, ok);
 				if (!ok) {        // this range does not fit: split it on the next bit (nothing of it has been emitted)
 					if (e < a.low_bits && e < e0 + kLwMaxSplit) { ++e; r <<= 1; continue; }
 					failed = true;
 					break;
 				}
-				// the k-mer of a main / side entry
-				const uint64_t key_hi = (WORDS > 1 || (slot_shift + SLOT_BITS) >= 64) ? 0ull
-					: (((((uint64_t)leaf << a.low_bits) | ((uint64_t)r << sub_shift)) >> (slot_shift + SLOT_BITS)) << (slot_shift + SLOT_BITS));
-				auto main_key = [&](uint32_t s, uint64_t ent) -> R {
+				t_unique += r_claim;
+				t_max += r_max;
+				// the k-mer of an entry
+				const uint64_t key_hi = (WORDS > 1 || (gshift + GB) >= 64) ? 0ull
+					: (((((uint64_t)leaf << a.low_bits) | ((uint64_t)r << sub_shift)) >> (gshift + GB)) << (gshift + GB));
+				auto entry_key = [&](uint32_t s, uint64_t ent) -> R {
 					R kk;
-					if (WORDS == 1) kk.w[0] = key_hi | ((uint64_t)s << slot_shift) | ((ent >> cb) & rem_mask);
+					if (WORDS == 1) kk.w[0] = key_hi | ((uint64_t)(s >> kLwGroupBits) << gshift) | ((ent >> cb) & rem_mask);
 					else kk = lw_load<WORDS>(recs + lo + (uint32_t)(ent >> 32));
 					return kk;
 				};
-				auto side_key = [&](uint32_t h) -> R {
-					R kk;
-					if (WORDS == 1) kk.w[0] = S.skey[h];
-					else kk = lw_load<WORDS>(recs + lo + (uint32_t)S.skey[h]);
-					return kk;
-				};
-				auto survives = [&](uint32_t c) -> bool { return !never && (c - a.cutoff_min) <= span; };     // kb_sorter.h:1174-1191
-				// ---- side entries: cutoffs, the survivors as a list + one byte per slot
-				uint32_t n_dense = 0;
-				if (n_side) {
+				// ---- reached & ~over is the result: prefix popcounts of the words = positions of the groups
+				const uint32_t w_main = lane < (uint32_t)NW ? (S.surv[lane] & ~S.over[lane]) : 0u;
+				uint32_t inc = __popc(w_main);
 #pragma unroll
-					for (int i = 0; i < kLwSide / 32; ++i) {
-						const uint32_t h = i * 32 + lane;
-						const bool occ = S.skey[h] != kLwEmpty;
-						const uint32_t c = S.scnt[h];
-						const bool sv = occ && survives(c);
-						n_min += occ && c < a.cutoff_min;
-						n_max += occ && !sv && c >= a.cutoff_min;
-						if (sv) {
-							const uint32_t s = rec_bits<WORDS>(side_key(h), slot_shift, SLOTS - 1);
-							atomicAdd(&S.extra[s >> 2], 1u << (8u * (s & 3u)));
-						}
-						const uint32_t sm = __ballot_sync(FULL, sv);
-						if (sv) S.dense[n_dense + __popc(sm & lt)] = (uint8_t)h;
-						n_dense += __popc(sm);
-					}
-					n_unique += lane == 0 ? n_side : 0;
-					__syncwarp();
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t t = __shfl_up_sync(FULL, inc, o);
+					if (lane >= (uint32_t)o) inc += t;
 				}
-				// ---- one sweep over the slots (4 consecutive slots per lane and step): cutoffs, positions, survivors listed in
-				// output order; the list is emitted lane-dense whenever the next step might not fit
-				uint32_t running = 0, listed_from = 0;          // survivors so far in this round; first position held by the list
-				auto flush = [&](uint32_t upto) {                // emits the listed survivors [listed_from, upto)
+				const uint32_t w_excl = inc - __popc(w_main);
+				const uint32_t n_main = __shfl_sync(FULL, inc, 31);
+				__syncwarp();
+				if (lane < (uint32_t)NW) { S.surv[lane] = w_main; S.over[lane] = w_excl; }
+				// ---- survivors: listed group by group (kLwList positions at a time); inside its group a k-mer is placed by comparing it
+				// with the other survivors of the word; emitted lane-dense
+				for (uint32_t q0 = 0; q0 < n_main; q0 += kLwList) {
 					__syncwarp();
-					for (uint32_t p = listed_from + lane; p < upto; p += 32) {
-						const uint32_t v = S.list[p - listed_from];
-						R kk; uint32_t c;
-						if (v & 0x8000u) { const uint32_t h = v & 0x7fffu; kk = side_key(h); c = S.scnt[h]; }
-						else { const uint64_t ent = S.main[v]; kk = main_key(v, ent); c = (uint32_t)ent & cmask; }
+					{
+						uint32_t w = w_main, q = w_excl;
+						while (w) {
+							const uint32_t b = __ffs(w) - 1;
+							w &= w - 1;
+							if (q - q0 < (uint32_t)kLwList) list[q - q0] = (uint16_t)(lane * 32 + b);
+							++q;
+						}
+					}
+					__syncwarp();
+					const uint32_t q1 = min(n_main, q0 + (uint32_t)kLwList);
+					for (uint32_t q = q0 + lane; q < q1; q += 32) {
+						const uint32_t s = list[q - q0];
+						const uint64_t ent = S.main[s];
+						const R kk = entry_key(s, ent);
+						const uint32_t w0 = (s >> kLwGroupBits) << (kLwGroupBits - 5);          // first bitmap word of the group
+						uint32_t pos = S.over[w0];
+#pragma unroll
+						for (uint32_t wi = 0; wi < (1u << (kLwGroupBits - 5)); ++wi) {
+							uint32_t others = S.surv[w0 + wi];
+							if (w0 + wi == (s >> 5)) others &= ~(1u << (s & 31u));
+							while (others) {
+								const uint32_t s2 = ((w0 + wi) << 5) | (uint32_t)(__ffs(others) - 1);
+								others &= others - 1;
+								pos += rec_less<WORDS>(entry_key(s2, S.main[s2]), kk) ? 1u : 0u;
+							}
+						}
+						const uint32_t c = (uint32_t)ent & cmask;
 						const uint32_t value = c > a.counter_max ? a.counter_max : c;          // kb_sorter.h:1190
-						uint64_t* dst = tmp64 + (lo + emit_base + p) * padw;
+						uint64_t* dst = tmp64 + (lo + emit_base + pos) * padw;
 						for (uint32_t w = 0; w < padw; ++w) dst[w] = lw_out_word<WORDS>(kk, value, a.suffix_bytes, w);
 						if (!one_prefix) atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + rec_prefix<WORDS>(kk, prefix_shift), 1ull);     // kb_sorter.h:1203
 					}
-					__syncwarp();
-					listed_from = upto;
-				};
-				for (int it = 0; it < SLOTS / 128; ++it) {
-					const uint32_t g = it * 32 + lane;           // group of 4 slots
-					if (running - listed_from + 128u + n_dense > (uint32_t)kLwRetry) flush(running);
-					const uint4 x0 = reinterpret_cast<const uint4*>(S.main)[2 * g], x1 = reinterpret_cast<const uint4*>(S.main)[2 * g + 1];
-					const uint32_t xs = n_dense ? S.extra[g] : 0u;
-					const uint64_t ent[4] = {((uint64_t)x0.y << 32) | x0.x, ((uint64_t)x0.w << 32) | x0.z, ((uint64_t)x1.y << 32) | x1.x, ((uint64_t)x1.w << 32) | x1.z};
-					uint32_t nib = 0;
-#pragma unroll
-					for (int i = 0; i < 4; ++i) {
-						const bool occ = ent[i] != kLwEmpty;
-						const uint32_t c = (uint32_t)ent[i] & cmask;
-						const bool sv = occ && survives(c);
-						n_unique += occ;
-						n_min += occ && c < a.cutoff_min;
-						n_max += occ && !sv && c >= a.cutoff_min;
-						nib |= sv ? (1u << i) : 0u;
-					}
-					const uint32_t c4 = __popc(nib) + lw_bytesum(xs);
-					uint32_t inc = c4;
-#pragma unroll
-					for (int o = 1; o < 32; o <<= 1) {
-						const uint32_t t = __shfl_up_sync(FULL, inc, o);
-						if (lane >= (uint32_t)o) inc += t;
-					}
-					const uint32_t base = running + inc - c4;
-					running += __shfl_sync(FULL, inc, 31);
-					if (xs) S.gbase[g] = (uint16_t)base;
-					uint32_t off = 0;
-#pragma unroll
-					for (int i = 0; i < 4; ++i) {
-						const uint32_t xi = (xs >> (8 * i)) & 0xffu;
-						if (((nib >> i) & 1u) && xi == 0) S.list[base + off - listed_from] = (uint16_t)(4 * g + i);      // slots with side entries: below
-						off += ((nib >> i) & 1u) + xi;
-					}
-					if (__any_sync(FULL, xs != 0)) {
-						// ---- slots that hold surviving side entries: every side entry ranks itself among the entries of its slot
-						__syncwarp();
-						for (uint32_t f = lane; f < n_dense; f += 32) {
-							const uint32_t h = S.dense[f];
-							const R kk = side_key(h);
-							const uint32_t s = rec_bits<WORDS>(kk, slot_shift, SLOTS - 1);
-							if ((s >> 7) != (uint32_t)it) continue;
-							const uint32_t gg = s >> 2, ii = s & 3u;
-							const uint32_t xg = S.extra[gg];
-							uint32_t o2 = 0;
-							bool main_sv = false;
-							uint64_t main_ent = 0;
-#pragma unroll
-							for (int i = 0; i < 4; ++i) {
-								const uint64_t en = S.main[4 * gg + i];
-								const bool sv = en != kLwEmpty && survives((uint32_t)en & cmask);
-								if ((uint32_t)i < ii) o2 += (sv ? 1u : 0u) + ((xg >> (8 * i)) & 0xffu);
-								if ((uint32_t)i == ii) { main_sv = sv; main_ent = en; }
-							}
-							const uint32_t p0 = (uint32_t)S.gbase[gg] + o2;              // first position of the slot
-							const uint32_t xi = (xg >> (8 * ii)) & 0xffu;
-							uint32_t rank = 0, side_lt_main = 0;
-							R mk;
-							if (main_sv) { mk = main_key(s, main_ent); rank += rec_less<WORDS>(mk, kk) ? 1u : 0u; }
-							bool first = true;                                            // the smallest side entry of the slot also places the main entry
-							if (xi > 1) {
-								for (uint32_t f2 = 0; f2 < n_dense; ++f2) {
-									if (f2 == f) continue;
-									const R k2 = side_key(S.dense[f2]);
-									if (rec_bits<WORDS>(k2, slot_shift, SLOTS - 1) != s) continue;
-									if (rec_less<WORDS>(k2, kk)) { ++rank; first = false; }
-									if (main_sv && rec_less<WORDS>(k2, mk)) ++side_lt_main;
-								}
-							}
-							S.list[p0 + rank - listed_from] = (uint16_t)(0x8000u | h);
-							if (main_sv && first) {
-								side_lt_main += rec_less<WORDS>(kk, mk) ? 1u : 0u;
-								S.list[p0 + side_lt_main - listed_from] = (uint16_t)s;
-							}
-						}
-					}
 				}
-				flush(running);
-				emit_base += running;
+				emit_base += n_main;
 				// ---- next round: back up from finished halves of a split, then one step to the right
 				while (e > e0 && (r & 1u)) { r >>= 1; --e; }
 				++r;
@@ -415,6 +431,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 		}
 		if (lane == 0) {
 			a.leaf_emit[leaf] = failed ? 0u : emit_base;
+			t_emit += emit_base;
 			if (one_prefix && emit_base && !failed)
 				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (leaf >> (prefix_shift - a.low_bits)), (unsigned long long)emit_base);      // leaf = k-mer >> low_bits
 		}
@@ -422,17 +439,17 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 		leaf = __shfl_sync(FULL, next_t, 0);
 	}
 	// ---- statistics of this warp
+	failed = __any_sync(FULL, failed);
 	if (failed) { if (lane == 0) atomicOr(a.flags, kMsdFlagFallback); return; }
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
-		n_unique += __shfl_down_sync(FULL, n_unique, o);
-		n_min += __shfl_down_sync(FULL, n_min, o);
-		n_max += __shfl_down_sync(FULL, n_max, o);
+		t_unique += __shfl_down_sync(FULL, t_unique, o);
+		t_max += __shfl_down_sync(FULL, t_max, o);
 	}
 	if (lane == 0) {
-		if (n_unique) atomicAdd(reinterpret_cast<unsigned long long*>(a.result), (unsigned long long)n_unique);
-		if (n_min) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 1, (unsigned long long)n_min);
-		if (n_max) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 2, (unsigned long long)n_max);
+		if (t_unique) atomicAdd(reinterpret_cast<unsigned long long*>(a.result), (unsigned long long)t_unique);
+		if (t_unique - t_emit - t_max) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 1, (unsigned long long)(t_unique - t_emit - t_max));
+		if (t_max) atomicAdd(reinterpret_cast<unsigned long long*>(a.result) + 2, (unsigned long long)t_max);
 	}
 }
 
