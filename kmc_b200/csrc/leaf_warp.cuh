@@ -38,7 +38,7 @@ namespace kmcb {
 constexpr int kLwWarps = 4;                      // warps per CTA (independent of each other)
 constexpr uint32_t kLwGroupBits = 6;              // slots per group = 64: a real k-mer and its error variants share a group, groups must absorb such clumps
 constexpr int kLwList = 256;                     // u16 list of survivors, one step of the emission
-constexpr uint32_t kLwRing = 128;                // ring of compacted k-mers (WORDS == 1, multi-round leaves)
+constexpr uint32_t kLwRing = 256;                // ring of compacted k-mers (WORDS == 1, multi-round leaves)
 constexpr uint32_t kLwMaxLeaf = 65534;           // records of a warp-counted leaf (count field >= 16 bits)
 constexpr uint32_t kLwMaxSplit = 12;             // extra split bits a round may descend
 constexpr uint64_t kLwEmpty = ~0ull;
@@ -127,17 +127,18 @@ __device__ __forceinline__ uint32_t lw_hash(const Rec<WORDS>& r)
 // cutoffs applied on the way (kb_sorter.h:1174-1191): what happens when a count goes from c-1 to c
 struct LwCut {
 	uint32_t cmin;               // max(cutoff_min, 1): reaching it makes a survivor ...
-	uint32_t cmax;               // ... exceeding cutoff_max unmakes it
+	uint32_t cmax1;              // ... reaching cutoff_max + 1 unmakes it (0 = never: cutoff_max is 2^32 - 1)
 	bool never;                  // cutoff_max < cutoff_min: nothing survives, whatever reaches cmin counts as n_cutoff_max
 };
 // (two bitmaps, both only ever OR-ed: the result does not depend on the order in which lanes get to run)
 __device__ __forceinline__ void lw_transition(const LwCut& c, uint32_t newc, uint32_t* reached, uint32_t* over, uint32_t idx, uint32_t& r_max)
 {
+	if (newc != c.cmin && newc != c.cmax1) return;          // almost every add
 	if (newc == c.cmin) {
 		if (c.never) ++r_max;
 		else atomicOr(&reached[idx >> 5], 1u << (idx & 31u));
 	}
-	if (newc - 1u == c.cmax && !c.never) { atomicOr(&over[idx >> 5], 1u << (idx & 31u)); ++r_max; }
+	if (newc == c.cmax1 && !c.never) { atomicOr(&over[idx >> 5], 1u << (idx & 31u)); ++r_max; }
 }
 
 // ---- WORDS == 1: V k-mers per lane into the warp's table.  The first probes of all V are issued before any result is looked at
@@ -183,7 +184,7 @@ __device__ __forceinline__ void lw_insert1(const LwRound& t, const uint64_t (&kk
 }
 
 template <int WORDS, int SLOT_BITS>
-__global__ void __launch_bounds__(32 * kLwWarps, 8) leaf_warp_kernel(const LeafArgs a)
+__global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafArgs a)
 {
 	using R = Rec<WORDS>;
 	using SM = LwSmem<SLOT_BITS>;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, 8) leaf_warp_kernel(const LeafA
 	const uint32_t padw = (ob + 7) >> 3;                                   // temporary records: padw 64-bit words
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const bool one_prefix = prefix_shift >= a.low_bits;                    // every k-mer of a leaf has the same LUT prefix
-	const LwCut cut{a.cutoff_min > 1u ? a.cutoff_min : 1u, a.cutoff_max, a.cutoff_max < (a.cutoff_min > 1u ? a.cutoff_min : 1u)};
+	const LwCut cut{a.cutoff_min > 1u ? a.cutoff_min : 1u, a.cutoff_max + 1u, a.cutoff_max < (a.cutoff_min > 1u ? a.cutoff_min : 1u)};
 	uint64_t* const tmp64 = reinterpret_cast<uint64_t*>(a.tmp);
 	uint16_t* const list = S.list();
 	uint32_t t_unique = 0, t_max = 0, t_emit = 0;        // per lane; n_cutoff_min = unique - emitted - n_cutoff_max
@@ -264,34 +265,33 @@ __global__ void __launch_bounds__(32 * kLwWarps, 8) leaf_warp_kernel(const LeafA
 					} else {
 						// one of several rounds: a cheap scan compacts this round's k-mers into a ring, the ring is inserted 64 at a time
 						uint32_t head = 0, tail = 0;
-						uint64_t nx[2];
+						uint64_t nx[4];
 #pragma unroll
-						for (int u = 0; u < 2; ++u) { const uint32_t j = u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
-						for (uint32_t j0 = 0;; j0 += 64) {
-							if (j0 < m) {
-								uint64_t cur[2];
-								bool in[2];
+						for (int u = 0; u < 4; ++u) { const uint32_t j = u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+						for (uint32_t j0 = 0; j0 < m && ok; j0 += 128) {
+							uint64_t cur[4];
+							bool in[4];
 #pragma unroll
-								for (int u = 0; u < 2; ++u) { cur[u] = nx[u]; in[u] = (j0 + u * 32 + lane < m) && ((uint32_t)(cur[u] >> sub_shift) & emask) == r; }
+							for (int u = 0; u < 4; ++u) { cur[u] = nx[u]; in[u] = (j0 + u * 32 + lane < m) && ((uint32_t)(cur[u] >> sub_shift) & emask) == r; }
 #pragma unroll
-								for (int u = 0; u < 2; ++u) { const uint32_t j = j0 + 64 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+							for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + 128 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
 #pragma unroll
-								for (int u = 0; u < 2; ++u) {
-									const uint32_t bal = __ballot_sync(FULL, in[u]);
-									if (in[u]) S.ring[(tail + __popc(bal & lt)) & (kLwRing - 1)] = cur[u];
-									tail += __popc(bal);
-								}
+							for (int u = 0; u < 4; ++u) {
+								const uint32_t bal = __ballot_sync(FULL, in[u]);
+								if (in[u]) S.ring[(tail + __popc(bal & lt)) & (kLwRing - 1)] = cur[u];
+								tail += __popc(bal);
 							}
-							const uint32_t avail = tail - head;
-							if (avail >= 64 || (j0 + 64 >= m && avail)) {
+							const bool last = j0 + 128 >= m;
+							while (tail - head >= 64 || (last && tail != head)) {
+								const uint32_t avail = tail - head;
 								__syncwarp();
 								const uint64_t kk[2] = {S.ring[(head + lane) & (kLwRing - 1)], S.ring[(head + 32 + lane) & (kLwRing - 1)]};
 								__syncwarp();
 								head += min(avail, 64u);
 								lw_insert1<2>(T, kk, (lane < avail ? 1u : 0u) | (32 + lane < avail ? 2u : 0u), r_claim, r_max, ok);
-								if (!__all_sync(FULL, ok)) break;
+								ok = __all_sync(FULL, ok);
+								if (!ok) break;                            // a group is full: the round is split
 							}
-							if (j0 + 64 >= m && tail == head) break;
 						}
 					}
 				} else {
