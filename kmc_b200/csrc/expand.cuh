@@ -55,7 +55,14 @@ struct ExpandArgs {
 	uint64_t* item_lo1;          // [total_tiles] first output record of the tile
 	uint16_t* item_cnt1;         // [total_tiles]
 	uint32_t top_shift;
+	// oversized bins (kmc_b200.cu, run_oversized_bin): the bin is expanded chunk by chunk, once to count and once per key block
+	uint32_t mode;               // 0: everything (above); 1: only count the top 12 bits into hist12; 2: only k-mers of one key block, appended to recs
+	uint32_t fshift, fprefix, fmask;    // mode 2: keep the k-mers with ((kmer >> fshift) & fmask) == fprefix
+	uint64_t* hist12;            // mode 1: [4096]
+	unsigned long long* out_counter;     // mode 2: records appended so far
 };
+enum : uint32_t { kExpandAll = 0, kExpandCount12 = 1, kExpandFilter = 2 };
+constexpr uint64_t kExpandUnknownRecs = ~0ull;      // n_rec of a chunk: not checked
 
 enum : uint32_t { kErrPackWalk = 1, kErrRecCount = 2 };
 
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
 		a.pack_kbase[a.n_packs] = carry_k;
 		a.pack_tbase[a.n_packs] = carry_t;
 		a.status[1] = carry_t;
-		if (carry_k != a.n_rec) atomicOr(a.status, kErrRecCount);
+		if (a.n_rec != kExpandUnknownRecs && carry_k != a.n_rec) atomicOr(a.status, kErrRecCount);
 	}
 }
 
@@ -348,6 +355,23 @@ __device__ __forceinline__ uint32_t rec_top_digit(const Rec<WORDS>& r, uint32_t 
 	return (uint32_t)v & 0xFFu;
 }
 
+// bits [shift, shift + ...) of a record under `mask` (mask <= 32 bits)
+template <int WORDS>
+__device__ __forceinline__ uint32_t msd_free_bits(const Rec<WORDS>& r, uint32_t shift, uint32_t mask)
+{
+	if (WORDS == 1) return (uint32_t)(r.w[0] >> shift) & mask;
+	const uint32_t wi = shift >> 6, off = shift & 63u;
+	uint64_t lo = r.w[0], hi = 0;
+#pragma unroll
+	for (int i = 1; i < WORDS; ++i) {
+		if (wi == (uint32_t)i) lo = r.w[i];
+		if (wi + 1 == (uint32_t)i) hi = r.w[i];
+	}
+	uint64_t v = lo >> off;
+	if (off) v |= hi << (64u - off);
+	return (uint32_t)v & mask;
+}
+
 template <int WORDS>
 __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(const ExpandArgs a)
 {
@@ -359,6 +383,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 	__shared__ uint32_t s_kpre[MAXSK], s_off[MAXSK];
 	__shared__ __align__(16) uint8_t s_bytes[STAGE];
 	__shared__ uint32_t s_jmax;
+	__shared__ unsigned long long s_fbase;
 	__shared__ uint32_t hist[256], htop[256];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid < 256) { hist[tid] = 0; htop[tid] = 0; }
@@ -430,34 +455,65 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 
 		// striped extraction: consecutive lanes <-> consecutive output k-mers
 		const uint64_t obase = a.pack_kbase[p] + tile_start;
+		auto kmer_of = [&](uint32_t slot) -> Rec<WORDS> {
+			const uint32_t rel = head[slot];
+			if (staged) {
+				const uint32_t s = tile_start + slot - s_kpre[rel];
+				return extract_kmer<WORDS>(a.bin + s_off[rel] + 1, s, a.k, a.both_strands != 0,
+					[&](uintptr_t wa) { return *reinterpret_cast<const unsigned long long*>(s_bytes + (wa - g0a)); });
+			}
+			const uint32_t j = j_lo + rel;
+			const uint32_t s = tile_start + slot - kpre[j];
+			return extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0,
+				[](uintptr_t wa) { return __ldg(reinterpret_cast<const unsigned long long*>(wa)); });
+		};
+		if (a.mode == kExpandAll) {
 #pragma unroll 2
-		for (int i = 0; i < IPT; ++i) {
-			const uint32_t slot = i * kExpandThreads + tid;
-			if (slot < cnt) {
-				const uint32_t rel = head[slot];
-				Rec<WORDS> r;
-				if (staged) {
-					const uint32_t s = tile_start + slot - s_kpre[rel];
-					r = extract_kmer<WORDS>(a.bin + s_off[rel] + 1, s, a.k, a.both_strands != 0,
-						[&](uintptr_t wa) { return *reinterpret_cast<const unsigned long long*>(s_bytes + (wa - g0a)); });
-				} else {
-					const uint32_t j = j_lo + rel;
-					const uint32_t s = tile_start + slot - kpre[j];
-					r = extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0,
-						[](uintptr_t wa) { return __ldg(reinterpret_cast<const unsigned long long*>(wa)); });
+			for (int i = 0; i < IPT; ++i) {
+				const uint32_t slot = i * kExpandThreads + tid;
+				if (slot < cnt) {
+					const Rec<WORDS> r = kmer_of(slot);
+					out[obase + slot] = r;
+					atomicAdd(&hist[(uint32_t)r.w[0] & 0xFFu], 1u);
+					atomicAdd(&htop[rec_top_digit<WORDS>(r, a.top_shift)], 1u);
 				}
-				out[obase + slot] = r;
-				atomicAdd(&hist[(uint32_t)r.w[0] & 0xFFu], 1u);
-				atomicAdd(&htop[rec_top_digit<WORDS>(r, a.top_shift)], 1u);
+			}
+			__syncthreads();
+			// this tile is one work item of the level-1 partition: its digit counts go straight into the cell layout
+			if (tid < 256) {
+				a.cells1[(uint64_t)tid * total_tiles + g] = (uint16_t)htop[tid];
+				htop[tid] = 0;
+			}
+			if (tid == 0) { a.item_lo1[g] = obase; a.item_cnt1[g] = (uint16_t)cnt; }
+		} else if (a.mode == kExpandCount12) {
+			// oversized bin, first pass: where do the k-mers fall?  (top 12 bits; nothing is written)
+			for (int i = 0; i < IPT; ++i) {
+				const uint32_t slot = i * kExpandThreads + tid;
+				if (slot < cnt) {
+					const Rec<WORDS> r = kmer_of(slot);
+					atomicAdd(reinterpret_cast<unsigned long long*>(a.hist12) + msd_free_bits<WORDS>(r, a.fshift, 0xFFFu), 1ull);
+				}
+			}
+		} else {
+			// oversized bin, one key block: the k-mers of the block are appended densely (their order does not matter, they get sorted)
+			for (int i = 0; i < IPT; ++i) {
+				const uint32_t slot = i * kExpandThreads + tid;
+				Rec<WORDS> r;
+				bool keep = false;
+				if (slot < cnt) { r = kmer_of(slot); keep = msd_free_bits<WORDS>(r, a.fshift, a.fmask) == a.fprefix; }
+				const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+				__syncthreads();          // (warp_max / s_jmax are free again)
+				if (lane == 0) warp_max[warp] = __popc(bal);
+				__syncthreads();
+				if (tid == 0) {
+					uint32_t tot = 0;
+					for (int w = 0; w < kExpandThreads / 32; ++w) { const uint32_t c = warp_max[w]; warp_max[w] = tot; tot += c; }
+					s_fbase = tot ? atomicAdd(a.out_counter, (unsigned long long)tot) : 0ull;
+				}
+				__syncthreads();
+				if (keep) out[s_fbase + warp_max[warp] + __popc(bal & lanemask_lt())] = r;
 			}
 		}
-		__syncthreads();
-		// this tile is one work item of the level-1 partition: its digit counts go straight into the cell layout
-		if (tid < 256) {
-			a.cells1[(uint64_t)tid * total_tiles + g] = (uint16_t)htop[tid];
-			htop[tid] = 0;
-		}
-		if (tid == 0) { a.item_lo1[g] = obase; a.item_cnt1[g] = (uint16_t)cnt; }
 	}
 	__syncthreads();
 	if (tid < 256) {

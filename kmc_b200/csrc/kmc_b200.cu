@@ -84,6 +84,9 @@ struct Slot {
 	cudaEvent_t ev_pass[kMaxPasses + 8] = {};
 	int n_passes_run = 0;                                   // number of timed sort intervals (ev_pass[i] .. ev_pass[i+1])
 	bool ran_expand = false, ran_sort = false, ran_count = false;
+	// oversized bins
+	uint64_t* d_hist12 = nullptr; unsigned long long* d_out_counter = nullptr;
+	bool sync_done = false; uint64_t sync_out_bytes = 0; uint64_t sync_stats[4] = {};
 	// pending host-buffer bin
 	bool busy = false;
 	uint8_t* host_out = nullptr; uint64_t host_out_cap = 0; uint64_t* host_lut = nullptr; uint64_t pending_n_rec = 0;
@@ -101,6 +104,8 @@ struct kmcb200_ctx {
 	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
+	uint64_t max_block_records = 1ull << 28;                // KMCB200_MAX_BLOCK_RECORDS: a bin with more k-mers is counted key block by key block
+	uint64_t max_chunk_bytes = 1ull << 30;                  // KMCB200_MAX_CHUNK_BYTES: ... and expanded chunk by chunk
 	int leaf_slot_bits = 9;                                 // KMCB200_LEAF_SLOT_BITS = 8 | 9 | 10: slots of a warp's leaf table
 	uint32_t epoch = 1;
 	uint64_t launches = 0;
@@ -184,7 +189,8 @@ int setup_kernels(kmcb200_ctx* ctx)
 template <int WORDS>
 int launch_expand(kmcb200_ctx* ctx, const ExpandArgs& a, cudaStream_t st)
 {
-	const uint32_t max_tiles = (uint32_t)(a.n_rec / ExpandCfg<WORDS>::kTile) + a.n_packs + 1;
+	const uint64_t n_bound = a.n_rec == kExpandUnknownRecs ? a.size * 4 : a.n_rec;
+	const uint32_t max_tiles = (uint32_t)(n_bound / ExpandCfg<WORDS>::kTile) + a.n_packs + 1;
 	const uint32_t grid = std::min<uint32_t>(max_tiles, (uint32_t)(ctx->sm_count * ctx->occ_expand));
 	expand_kernel<WORDS><<<grid, ExpandCfg<WORDS>::kThreads, 0, st>>>(a);
 	ctx->launches++;
@@ -421,8 +427,14 @@ int check_slot(kmcb200_ctx* ctx, uint32_t slot)
 }
 
 // index + expand; pack_bytes is a host array (may be null / empty: the whole bin is one pack)
+struct ExpandMode {            // oversized bins: count the top 12 bits / keep one key block (expand.cuh)
+	uint32_t mode = kExpandAll, fshift = 0, fprefix = 0, fmask = 0xFFFu;
+	uint64_t* hist12 = nullptr;
+	unsigned long long* out_counter = nullptr;
+};
+
 int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec,
-	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st)
+	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st, const ExpandMode& em = ExpandMode())
 {
 	if (size >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin of %llu bytes: bins of 4 GiB or more are not supported", (unsigned long long)size);
 	const uint32_t k = ctx->prm.kmer_len;
@@ -467,7 +479,8 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	if (int rc = ensure(ctx, s.sk_off, s.sk_off_cap, size / min_rec + 2)) return rc;
 	if (int rc = ensure(ctx, s.sk_kpre, s.sk_kpre_cap, size / min_rec + 2)) return rc;
 	if (int rc = ensure(ctx, s.tile_first, s.tile_first_cap, size * 4 / kExpandMinTile + np + 2)) return rc;
-	if (int rc = ensure(ctx, s.tile_pack, s.tile_pack_cap, n_rec / kExpandMinTile + np + 2)) return rc;
+	const uint64_t n_bound = n_rec == kExpandUnknownRecs ? size * 4 : n_rec;        // a record of 1 + ceil((k+a)/4) bytes holds a+1 k-mers: < 4 per byte
+	if (int rc = ensure(ctx, s.tile_pack, s.tile_pack_cap, n_bound / kExpandMinTile + np + 2)) return rc;
 
 	ExpandArgs a;
 	a.bin = d_bin; a.size = size; a.pack_start = s.d_pack_start; a.n_packs = np; a.k = k; a.min_rec_bytes = min_rec;
@@ -476,8 +489,11 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
 	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.status = s.zero->status;
 	a.recs = d_recs; a.hist0 = s.zero->hist[0];
-	if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np)) return rc;
-	a.cells1 = s.msd_cells; a.item_lo1 = s.msd_item_lo1; a.item_cnt1 = s.msd_item_cnt1;
+	a.mode = em.mode; a.fshift = em.fshift; a.fprefix = em.fprefix; a.fmask = em.fmask; a.hist12 = em.hist12; a.out_counter = em.out_counter;
+	if (em.mode == kExpandAll) {
+		if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np)) return rc;
+		a.cells1 = s.msd_cells; a.item_lo1 = s.msd_item_lo1; a.item_cnt1 = s.msd_item_cnt1;
+	} else { a.cells1 = nullptr; a.item_lo1 = nullptr; a.item_cnt1 = nullptr; }
 	a.top_shift = std::max(2u * k, 8u) - 8u;
 	s.last_n_packs = np;
 
@@ -537,11 +553,14 @@ template <int WORDS> int setup_leaves_w(kmcb200_ctx* ctx) { return DISPATCH_SLOT
 // Partition (two MSD levels), then COUNT the leaves (leaf_warp.cuh) instead of sorting them; the LSD passes + count_emit_kernel
 // stand behind as the device-flagged fallback (they return at once unless a leaf could not be counted).
 template <int WORDS>
-int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np_eff, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np_eff, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st,
+	bool from_blocks = false, uint32_t block_bits = 0, uint32_t block_prefix = 0)
 {
+	// block_bits > 0: the records are one key block of an oversized bin (all share their top block_bits bits = block_prefix):
+	// the sort starts below those bits, and nobody has counted the first digit yet
 	bool in_b = false;
 	LeafPlan plan;
-	if (int rc = launch_sort<WORDS>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b, &plan)) return rc;
+	if (int rc = launch_sort<WORDS>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len - block_bits, !from_blocks, np_eff, st, &in_b, &plan)) return rc;
 	if (!plan.active) {          // small bin: plain LSD passes, classic count
 		CU(cudaEventRecord(s.ev_sort, st));
 		s.ran_sort = true;
@@ -556,6 +575,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	uint32_t* flags = s.zero->msd_flags;
 	LeafArgs la{};
 	la.recs = plan.recs; la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
+	la.leaf_prefix = block_bits ? block_prefix * plan.n_leaves : 0u;          // n_leaves is a power of two
 	la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
 	la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
 	la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
@@ -615,6 +635,116 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Oversized bins (the reference's answer is strict-memory mode, bkb_sorter.h / bkb_merger.h): more k-mers than
+// one sort should take, or 4 GiB and more of bin bytes.  The bin bytes (~1.1 B per k-mer) stay in HBM, the RECORDS (8-32 B per k-mer,
+// twice) are what does not fit, so the k-mer space is cut into aligned key blocks (a prefix of <= 12 bits each) that hold at most
+// max_block_records k-mers: one expansion pass counts the top 12 bits, then every block is expanded again with a filter, sorted and
+// counted on its own.  Blocks are disjoint ranges of the sorted order, so their outputs simply follow each other, the LUTs add up,
+// and the result is bit-identical to the one-shot path.  The input is cut at pack boundaries into chunks (< 2 GiB, u32 offsets).
+int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
+	uint8_t* h_out, uint64_t out_capacity, uint64_t* h_lut, uint64_t* out_bytes, uint64_t stats[4])
+{
+	cudaStream_t st = ctx->compute;
+	const uint32_t k = ctx->prm.kmer_len;
+	if (2 * k < 24) return fail(ctx, KMCB200_ERR_INVALID, "a bin of %llu k-mers with k = %u: oversized bins need k >= 12", (unsigned long long)n_rec, k);
+	if (!pack_bytes || n_packs == 0) return fail(ctx, KMCB200_ERR_INVALID, "an oversized bin (%llu bytes, %llu k-mers) needs its expander packs", (unsigned long long)size, (unsigned long long)n_rec);
+	struct Chunk { uint32_t pack0, npacks; uint64_t byte0, bytes, dev_off; };
+	std::vector<Chunk> chunks;
+	{
+		Chunk c{0, 0, 0, 0, 0};
+		uint64_t pos = 0, dev = 0;
+		for (uint32_t i = 0; i < n_packs; ++i) {
+			if (pack_bytes[i] >= ctx->max_chunk_bytes) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander pack %u has %llu bytes", i, (unsigned long long)pack_bytes[i]);
+			if (c.npacks && c.bytes + pack_bytes[i] > ctx->max_chunk_bytes) { c.dev_off = dev; dev += (c.bytes + 64 + 15) & ~15ull; chunks.push_back(c); c = Chunk{i, 0, pos, 0, 0}; }
+			c.npacks++; c.bytes += pack_bytes[i]; pos += pack_bytes[i];
+		}
+		if (c.npacks) { c.dev_off = dev; dev += (c.bytes + 64 + 15) & ~15ull; chunks.push_back(c); }
+		if (pos != size) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander packs cover %llu bytes but the bin has %llu", (unsigned long long)pos, (unsigned long long)size);
+		if (int rc = ensure(ctx, s.d_bin, s.bin_cap, dev + 64)) return rc;
+	}
+	for (const Chunk& c : chunks) CU(cudaMemcpyAsync(s.d_bin + c.dev_off, h_bin + c.byte0, c.bytes, cudaMemcpyHostToDevice, st));
+	if (!s.d_hist12) { CU(cudaMalloc(reinterpret_cast<void**>(&s.d_hist12), 4096 * 8)); CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), 8)); }
+	// ---- pass 0: where do the k-mers fall (top 12 bits)?  Also checks the packs and n_rec.
+	CU(cudaMemsetAsync(s.d_hist12, 0, 4096 * 8, st));
+	ExpandMode em;
+	em.mode = kExpandCount12; em.fshift = 2 * k - 12; em.hist12 = s.d_hist12;
+	for (const Chunk& c : chunks) {
+		if (int rc = stage_expand(ctx, s, s.d_bin + c.dev_off, c.bytes, kExpandUnknownRecs, pack_bytes + c.pack0, c.npacks, nullptr, st, em)) return rc;
+		uint32_t status = 0;
+		CU(cudaMemcpyAsync(&status, s.zero->status, 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		if (status & kErrPackWalk) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: an expander pack does not end on a record boundary");
+	}
+	std::vector<uint64_t> hist(4096);
+	CU(cudaMemcpyAsync(hist.data(), s.d_hist12, 4096 * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	uint64_t total = 0;
+	for (uint64_t v : hist) total += v;
+	if (total != n_rec) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: the bin holds %llu k-mers, not n_rec = %llu", (unsigned long long)total, (unsigned long long)n_rec);
+	// ---- key blocks: aligned prefixes of <= 12 bits with at most max_block_records k-mers (bisection of the histogram)
+	struct Block { uint32_t prefix, bits; uint64_t n; };
+	std::vector<Block> blocks;
+	struct Range { uint32_t lo, len; };
+	std::vector<Range> todo{{0, 4096}};
+	while (!todo.empty()) {
+		const Range r = todo.back(); todo.pop_back();
+		uint64_t cnt = 0;
+		for (uint32_t i = r.lo; i < r.lo + r.len; ++i) cnt += hist[i];
+		if (cnt == 0) continue;
+		if (cnt <= ctx->max_block_records || r.len == 1) {
+			if (cnt >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin too skewed: %llu k-mers share their first 6 symbols", (unsigned long long)cnt);
+			uint32_t lg = 0; while ((1u << lg) < r.len) ++lg;
+			blocks.push_back(Block{r.lo >> lg, 12 - lg, cnt});
+		} else { todo.push_back(Range{r.lo + r.len / 2, r.len / 2}); todo.push_back(Range{r.lo, r.len / 2}); }      // (the lower half is popped first)
+	}
+	// ---- every block: expand with the filter (all chunks), sort, count; outputs follow each other
+	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
+	const size_t rec_bytes = (size_t)ctx->words * 8;
+	std::vector<uint64_t> lut_blk(ctx->lut_entries);
+	for (uint64_t i = 0; i < ctx->lut_entries; ++i) h_lut[i] = 0;
+	uint64_t out_pos = 0, acc[3] = {0, 0, 0};
+	for (const Block& b : blocks) {
+		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, b.n * rec_bytes)) return rc;
+		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, b.n * rec_bytes)) return rc;
+		CU(cudaMemsetAsync(s.d_out_counter, 0, 8, st));
+		ExpandMode ef;
+		ef.mode = kExpandFilter; ef.fshift = 2 * k - b.bits; ef.fprefix = b.prefix; ef.out_counter = s.d_out_counter;
+		if (b.bits == 0) { ef.fshift = 0; ef.fprefix = 0; ef.fmask = 0; }          // one block = the whole bin (oversized only by its bytes): keep everything
+		for (const Chunk& c : chunks)
+			if (int rc = stage_expand(ctx, s, s.d_bin + c.dev_off, c.bytes, kExpandUnknownRecs, pack_bytes + c.pack0, c.npacks, s.recs_a, st, ef)) return rc;
+		const uint64_t cap_b = ((b.n + 1) / std::max(ctx->prm.cutoff_min, 1u)) * (uint64_t)ob;
+		if (int rc = ensure(ctx, s.d_out, s.out_cap, cap_b + 64)) return rc;
+		s.ran_expand = false;
+		CU(cudaEventRecord(s.ev_expand, st));
+		if (ctx->use_leaf) {
+			if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, b.n, 1u, s.d_out, cap_b, s.d_lut, s.d_result, st, true, b.bits, b.prefix)) return rc;
+		} else {
+			bool in_b = false;
+			if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, b.n, ctx->key_bytes, 2u * k - b.bits, false, 1u, st, &in_b)) return rc;
+			CU(cudaEventRecord(s.ev_sort, st));
+			if (int rc = stage_count(ctx, s, in_b ? s.recs_b : s.recs_a, b.n, s.d_out, cap_b, s.d_lut, s.d_result, st)) return rc;
+		}
+		uint64_t r[8];
+		unsigned long long appended = 0;
+		CU(cudaMemcpyAsync(r, s.d_result, 64, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(&appended, s.d_out_counter, 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(lut_blk.data(), s.d_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		if (appended != b.n) return fail(ctx, KMCB200_ERR_CUDA, "internal error: key block %u/%u took %llu k-mers, expected %llu", b.prefix, b.bits, appended, (unsigned long long)b.n);
+		const uint64_t bytes = r[4] * (uint64_t)ob;
+		if (r[5] || out_pos + bytes > out_capacity) return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small", (unsigned long long)out_capacity);
+		if (bytes) CU(cudaMemcpyAsync(h_out + out_pos, s.d_out, bytes, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		out_pos += bytes;
+		for (int i = 0; i < 3; ++i) acc[i] += r[i];
+		for (uint64_t i = 0; i < ctx->lut_entries; ++i) h_lut[i] += lut_blk[i];
+	}
+	if (out_bytes) *out_bytes = out_pos;
+	if (stats) { stats[0] = acc[0]; stats[1] = acc[1]; stats[2] = acc[2]; stats[3] = n_rec; }      // n_total = n_rec (kb_sorter.h:1166)
+	return 0;
+}
+
 }  // namespace
 
 // ================================================================================================= C ABI
@@ -648,6 +778,8 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	ctx->sm_count = dp.multiProcessorCount;
 	if (const char* e = getenv("KMCB200_SORT")) ctx->use_msd = std::string(e) != "lsd";
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
+	if (const char* e = getenv("KMCB200_MAX_BLOCK_RECORDS")) { const long long v = atoll(e); if (v >= 1024) ctx->max_block_records = (uint64_t)v; }
+	if (const char* e = getenv("KMCB200_MAX_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= (1 << 17) && v < (1ll << 31)) ctx->max_chunk_bytes = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_SLOT_BITS")) { const int b = atoi(e); if (b == 8 || b == 9 || b == 10) ctx->leaf_slot_bits = b; }
 	ctx->slots.resize(prm->n_slots);
 	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };
@@ -692,7 +824,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
-				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off})
+				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter})
 			if (p) cudaFree(p);
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
@@ -740,6 +872,12 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	if (s.busy) return fail(ctx, KMCB200_ERR_BUSY, "slot %u already holds a submitted bin", slot);
 	if ((size && !superkmers) || !lut || (!out_suffix && out_capacity)) return fail(ctx, KMCB200_ERR_INVALID, "null buffer");
 	if (int rc = set_device(ctx)) return rc;
+	if (n_rec > ctx->max_block_records || size >= 4 * ctx->max_chunk_bytes) {        // oversized: counted key block by key block, synchronously
+		CU(cudaStreamSynchronize(ctx->compute));
+		if (int rc = run_oversized_bin(ctx, s, superkmers, size, n_rec, pack_bytes, n_packs, out_suffix, out_capacity, lut, &s.sync_out_bytes, s.sync_stats)) return rc;
+		s.busy = true; s.sync_done = true;
+		return 0;
+	}
 	cudaStream_t st = s.stream;       // copies
 	if (int rc = ensure(ctx, s.d_bin, s.bin_cap, size + 64)) return rc;
 	if (int rc = ensure(ctx, s.d_out, s.out_cap, out_capacity + 64)) return rc;
@@ -764,6 +902,12 @@ int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint6
 	if (!s.busy) return fail(ctx, KMCB200_ERR_INVALID, "slot %u has no submitted bin", slot);
 	if (int rc = set_device(ctx)) return rc;
 	s.busy = false;
+	if (s.sync_done) {          // an oversized bin: everything happened inside submit
+		s.sync_done = false;
+		if (out_bytes) *out_bytes = s.sync_out_bytes;
+		if (stats) for (int i = 0; i < 4; ++i) stats[i] = s.sync_stats[i];
+		return 0;
+	}
 	CU(cudaEventSynchronize(s.ev_result));
 	const uint64_t* r = s.h_result;
 	if (r[6] & (kErrPackWalk | kErrRecCount)) {

@@ -48,6 +48,7 @@ struct LeafArgs {
 	const uint64_t* start;       // [n_leaves + 1]
 	uint32_t n_leaves;
 	uint32_t low_bits;           // bits below the partition digits
+	uint32_t leaf_prefix;        // key block of an oversized bin: (block prefix << log2(n_leaves)), so that (leaf_prefix | leaf) = k-mer >> low_bits; else 0
 	uint32_t k, lut_prefix_len, cutoff_min, cutoff_max, counter_max, counter_bytes, suffix_bytes;
 	uint8_t* tmp;                // leaf L writes its records, padded to a multiple of 8 bytes, at tmp + start[L] * pad
 	uint32_t* leaf_emit;         // [n_leaves] emitted records
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 				t_max += r_max;
 				// the k-mer of an entry
 				const uint64_t key_hi = (WORDS > 1 || (gshift + GB) >= 64) ? 0ull
-					: (((((uint64_t)leaf << a.low_bits) | ((uint64_t)r << sub_shift)) >> (gshift + GB)) << (gshift + GB));
+					: (((((uint64_t)(a.leaf_prefix | leaf) << a.low_bits) | ((uint64_t)r << sub_shift)) >> (gshift + GB)) << (gshift + GB));
 				auto entry_key = [&](uint32_t s, uint64_t ent) -> R {
 					R kk;
 					if (WORDS == 1) kk.w[0] = key_hi | ((uint64_t)(s >> kLwGroupBits) << gshift) | ((ent >> cb) & rem_mask);
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 			a.leaf_emit[leaf] = failed ? 0u : emit_base;
 			t_emit += emit_base;
 			if (one_prefix && emit_base && !failed)
-				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + (leaf >> (prefix_shift - a.low_bits)), (unsigned long long)emit_base);      // leaf = k-mer >> low_bits
+				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + ((a.leaf_prefix | leaf) >> (prefix_shift - a.low_bits)), (unsigned long long)emit_base);      // leaf = k-mer >> low_bits
 		}
 		if (failed) break;
 		leaf = __shfl_sync(FULL, next_t, 0);

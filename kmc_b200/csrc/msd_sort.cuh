@@ -252,26 +252,44 @@ template <int WORDS>
 __global__ void __launch_bounds__(512) msd_count_kernel(const MsdCountArgs p)
 {
 	using R = Rec<WORDS>;
-	__shared__ uint32_t sh[256];
+	__shared__ uint32_t sh[2][256];
 	if (*p.flags & kMsdFlagFallback) return;
 	const R* __restrict__ g = reinterpret_cast<const R*>(p.in);
 	const uint32_t n_items = *p.items.n_items;
 	const uint32_t mask = p.nd - 1;
 	const uint32_t tid = threadIdx.x;
-	for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-		const MsdItemGeom gm = msd_item_geom<WORDS>(p.items, item, p.nd);
-		if (tid < 256) sh[tid] = 0;
-		__syncthreads();
-		const uint32_t m = (uint32_t)(gm.hi - gm.lo);
-		constexpr int U = (msd_tile<WORDS>() + 511) / 512;
-		R k[U];
+	constexpr int U = (msd_tile<WORDS>() + 511) / 512;
+	if (tid < 256) { sh[0][tid] = 0; sh[1][tid] = 0; }
+	// software pipeline: the records of the next item are in flight while this one is counted; one barrier per item
+	uint32_t item = blockIdx.x;
+	MsdItemGeom gm{};
+	uint32_t m = 0;
+	R k[U];
+	if (item < n_items) {
+		gm = msd_item_geom<WORDS>(p.items, item, p.nd);
+		m = (uint32_t)(gm.hi - gm.lo);
 #pragma unroll
-		for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) k[u] = g[gm.lo + j]; }      // all loads in flight first
+		for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) k[u] = g[gm.lo + j]; }
+	}
+	__syncthreads();
+	int cur = 0;
+	while (item < n_items) {
 #pragma unroll
-		for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) atomicAdd(&sh[rec_bits<WORDS>(k[u], p.shift, mask)], 1u); }
+		for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) atomicAdd(&sh[cur][rec_bits<WORDS>(k[u], p.shift, mask)], 1u); }
+		const MsdItemGeom done = gm;
+		item += gridDim.x;
+		if (item < n_items) {
+			gm = msd_item_geom<WORDS>(p.items, item, p.nd);
+			m = (uint32_t)(gm.hi - gm.lo);
+#pragma unroll
+			for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) k[u] = g[gm.lo + j]; }
+		}
 		__syncthreads();
-		if (tid < p.nd) p.cells[gm.cell0 + (uint64_t)tid * gm.cell_stride] = (uint16_t)sh[tid];
-		__syncthreads();
+		if (tid < 256) {          // (a bin is read and zeroed by its own thread; it is used again two items later, a barrier in between)
+			if (tid < p.nd) p.cells[done.cell0 + (uint64_t)tid * done.cell_stride] = (uint16_t)sh[cur][tid];
+			sh[cur][tid] = 0;
+		}
+		cur ^= 1;
 	}
 }
 
