@@ -117,7 +117,7 @@ int kmcb200_dev_process_bin(kmcb200_ctx* ctx, uint32_t slot,
 	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, void* stream);
 
 /* Individual stages, for per-kernel measurement.  d_recs/d_tmp hold n records of 8*ceil(k/32) bytes.
- * kmcb200_dev_expand also leaves the histogram of the first radix digit in the slot's workspace, which
+ * kmcb200_dev_expand also leaves the first partition level's work items and digit counts in the slot's workspace, which
  * kmcb200_dev_sort(..., hist_ready=1) consumes; with hist_ready=0 the sort counts the first digit itself.
  * kmcb200_dev_sort returns 1 when the sorted records are in d_tmp, 0 when they are in d_recs. */
 int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkmers, uint64_t size, uint64_t n_rec,

@@ -32,3 +32,12 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+
+
+def build_variant(name, extra_flags):
+    """Experiment builds (compile-time knobs) next to the product library: build/libkmc_b200_<name>.so, selected by scripts/ via KMCB200_LIB."""
+    d = os.path.join(os.path.dirname(HERE), "build")
+    os.makedirs(d, exist_ok=True)
+    out = os.path.join(d, "libkmc_b200_%s.so" % name)
+    subprocess.check_call([NVCC] + FLAGS + list(extra_flags) + ["-o", out, SRC])
+    return out

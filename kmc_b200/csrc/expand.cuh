@@ -49,7 +49,6 @@ struct ExpandArgs {
 	uint32_t* status;            // [0] error bits, [1] total tiles
 	// output
 	void* recs;
-	uint64_t* hist0;             // [256] histogram of record byte 0 (zero-initialised): first digit of the LSD passes
 	// level-1 work items of the MSD partition = the output tiles of this kernel (msd_sort.cuh)
 	uint16_t* cells1;            // [256][total_tiles] counts of bits [top_shift, top_shift + 8) per tile
 	uint64_t* item_lo1;          // [total_tiles] first output record of the tile
@@ -86,7 +85,7 @@ constexpr int kWalkSpec = 1024;
 __global__ void __launch_bounds__(kWalkSegs) walk_packs_parallel_kernel(const ExpandArgs a, uint32_t* pack_done)
 {
 	extern __shared__ __align__(16) uint8_t wsm[];               // the pack (+ 16 bytes of slack)
-	__shared__ uint32_t s_entry[kWalkSegs], s_exit[kWalkSegs], s_nrec[kWalkSegs], s_nk[kWalkSegs], s_w[16];
+	__shared__ uint32_t s_entry[kWalkSegs], s_exit[kWalkSegs], s_w[16];
 	__shared__ uint32_t s_bad;
 	const uint32_t p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint64_t pstart = a.pack_start[p];
@@ -128,7 +127,6 @@ __global__ void __launch_bounds__(kWalkSegs) walk_packs_parallel_kernel(const Ex
 				s_entry[tid] = entry; s_exit[tid] = pos;
 			}
 		}
-		s_nrec[tid] = nrec; s_nk[tid] = nk;
 		__syncthreads();
 		// ---- verify (cheap, and the only thing correctness rests on)
 		bool bad = false;
@@ -339,6 +337,42 @@ __device__ __forceinline__ Rec<WORDS> extract_kmer(const uint8_t* payload, uint3
 	return rec_less<WORDS>(f, r) ? f : r;       // kmer < rev ? kmer : rev  (kb_sorter.h:340,356)
 }
 
+// The staged fast path: the tile's bytes lie in shared memory as BIG-ENDIAN 32-bit words (one byte_perm per word when they are
+// staged, not per k-mer), so the k-mer that starts at bit B of the staged stream is a funnel shift over 2*WORDS+1 consecutive words.
+// Bits past the k-mer (the next super-k-mer, or stale bytes behind the tile) only reach positions that the right-alignment shifts out.
+template <int WORDS>
+__device__ __forceinline__ Rec<WORDS> extract_kmer_be32(const uint32_t* sw, uint32_t B, uint32_t k, bool canonical)
+{
+	const uint32_t wi = B >> 5, bo = B & 31u;
+	uint32_t w[2 * WORDS + 1];
+#pragma unroll
+	for (int i = 0; i <= 2 * WORDS; ++i) w[i] = sw[wi + i];
+	uint64_t t[WORDS];          // t[0] most significant: bits [B, B + 64*WORDS)
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i)
+		t[i] = ((uint64_t)__funnelshift_l(w[2 * i + 1], w[2 * i], bo) << 32) | (uint64_t)__funnelshift_l(w[2 * i + 2], w[2 * i + 1], bo);
+	const uint32_t rs = 64u * WORDS - 2u * k;     // 0..63
+	Rec<WORDS> f;
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i) {
+		uint64_t v = t[i] >> rs;
+		if (i > 0 && rs) v |= t[i - 1] << (64u - rs);
+		f.w[WORDS - 1 - i] = v;
+	}
+	if (!canonical) return f;
+	uint64_t u[WORDS];
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i) u[i] = ~rev_symbols64(f.w[i]);
+	Rec<WORDS> r;
+#pragma unroll
+	for (int i = 0; i < WORDS; ++i) {
+		uint64_t v = u[i] >> rs;
+		if (i > 0 && rs) v |= u[i - 1] << (64u - rs);
+		r.w[WORDS - 1 - i] = v;
+	}
+	return rec_less<WORDS>(f, r) ? f : r;       // kmer < rev ? kmer : rev  (kb_sorter.h:340,356)
+}
+
 // 8 bits starting at bit `shift` of the record
 template <int WORDS>
 __device__ __forceinline__ uint32_t rec_top_digit(const Rec<WORDS>& r, uint32_t shift)
@@ -380,13 +414,13 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 	constexpr int MAXSK = 1024, STAGE = 12288;          // per-tile staging of the super-k-mer index and bytes (typical tile: ~350 super-k-mers, ~4.5 KB)
 	__shared__ uint16_t head[kExpandTile];
 	__shared__ uint32_t warp_max[kExpandThreads / 32];
-	__shared__ uint32_t s_kpre[MAXSK], s_off[MAXSK];
-	__shared__ __align__(16) uint8_t s_bytes[STAGE];
+	__shared__ uint32_t s_bit[MAXSK];                    // staged tiles: bit position of (k-mer of output slot 0) of every super-k-mer, minus 2 * slot
+	__shared__ __align__(16) uint8_t s_bytes[STAGE + 32];       // the tile's bytes as big-endian 32-bit words (+ slack: a funnel shift looks 2*WORDS words ahead)
 	__shared__ uint32_t s_jmax;
 	__shared__ unsigned long long s_fbase;
-	__shared__ uint32_t hist[256], htop[256];
+	__shared__ uint32_t htop[256];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid < 256) { hist[tid] = 0; htop[tid] = 0; }
+	if (tid < 256) htop[tid] = 0;
 	const uint32_t total_tiles = a.status[1];
 	Rec<WORDS>* __restrict__ out = reinterpret_cast<Rec<WORDS>*>(a.recs);
 
@@ -402,6 +436,9 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 		const uint32_t j_lo = a.tile_first[tile_first_base(pstart, p, kExpandTile) + t];
 		const uint32_t* __restrict__ kpre = a.sk_kpre + slot0;
 		const uint32_t* __restrict__ off = a.sk_off + slot0;
+		const uint32_t off_lo = off[j_lo];
+		const uintptr_t g0a = reinterpret_cast<uintptr_t>(a.bin + off_lo) & ~(uintptr_t)15;          // staging starts on the absolute 16-byte grid
+		const uint32_t base_off = (uint32_t)(reinterpret_cast<uintptr_t>(a.bin + off_lo) - g0a);
 
 		__syncthreads();      // previous tile is done with head[]
 #pragma unroll
@@ -415,7 +452,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				const uint32_t kp = kpre[j];
 				if (j > j_lo && kp >= tile_start + cnt) break;
 				const uint32_t rel = j - j_lo;
-				if (rel < (uint32_t)MAXSK) { s_kpre[rel] = kp; s_off[rel] = off[j]; }
+				if (rel < (uint32_t)MAXSK) s_bit[rel] = 8u * (base_off + (off[j] - off_lo) + 1u) + 2u * tile_start - 2u * kp;      // (mod 2^32; + 2 * slot is the k-mer's bit)
 				if (j > j_lo) head[kp - tile_start] = (uint16_t)rel;
 				jm = j;
 			}
@@ -424,12 +461,15 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 		__syncthreads();
 		// stage the tile's bytes of the bin (contiguous: from its first super-k-mer to the end of its last one) when they fit
 		const uint32_t j_hi = s_jmax;
-		const uint64_t b_lo = off[j_lo], b_hi = j_hi + 1 < nsk ? (uint64_t)off[j_hi + 1] : a.pack_start[p + 1];
-		const uintptr_t g0a = reinterpret_cast<uintptr_t>(a.bin + b_lo) & ~(uintptr_t)15;
+		const uint64_t b_hi = j_hi + 1 < nsk ? (uint64_t)off[j_hi + 1] : a.pack_start[p + 1];
 		const uint64_t span = reinterpret_cast<uintptr_t>(a.bin + b_hi) - g0a;
 		const bool staged = (j_hi - j_lo) < (uint32_t)MAXSK && span + 16 <= (uint64_t)STAGE;
 		if (staged)
-			for (uint32_t v = tid; v * 16 < span + 8; v += kExpandThreads) reinterpret_cast<uint4*>(s_bytes)[v] = __ldg(reinterpret_cast<const uint4*>(g0a) + v);
+			for (uint32_t v = tid; v * 16 < span + 8; v += kExpandThreads) {
+				uint4 x = __ldg(reinterpret_cast<const uint4*>(g0a) + v);
+				x.x = __byte_perm(x.x, 0, 0x0123); x.y = __byte_perm(x.y, 0, 0x0123); x.z = __byte_perm(x.z, 0, 0x0123); x.w = __byte_perm(x.w, 0, 0x0123);
+				reinterpret_cast<uint4*>(s_bytes)[v] = x;
+			}
 		// inclusive max-scan (blocked: 8 consecutive slots per thread)
 		uint32_t v[IPT];
 		uint32_t m = 0;
@@ -457,11 +497,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 		const uint64_t obase = a.pack_kbase[p] + tile_start;
 		auto kmer_of = [&](uint32_t slot) -> Rec<WORDS> {
 			const uint32_t rel = head[slot];
-			if (staged) {
-				const uint32_t s = tile_start + slot - s_kpre[rel];
-				return extract_kmer<WORDS>(a.bin + s_off[rel] + 1, s, a.k, a.both_strands != 0,
-					[&](uintptr_t wa) { return *reinterpret_cast<const unsigned long long*>(s_bytes + (wa - g0a)); });
-			}
+			if (staged) return extract_kmer_be32<WORDS>(reinterpret_cast<const uint32_t*>(s_bytes), s_bit[rel] + 2u * slot, a.k, a.both_strands != 0);
 			const uint32_t j = j_lo + rel;
 			const uint32_t s = tile_start + slot - kpre[j];
 			return extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0,
@@ -474,7 +510,6 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				if (slot < cnt) {
 					const Rec<WORDS> r = kmer_of(slot);
 					out[obase + slot] = r;
-					atomicAdd(&hist[(uint32_t)r.w[0] & 0xFFu], 1u);
 					atomicAdd(&htop[rec_top_digit<WORDS>(r, a.top_shift)], 1u);
 				}
 			}
@@ -514,11 +549,6 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				if (keep) out[s_fbase + warp_max[warp] + __popc(bal & lanemask_lt())] = r;
 			}
 		}
-	}
-	__syncthreads();
-	if (tid < 256) {
-		const uint32_t c = hist[tid];
-		if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.hist0) + tid, (unsigned long long)c);
 	}
 }
 

@@ -106,7 +106,8 @@ struct kmcb200_ctx {
 	int occ_leaf = 1;
 	uint64_t max_block_records = 1ull << 28;                // KMCB200_MAX_BLOCK_RECORDS: a bin with more k-mers is counted key block by key block
 	uint64_t max_chunk_bytes = 1ull << 30;                  // KMCB200_MAX_CHUNK_BYTES: ... and expanded chunk by chunk
-	int leaf_slot_bits = 9;                                 // KMCB200_LEAF_SLOT_BITS = 8 | 9 | 10: slots of a warp's leaf table
+	uint32_t leaf_round_pct = 100;                          // KMCB200_LEAF_ROUND_PCT: records per table round in percent of the slots
+	int leaf_slot_bits = 10;                                // KMCB200_LEAF_SLOT_BITS = 8 | 9 | 10: slots of a warp's leaf table
 	uint32_t epoch = 1;
 	uint64_t launches = 0;
 	// All kernels of a context run on ONE stream: the persistent radix passes size their grids to fill the GPU and two of
@@ -175,7 +176,7 @@ int setup_kernels(kmcb200_ctx* ctx)
 	const size_t cs = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	CU(cudaFuncSetAttribute(count_emit_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
 	CU(cudaFuncSetAttribute(msd_partition_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MsdSmem<WORDS>::kBytes));
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_part, msd_partition_kernel<WORDS>, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_part, msd_partition_kernel<WORDS>, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS>::kBytes));
 	const int local_smem = msd_local_cap<WORDS>() * 8 * WORDS + (MsdLocalCfg<WORDS>::kThreads / 32) * 1024;
 	CU(cudaFuncSetAttribute(msd_local_sort_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, local_smem));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_local, msd_local_sort_kernel<WORDS>, MsdLocalCfg<WORDS>::kThreads, local_smem));
@@ -243,6 +244,11 @@ int launch_lsd_passes(kmcb200_ctx* ctx, Slot& s, void* in, void* out, uint64_t n
 	constexpr int TILE = SortSmem<WORDS>::kTile;
 	const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
 	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix));
+	{          // the histogram of the first digit (hist[0] is zero: the ZeroBlock is cleared once per bin / sort)
+		const uint32_t hgrid = (uint32_t)std::min<uint64_t>((n + 511) / 512, (uint64_t)ctx->sm_count * 4);
+		digit_histogram_kernel<WORDS><<<hgrid, 512, 0, st>>>(in, n, 0, s.zero->hist[0], run_flag);
+		ctx->launches++;
+	}
 	for (uint32_t pass = 0; pass < key_bytes; ++pass) {
 		SortPass p;
 		p.in = in; p.out = out; p.n = n; p.n_tiles = n_tiles; p.byte = pass;
@@ -271,7 +277,7 @@ struct LeafPlan {
 };
 
 // Sorts n records from `a` (with `b` as the second buffer).  *result_in_b tells where the sorted records end up.
-// hist_ready: expand_kernel has zeroed the slot's ZeroBlock, counted hist[0] (LSD digit 0) and written the level-1 cells / items.
+// hist_ready: the expand stage has zeroed the slot's ZeroBlock and written the level-1 cells / items.
 template <int WORDS>
 int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, uint32_t key_bits, bool hist_ready, uint32_t n_packs, cudaStream_t st, bool* result_in_b, LeafPlan* plan = nullptr)
 {
@@ -286,12 +292,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
 	if (msd) if (int rc = ensure_msd<WORDS>(ctx, s, n, n_packs)) return rc;
 
-	if (!hist_ready) {
-		CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
-		const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 511) / 512, (uint64_t)ctx->sm_count * 4);
-		digit_histogram_kernel<WORDS><<<grid, 512, 0, st>>>(a, n, 0, s.zero->hist[0]);
-		ctx->launches++;
-	}
+	if (!hist_ready) CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
 	int iv = 0;      // timed interval index
 	CU(cudaEventRecord(s.ev_pass[0], st));
 	void* lsd_in = a; void* lsd_out = b;
@@ -336,9 +337,9 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		b1.tile = b2 > 0 ? MTILE : 0; b1.item_base = s.msd_item_base2; b1.item_seg = s.msd_item_seg2; b1.n_items = &s.zero->msd_n_items[1];
 		MsdPartArgs p1{};
 		p1.in = a; p1.out = b; p1.items = items1; p1.cell_scan = s.msd_cell_scan; p1.shift = top_shift; p1.nd = 256;
-		p1.tile_counter = &s.zero->msd_counters[0]; p1.flags = never;
+		p1.flags = never;
 		// (the item_seg table of the level-2 items shares its buffer with the all-zero level-1 table: partition first, bounds after)
-		msd_partition_kernel<WORDS><<<pgrid1, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p1);
+		msd_partition_kernel<WORDS><<<pgrid1, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS>::kBytes, st>>>(p1);
 		s.pass_names[iv] = "msd_partition_L1"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		msd_bounds_kernel<<<1, 1024, 0, st>>>(b1);
 		ctx->launches += 2;
@@ -356,8 +357,8 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			s.pass_names[iv] = "msd_count_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 			MsdPartArgs p2{};
 			p2.in = b; p2.out = a; p2.items = items2; p2.cell_scan = s.msd_cell_scan; p2.shift = top_shift - b2; p2.nd = nd2;
-			p2.tile_counter = &s.zero->msd_counters[1]; p2.flags = flags;
-			msd_partition_kernel<WORDS><<<pgrid2, MsdCfg<WORDS>::kThreads, MsdSmem<WORDS>::kBytes, st>>>(p2);
+			p2.flags = flags;
+			msd_partition_kernel<WORDS><<<pgrid2, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS>::kBytes, st>>>(p2);
 			ctx->launches++;
 			s.pass_names[iv] = "msd_partition_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		}
@@ -433,17 +434,15 @@ struct ExpandMode {            // oversized bins: count the top 12 bits / keep o
 	unsigned long long* out_counter = nullptr;
 };
 
-int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec,
-	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st, const ExpandMode& em = ExpandMode())
+// Host prefix sum of the expander-pack sizes -> pinned staging -> device, on `st`.  The host-buffer path enqueues this on the slot's
+// COPY stream, next to the bin itself: on the compute stream the 8 KB copy would queue up behind the next bin's 66 MB H2D transfer on
+// the same DMA engine and stall the kernels (measured: 0.45 ms per bin).
+int upload_packs(kmcb200_ctx* ctx, Slot& s, uint64_t size, const uint64_t* pack_bytes, uint32_t n_packs, cudaStream_t st)
 {
-	if (size >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin of %llu bytes: bins of 4 GiB or more are not supported", (unsigned long long)size);
-	const uint32_t k = ctx->prm.kmer_len;
-	const uint32_t min_rec = 1 + (k + 3) / 4;
 	const uint32_t np = (n_packs && pack_bytes) ? n_packs : 1;
-	// host prefix sum of the pack sizes -> device
 	if (np + 1 > s.packs_cap) {
 		const size_t cap = np + np / 4 + 64;
-		CU(cudaStreamSynchronize(st));
+		CU(cudaDeviceSynchronize());
 		for (int i = 0; i < kStageRing; ++i) {
 			if (s.h_pack_start[i]) CU(cudaFreeHost(s.h_pack_start[i]));
 			s.h_pack_start[i] = nullptr;
@@ -461,7 +460,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 		CU(cudaMalloc(reinterpret_cast<void**>(&s.pack_done), cap * 4));
 		s.packs_cap = cap;
 	}
-	// host prefix sum of the pack sizes into a pinned staging buffer (ring: the copy of an earlier bin may still be queued)
+	// (ring: the copy of an earlier bin may still be queued)
 	s.ring = (s.ring + 1) % kStageRing;
 	CU(cudaEventSynchronize(s.ev_pack[s.ring]));
 	uint64_t* hps = s.h_pack_start[s.ring];
@@ -475,6 +474,17 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	if (acc != size) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander packs cover %llu bytes but the bin has %llu", (unsigned long long)acc, (unsigned long long)size);
 	CU(cudaMemcpyAsync(s.d_pack_start, hps, (np + 1) * 8, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(s.ev_pack[s.ring], st));
+	return 0;
+}
+
+int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st, const ExpandMode& em = ExpandMode(), bool packs_uploaded = false)
+{
+	if (size >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin of %llu bytes: bins of 4 GiB or more are not supported", (unsigned long long)size);
+	const uint32_t k = ctx->prm.kmer_len;
+	const uint32_t min_rec = 1 + (k + 3) / 4;
+	const uint32_t np = (n_packs && pack_bytes) ? n_packs : 1;
+	if (!packs_uploaded) if (int rc = upload_packs(ctx, s, size, pack_bytes, n_packs, st)) return rc;
 
 	if (int rc = ensure(ctx, s.sk_off, s.sk_off_cap, size / min_rec + 2)) return rc;
 	if (int rc = ensure(ctx, s.sk_kpre, s.sk_kpre_cap, size / min_rec + 2)) return rc;
@@ -488,7 +498,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.tile = ctx->words == 1 ? ExpandCfg<1>::kTile : ExpandCfg<2>::kTile;
 	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
 	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.status = s.zero->status;
-	a.recs = d_recs; a.hist0 = s.zero->hist[0];
+	a.recs = d_recs;
 	a.mode = em.mode; a.fshift = em.fshift; a.fprefix = em.fprefix; a.fmask = em.fmask; a.hist12 = em.hist12; a.out_counter = em.out_counter;
 	if (em.mode == kExpandAll) {
 		if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np)) return rc;
@@ -575,6 +585,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	uint32_t* flags = s.zero->msd_flags;
 	LeafArgs la{};
 	la.recs = plan.recs; la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
+	la.round_pct = ctx->leaf_round_pct;
 	la.leaf_prefix = block_bits ? block_prefix * plan.n_leaves : 0u;          // n_leaves is a power of two
 	la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
 	la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
@@ -600,7 +611,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 
 // Expand -> Sort -> Compact on device buffers; records live in the slot workspace
 int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
-	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool packs_uploaded = false)
 {
 	const size_t rec_bytes = (size_t)ctx->words * 8;
 	s.ran_expand = s.ran_sort = s.ran_count = false;
@@ -614,7 +625,7 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	}
 	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, n_rec * rec_bytes)) return rc;
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n_rec * rec_bytes)) return rc;
-	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st)) return rc;
+	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st, ExpandMode(), packs_uploaded)) return rc;
 	CU(cudaEventRecord(s.ev_expand, st));
 	s.ran_expand = true;
 	bool in_b = false;
@@ -780,6 +791,7 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
 	if (const char* e = getenv("KMCB200_MAX_BLOCK_RECORDS")) { const long long v = atoll(e); if (v >= 1024) ctx->max_block_records = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_MAX_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= (1 << 17) && v < (1ll << 31)) ctx->max_chunk_bytes = (uint64_t)v; }
+	if (const char* e = getenv("KMCB200_LEAF_ROUND_PCT")) { const int v = atoi(e); if (v >= 50 && v <= 1000) ctx->leaf_round_pct = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_SLOT_BITS")) { const int b = atoi(e); if (b == 8 || b == 9 || b == 10) ctx->leaf_slot_bits = b; }
 	ctx->slots.resize(prm->n_slots);
 	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };
@@ -882,9 +894,11 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	if (int rc = ensure(ctx, s.d_bin, s.bin_cap, size + 64)) return rc;
 	if (int rc = ensure(ctx, s.d_out, s.out_cap, out_capacity + 64)) return rc;
 	if (size) CU(cudaMemcpyAsync(s.d_bin, superkmers, size, cudaMemcpyHostToDevice, st));
+	const bool with_packs = size != 0 && n_rec != 0;
+	if (with_packs) if (int rc = upload_packs(ctx, s, size, pack_bytes, n_packs, st)) return rc;      // on the copy stream, next to the bin
 	CU(cudaEventRecord(s.ev_h2d, st));
 	CU(cudaStreamWaitEvent(ctx->compute, s.ev_h2d, 0));
-	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute)) return rc;
+	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute, with_packs)) return rc;
 	CU(cudaEventRecord(s.ev_done, ctx->compute));
 	CU(cudaStreamWaitEvent(st, s.ev_done, 0));
 	CU(cudaMemcpyAsync(s.h_result, s.d_result, 64, cudaMemcpyDeviceToHost, st));

@@ -36,7 +36,10 @@
 namespace kmcb {
 
 constexpr int kLwWarps = 4;                      // warps per CTA (independent of each other)
-constexpr uint32_t kLwGroupBits = 6;              // slots per group = 64: a real k-mer and its error variants share a group, groups must absorb such clumps
+#ifndef KMCB200_LW_GROUP_BITS
+#define KMCB200_LW_GROUP_BITS 6
+#endif
+constexpr uint32_t kLwGroupBits = KMCB200_LW_GROUP_BITS;              // slots per group = 64: a real k-mer and its error variants share a group, groups must absorb such clumps
 constexpr int kLwList = 256;                     // u16 list of survivors, one step of the emission
 constexpr uint32_t kLwRing = 256;                // ring of compacted k-mers (WORDS == 1, multi-round leaves)
 constexpr uint32_t kLwMaxLeaf = 65534;           // records of a warp-counted leaf (count field >= 16 bits)
@@ -48,6 +51,7 @@ struct LeafArgs {
 	const uint64_t* start;       // [n_leaves + 1]
 	uint32_t n_leaves;
 	uint32_t low_bits;           // bits below the partition digits
+	uint32_t round_pct;          // records a round of the table is sized for, in percent of its slots (duplicate-rich bins: ~0.3 distinct k-mers per record)
 	uint32_t leaf_prefix;        // key block of an oversized bin: (block prefix << log2(n_leaves)), so that (leaf_prefix | leaf) = k-mer >> low_bits; else 0
 	uint32_t k, lut_prefix_len, cutoff_min, cutoff_max, counter_max, counter_bytes, suffix_bytes;
 	uint8_t* tmp;                // leaf L writes its records, padded to a multiple of 8 bytes, at tmp + start[L] * pad
@@ -151,9 +155,13 @@ struct LwRound {
 	LwCut cut;
 };
 
+#ifndef KMCB200_LW_INSERT_ATTR
+#define KMCB200_LW_INSERT_ATTR __forceinline__
+#endif
 template <int V>
-__device__ __forceinline__ void lw_insert1(const LwRound& t, const uint64_t (&kk)[V], uint32_t vmask, uint32_t& r_claim, uint32_t& r_max, bool& ok)
+__device__ KMCB200_LW_INSERT_ATTR void lw_insert1(const LwRound& t, const uint64_t (&kk)[V], uint32_t vmask, uint32_t& r_claim, uint32_t& r_max, bool& ok)
 {
+	constexpr uint32_t GM = (1u << kLwGroupBits) - 1u;
 	uint32_t slot[V];
 	unsigned long long old[V], ent[V];
 #pragma unroll
@@ -161,25 +169,29 @@ __device__ __forceinline__ void lw_insert1(const LwRound& t, const uint64_t (&kk
 		const uint64_t rem = kk[v] & t.rem_mask;
 		slot[v] = ((((uint32_t)(kk[v] >> t.gshift)) & t.gmask) << kLwGroupBits) | (uint32_t)((rem * 0x9E3779B97F4A7C15ull) >> (64 - kLwGroupBits));
 		ent[v] = (rem << t.cb) | 1ull;
-		old[v] = 0;
+		old[v] = kLwEmpty;
 		if ((vmask >> v) & 1u) old[v] = atomicCAS(reinterpret_cast<unsigned long long*>(&t.main[slot[v]]), (unsigned long long)kLwEmpty, ent[v]);
 	}
+	// The probe loop only LOOKS for the k-mer's slot: lanes diverge here (the warp iterates as often as its unluckiest lane), so it is
+	// kept to a handful of instructions; what happens to the slot comes after it, converged.
 #pragma unroll
 	for (int v = 0; v < V; ++v) {
-		if (!((vmask >> v) & 1u)) continue;
+		const bool act = (vmask >> v) & 1u;
+		const unsigned long long tag = ent[v] >> t.cb;
 		uint32_t s = slot[v];
 		unsigned long long o = old[v];
-		int probe = 0;
-		while (true) {
-			if (o == kLwEmpty) { ++r_claim; lw_transition(t.cut, 1u, t.surv, t.over, s, r_max); break; }
-			if ((o >> t.cb) == (ent[v] >> t.cb)) {
-				const uint32_t oc = atomicAdd(reinterpret_cast<uint32_t*>(&t.main[s]), 1u) & t.cmask;      // low word = count
-				lw_transition(t.cut, oc + 1u, t.surv, t.over, s, r_max);
-				break;
-			}
-			if (++probe == (1 << kLwGroupBits)) { ok = false; break; }      // the group is full
-			s = (s & ~((1u << kLwGroupBits) - 1u)) | ((s + 1u) & ((1u << kLwGroupBits) - 1u));
+		uint32_t probe = 0;
+		while (o != kLwEmpty && (o >> t.cb) != tag) {
+			if (++probe > GM) break;                                  // the group is full
+			s = (s & ~GM) | ((s + 1u) & GM);
 			o = atomicCAS(reinterpret_cast<unsigned long long*>(&t.main[s]), (unsigned long long)kLwEmpty, ent[v]);
+		}
+		if (probe > GM) ok = false;
+		else if (act) {
+			uint32_t newc = 1u;
+			if (o == kLwEmpty) ++r_claim;
+			else newc = (atomicAdd(reinterpret_cast<uint32_t*>(&t.main[s]), 1u) & t.cmask) + 1u;      // low word = count
+			lw_transition(t.cut, newc, t.surv, t.over, s, r_max);
 		}
 	}
 }
@@ -193,13 +205,13 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 	constexpr int NW = SLOTS / 32;                       // groups = bitmap words (<= 32)
 	constexpr int NG = SLOTS >> kLwGroupBits;           // groups
 	constexpr uint32_t GB = SLOT_BITS - kLwGroupBits;    // group bits
-	constexpr uint32_t ROUND = SLOTS + SLOTS / 2;        // records a round is sized for (30x coverage: ~0.3 distinct k-mers per record)
 	constexpr uint32_t FULL = 0xffffffffu;
 	static_assert(NW <= 32 && NW >= 4, "one bitmap word per lane");
 	extern __shared__ __align__(16) uint8_t lw_dsm[];
 	SM& S = reinterpret_cast<SM*>(lw_dsm)[threadIdx.x >> 5];
 	if (*a.flags & kMsdFlagFallback) return;
 	const uint32_t lane = threadIdx.x & 31u, lt = lanemask_lt();
+	const uint32_t ROUND = (uint32_t)SLOTS * a.round_pct / 100u;          // a round that overflows a group is split on the next bit: optimism costs one wasted round
 	const R* __restrict__ recs = reinterpret_cast<const R*>(a.recs);
 	const uint32_t ob = a.suffix_bytes + a.counter_bytes;
 	const uint32_t padw = (ob + 7) >> 3;                                   // temporary records: padw 64-bit words
@@ -325,22 +337,23 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 							}
 						}
 #pragma unroll
-						for (int u = 0; u < U; ++u) {
-							if (!((live >> u) & 1u)) continue;
+						for (int u = 0; u < U; ++u) {          // (the probe loop only looks for the slot, as in lw_insert1)
+							const bool act = (live >> u) & 1u;
 							const uint32_t j = j0 + u * 32 + lane;
 							uint32_t s = slot[u];
-							unsigned long long o = old[u];
-							int probe = 0;
-							while (true) {
-								if (o == kLwEmpty) { ++r_claim; lw_transition(cut, 1u, S.surv, S.over, s, r_max); break; }
-								if (rec_equal<WORDS>(lw_load<WORDS>(recs + lo + (uint32_t)(o >> 32)), key[u])) {
-									const uint32_t oc = atomicAdd(reinterpret_cast<uint32_t*>(&S.main[s]), 1u);       // low word = count
-									lw_transition(cut, oc + 1u, S.surv, S.over, s, r_max);
-									break;
-								}
-								if (++probe == (1 << kLwGroupBits)) { ok = false; break; }
+							unsigned long long o = act ? old[u] : kLwEmpty;
+							uint32_t probe = 0;
+							while (o != kLwEmpty && !rec_equal<WORDS>(lw_load<WORDS>(recs + lo + (uint32_t)(o >> 32)), key[u])) {
+								if (++probe > ((1u << kLwGroupBits) - 1u)) break;
 								s = (s & ~((1u << kLwGroupBits) - 1u)) | ((s + 1u) & ((1u << kLwGroupBits) - 1u));
 								o = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[s]), (unsigned long long)kLwEmpty, ((unsigned long long)j << 32) | 1ull);
+							}
+							if (probe > ((1u << kLwGroupBits) - 1u)) ok = false;
+							else if (act) {
+								uint32_t newc = 1u;
+								if (o == kLwEmpty) ++r_claim;
+								else newc = atomicAdd(reinterpret_cast<uint32_t*>(&S.main[s]), 1u) + 1u;       // low word = count
+								lw_transition(cut, newc, S.surv, S.over, s, r_max);
 							}
 						}
 						if (!__all_sync(FULL, ok)) break;

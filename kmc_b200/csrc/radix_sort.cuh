@@ -249,11 +249,12 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 	}
 }
 
-// histogram of one digit over N records (used when records arrive already expanded: seam #1)
+// histogram of the first digit over N records, in front of the LSD passes (run_flag as in SortPass)
 template <int WORDS>
-__global__ void __launch_bounds__(512) digit_histogram_kernel(const void* in, uint64_t n, uint32_t byte, uint64_t* hist)
+__global__ void __launch_bounds__(512) digit_histogram_kernel(const void* in, uint64_t n, uint32_t byte, uint64_t* hist, const uint32_t* run_flag)
 {
 	__shared__ uint32_t sh[256];
+	if (run_flag && !(*run_flag & 1u)) return;
 	const Rec<WORDS>* __restrict__ g = reinterpret_cast<const Rec<WORDS>*>(in);
 	if (threadIdx.x < 256) sh[threadIdx.x] = 0;
 	__syncthreads();
