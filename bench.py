@@ -6,7 +6,7 @@ through the whole hot path Expand -> Sort -> Compact (kmc_core/kb_sorter.h:210-2
 bin per GPU per step, bins are independent, no collective on the data path).
 
   value     : k-mers/s with the bin's super-k-mer bytes already resident in HBM, device-timed (CUDA events, max over ranks)
-  e2e       : the same through the host-buffer C ABI (kmcb200_submit_bin / kmcb200_wait_bin, two slots), pinned host
+  e2e       : the same through the host-buffer C ABI (kmcb200_submit_bin / kmcb200_wait_bin, three slots), pinned host
               buffers, H2D of the bin and D2H of the database records + LUT + counters inside the timed region
   roofline  : the radix pass (dominant kernel): 2*N*W algorithmic bytes / CUDA-event duration of the pass launches
   cpu_baseline / --impl reference : the UNMODIFIED reference classes (oracle/_ref, CKmerBinSorter<1> + RADULS) on the host cores
@@ -33,6 +33,7 @@ METRIC = "stage-2 k-mers/s (k=31)"
 UNIT = "k-mers/s"
 REC_BYTES = 8
 KEY_BYTES = 8
+E2E_SLOTS = int(os.environ.get("KMCB200_E2E_SLOTS", "3"))          # bins in flight through submit_bin / wait_bin: the D2H of bin i-3 and the H2D of bin i overlap the kernels of bins i-2, i-1
 
 
 def hbm_peak():
@@ -202,7 +203,7 @@ def main_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     n_rec = args.n_rec
 
-    ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(K, True, CUTOFF_MIN, CUTOFF_MAX, COUNTER_MAX, LUT_P), device=local_rank, n_slots=2)
+    ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(K, True, CUTOFF_MIN, CUTOFF_MAX, COUNTER_MAX, LUT_P), device=local_rank, n_slots=E2E_SLOTS)
     # two different bins per rank, alternating between steps
     host_bins = [kmc_b200.synth_bin(1000 + 17 * rank + j, K, n_rec) for j in range(2)]
     cap = ctx.out_capacity(n_rec) + 64
@@ -257,26 +258,26 @@ def main_ours(args, rank, world, local_rank):
 
     # ---- e2e: host buffers through submit/wait, two slots, pinned memory
     pin_bins = [torch.from_numpy(hb.data.copy()).pin_memory() for hb in host_bins]
-    pin_out = [torch.zeros(cap, dtype=torch.uint8).pin_memory() for _ in range(2)]
-    pin_lut = [torch.zeros(ctx.lut_entries, dtype=torch.int64).pin_memory() for _ in range(2)]
+    pin_out = [torch.zeros(cap, dtype=torch.uint8).pin_memory() for _ in range(E2E_SLOTS)]
+    pin_lut = [torch.zeros(ctx.lut_entries, dtype=torch.int64).pin_memory() for _ in range(E2E_SLOTS)]
 
     def e2e_run(n_steps, first):
         moved_in = moved_out = 0
         for i in range(n_steps):
-            s = (first + i) % 2
-            if i >= 2:
+            s = (first + i) % E2E_SLOTS
+            if i >= E2E_SLOTS:
                 nb, stats = ctx.wait_bin(s)
                 moved_out += nb
-            hb = host_bins[s]
-            ctx.submit_bin(s, pin_bins[s].data_ptr(), hb.size, n_rec, hb.pack_bytes, pin_out[s].data_ptr(), cap, pin_lut[s].data_ptr())
+            hb = host_bins[i % 2]
+            ctx.submit_bin(s, pin_bins[i % 2].data_ptr(), hb.size, n_rec, hb.pack_bytes, pin_out[s].data_ptr(), cap, pin_lut[s].data_ptr())
             moved_in += hb.size + 8 * (hb.pack_bytes.size + 1)
-        for i in range(max(n_steps - 2, 0), n_steps):
-            nb, stats = ctx.wait_bin((first + i) % 2)
+        for i in range(max(n_steps - E2E_SLOTS, 0), n_steps):
+            nb, stats = ctx.wait_bin((first + i) % E2E_SLOTS)
             moved_out += nb
             assert stats[3] == n_rec
         return moved_in, moved_out + n_steps * (8 * ctx.lut_entries + 64)
 
-    e2e_run(max(args.warmup, 2), 0)
+    e2e_run(max(args.warmup, E2E_SLOTS), 0)
     barrier()
     t0 = time.perf_counter()
     h2d, d2h = e2e_run(args.steps, 0)
@@ -320,7 +321,7 @@ def main_ours(args, rank, world, local_rank):
                          "pass_ms": pass_ms, "sort_intervals_ms": {k: v for k, v in intervals.items()},
                          "stage_ms": {"expand": st["expand_ms"], "sort": st["sort_ms"], "count": st["count_ms"]}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "ms_per_step": 1e3 * t_e2e / args.steps, "api": "kmcb200_submit_bin/kmcb200_wait_bin, 2 slots, pinned host buffers"},
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "api": "kmcb200_submit_bin/kmcb200_wait_bin, %d slots, pinned host buffers" % E2E_SLOTS},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -77,7 +77,7 @@ struct Slot {
 	// outputs of the host-buffer path
 	uint8_t* d_out = nullptr; size_t out_cap = 0;
 	uint64_t* d_lut = nullptr;
-	uint64_t* d_result = nullptr; uint64_t* h_result = nullptr;
+	uint64_t* d_result = nullptr; uint64_t* h_result = nullptr; uint64_t* h_result_dev = nullptr;
 	// events
 	cudaEvent_t ev_begin = nullptr, ev_expand = nullptr, ev_sort = nullptr, ev_count = nullptr, ev_result = nullptr;
 	cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;           // copy stream <-> compute stream hand-over
@@ -137,6 +137,23 @@ int fail(kmcb200_ctx* c, int code, const char* fmt, ...)
 		cudaError_t e_ = (call);                                                                             \
 		if (e_ != cudaSuccess) return fail(ctx, KMCB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while (0)
+
+// Zeroing on the compute stream is done by a kernel, not by cudaMemsetAsync: a memset may be carried out by a copy engine, and
+// the copy engines are busy with the next bin's 66 MB host-to-device transfer - the kernels behind the memset would wait for it.
+__global__ void zero_words_kernel(uint32_t* p, size_t n_words)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+int zero_async(kmcb200_ctx* ctx, void* ptr, size_t bytes, cudaStream_t st)
+{
+	if (bytes == 0) return 0;
+	if ((reinterpret_cast<uintptr_t>(ptr) & 3u) || (bytes & 3u) || bytes > (size_t(1) << 28)) { CU(cudaMemsetAsync(ptr, 0, bytes, st)); return 0; }
+	const size_t n = bytes / 4;
+	zero_words_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, st>>>(reinterpret_cast<uint32_t*>(ptr), n);
+	ctx->launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
 
 uint32_t byte_log(uint64_t x) { return x < (1u << 8) ? 1 : x < (1u << 16) ? 2 : x < (1u << 24) ? 3 : 4; }   // defs.h:121
 
@@ -292,7 +309,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
 	if (msd) if (int rc = ensure_msd<WORDS>(ctx, s, n, n_packs)) return rc;
 
-	if (!hist_ready) CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
+	if (!hist_ready) if (int rc = zero_async(ctx, s.zero, sizeof(ZeroBlock), st)) return rc;
 	int iv = 0;      // timed interval index
 	CU(cudaEventRecord(s.ev_pass[0], st));
 	void* lsd_in = a; void* lsd_out = b;
@@ -324,7 +341,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			msd_setup_kernel<<<1, 1, 0, st>>>(s.msd_seg1, s.msd_item_base1, &s.zero->msd_n_items[0], n, MTILE);
 			items1.seg_start = s.msd_seg1; items1.item_base = s.msd_item_base1; items1.item_seg = s.msd_item_seg2 /* all zero: see below */;
 			items1.n_items = &s.zero->msd_n_items[0];
-			CU(cudaMemsetAsync(s.msd_item_seg2, 0, max_items1 * sizeof(uint32_t), st));      // single segment: every item belongs to segment 0
+			if (int rc = zero_async(ctx, s.msd_item_seg2, max_items1 * sizeof(uint32_t), st)) return rc;      // single segment: every item belongs to segment 0
 			MsdCountArgs c1{a, items1, top_shift, 256, s.msd_cells, never};
 			msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items1, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c1);
 			ctx->launches += 2;
@@ -507,7 +524,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.top_shift = std::max(2u * k, 8u) - 8u;
 	s.last_n_packs = np;
 
-	CU(cudaMemsetAsync(s.zero, 0, sizeof(ZeroBlock), st));
+	if (int rc = zero_async(ctx, s.zero, sizeof(ZeroBlock), st)) return rc;
 	walk_packs_parallel_kernel<<<np, kWalkSegs, kWalkChunk + 32, st>>>(a, s.pack_done);
 	walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a, s.pack_done);
 	ctx->launches++;
@@ -520,11 +537,19 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
 	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
 {
-	CU(cudaMemsetAsync(d_lut, 0, ctx->lut_entries * 8, st));
-	CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
-	CU(cudaMemsetAsync(&s.zero->counters[kMaxPasses], 0, sizeof(uint32_t), st));
+	if (int rc = zero_async(ctx, d_lut, ctx->lut_entries * 8, st)) return rc;
+	if (int rc = zero_async(ctx, d_result, 8 * sizeof(uint64_t), st)) return rc;
+	if (int rc = zero_async(ctx, &s.zero->counters[kMaxPasses], sizeof(uint32_t), st)) return rc;
 	if (n == 0) return 0;
 	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, nullptr, st);
+}
+
+// the 8 result words -> pinned host memory, written by the GPU itself (zero-copy): the host-buffer path then needs no copy-engine
+// operation that WAITS for the kernels - such a pending wait can hold up the copies of other bins queued behind it on the engine
+__global__ void mirror_result_kernel(const uint64_t* result, volatile uint64_t* host_result)
+{
+	if (threadIdx.x < 8) host_result[threadIdx.x] = result[threadIdx.x];
+	__threadfence_system();
 }
 
 __global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uint32_t* status, const uint32_t* msd_flags = nullptr)
@@ -580,8 +605,8 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
 	const size_t pad = (size_t)((ob + 7) / 8) * 8;
 	if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * pad + 64)) return rc;
-	CU(cudaMemsetAsync(d_lut, 0, ctx->lut_entries * 8, st));
-	CU(cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st));
+	if (int rc = zero_async(ctx, d_lut, ctx->lut_entries * 8, st)) return rc;
+	if (int rc = zero_async(ctx, d_result, 8 * sizeof(uint64_t), st)) return rc;
 	uint32_t* flags = s.zero->msd_flags;
 	LeafArgs la{};
 	la.recs = plan.recs; la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
@@ -605,7 +630,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true;
 	const void* sorted = (ctx->key_bytes % 2 == 0) ? s.recs_b : s.recs_a;
-	CU(cudaMemsetAsync(&s.zero->counters[kMaxPasses], 0, sizeof(uint32_t), st));
+	if (int rc = zero_async(ctx, &s.zero->counters[kMaxPasses], sizeof(uint32_t), st)) return rc;
 	return launch_count<WORDS>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, st);
 }
 
@@ -677,7 +702,7 @@ int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t 
 	for (const Chunk& c : chunks) CU(cudaMemcpyAsync(s.d_bin + c.dev_off, h_bin + c.byte0, c.bytes, cudaMemcpyHostToDevice, st));
 	if (!s.d_hist12) { CU(cudaMalloc(reinterpret_cast<void**>(&s.d_hist12), 4096 * 8)); CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), 8)); }
 	// ---- pass 0: where do the k-mers fall (top 12 bits)?  Also checks the packs and n_rec.
-	CU(cudaMemsetAsync(s.d_hist12, 0, 4096 * 8, st));
+	if (int rc = zero_async(ctx, s.d_hist12, 4096 * 8, st)) return rc;
 	ExpandMode em;
 	em.mode = kExpandCount12; em.fshift = 2 * k - 12; em.hist12 = s.d_hist12;
 	for (const Chunk& c : chunks) {
@@ -718,7 +743,7 @@ int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t 
 	for (const Block& b : blocks) {
 		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, b.n * rec_bytes)) return rc;
 		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, b.n * rec_bytes)) return rc;
-		CU(cudaMemsetAsync(s.d_out_counter, 0, 8, st));
+		if (int rc = zero_async(ctx, s.d_out_counter, 8, st)) return rc;
 		ExpandMode ef;
 		ef.mode = kExpandFilter; ef.fshift = 2 * k - b.bits; ef.fprefix = b.prefix; ef.out_counter = s.d_out_counter;
 		if (b.bits == 0) { ef.fshift = 0; ef.fprefix = 0; ef.fmask = 0; }          // one block = the whole bin (oversized only by its bytes): keep everything
@@ -816,7 +841,8 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_item_base1), 2 * 4) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_item_base2), 257 * 4) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_result), 64) == cudaSuccess;
-		ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_result), 64, cudaHostAllocDefault) == cudaSuccess;
+		ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.h_result), 64, cudaHostAllocMapped) == cudaSuccess;
+		ok = ok && cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.h_result_dev), s.h_result, 0) == cudaSuccess;
 		for (cudaEvent_t* e : {&s.ev_begin, &s.ev_expand, &s.ev_sort, &s.ev_count, &s.ev_result}) ok = ok && cudaEventCreate(e) == cudaSuccess;
 		for (auto& e : s.ev_pass) ok = ok && cudaEventCreate(&e) == cudaSuccess;
 		for (auto& e : s.ev_pack) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
@@ -899,11 +925,10 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	CU(cudaEventRecord(s.ev_h2d, st));
 	CU(cudaStreamWaitEvent(ctx->compute, s.ev_h2d, 0));
 	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute, with_packs)) return rc;
-	CU(cudaEventRecord(s.ev_done, ctx->compute));
-	CU(cudaStreamWaitEvent(st, s.ev_done, 0));
-	CU(cudaMemcpyAsync(s.h_result, s.d_result, 64, cudaMemcpyDeviceToHost, st));
-	CU(cudaEventRecord(s.ev_result, st));
-	CU(cudaMemcpyAsync(lut, s.d_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, st));
+	mirror_result_kernel<<<1, 32, 0, ctx->compute>>>(s.d_result, s.h_result_dev);
+	ctx->launches++;
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(s.ev_result, ctx->compute));
 	s.busy = true;
 	s.host_out = out_suffix; s.host_out_cap = out_capacity; s.host_lut = lut; s.pending_n_rec = n_rec;
 	return 0;
@@ -934,6 +959,7 @@ int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint6
 		cudaStreamSynchronize(s.stream);
 		return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small for %llu bytes", (unsigned long long)s.host_out_cap, (unsigned long long)bytes);
 	}
+	CU(cudaMemcpyAsync(s.host_lut, s.d_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, s.stream));
 	if (bytes) CU(cudaMemcpyAsync(s.host_out, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
 	CU(cudaStreamSynchronize(s.stream));
 	if (out_bytes) *out_bytes = bytes;
@@ -992,7 +1018,7 @@ int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkm
 	CU(cudaEventRecord(s.ev_begin, st));
 	if (int rc = stage_expand(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_recs, st)) return rc;
 	if (d_result) {
-		CU(cudaMemsetAsync(d_result, 0, 64, st));
+		if (int rc = zero_async(ctx, d_result, 64, st)) return rc;
 		finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status);
 		ctx->launches++;
 	}
