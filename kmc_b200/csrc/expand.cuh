@@ -21,10 +21,19 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef KMCB200_EXPAND_UNROLL
+#define KMCB200_EXPAND_UNROLL 8
+#endif
+
 namespace kmcb {
 
+constexpr int kExpandUnroll = KMCB200_EXPAND_UNROLL;
+
 // output tile of expand_kernel = work item of the level-1 MSD partition: 4096 one-word records, 2048 wider ones
-template <int WORDS> struct ExpandCfg { static constexpr int kThreads = WORDS == 1 ? 512 : 256, kTile = 8 * kThreads; };
+#ifndef KMCB200_EXPAND_IPT
+#define KMCB200_EXPAND_IPT 8
+#endif
+template <int WORDS> struct ExpandCfg { static constexpr int kTile = WORDS == 1 ? 4096 : 2048, kThreads = WORDS == 1 ? 4096 / KMCB200_EXPAND_IPT : 256; };
 constexpr int kExpandMinTile = 2048;
 
 struct ExpandArgs {
@@ -410,7 +419,7 @@ template <int WORDS>
 __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(const ExpandArgs a)
 {
 	constexpr int kExpandTile = ExpandCfg<WORDS>::kTile, kExpandThreads = ExpandCfg<WORDS>::kThreads;
-	constexpr int IPT = kExpandTile / kExpandThreads;    // 8
+	constexpr int IPT = kExpandTile / kExpandThreads;    // 8 k-mers per thread
 	constexpr int MAXSK = 1024, STAGE = 12288;          // per-tile staging of the super-k-mer index and bytes (typical tile: ~350 super-k-mers, ~4.5 KB)
 	__shared__ uint16_t head[kExpandTile];
 	__shared__ uint32_t warp_max[kExpandThreads / 32];
@@ -504,7 +513,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				[](uintptr_t wa) { return __ldg(reinterpret_cast<const unsigned long long*>(wa)); });
 		};
 		if (a.mode == kExpandAll) {
-#pragma unroll 2
+#pragma unroll kExpandUnroll
 			for (int i = 0; i < IPT; ++i) {
 				const uint32_t slot = i * kExpandThreads + tid;
 				if (slot < cnt) {

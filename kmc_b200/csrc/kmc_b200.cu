@@ -37,6 +37,7 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint32_t msd_flags[4];                        // [0] kMsdFlagFallback (leaves too large -> LSD passes), [1] always 0
 	uint32_t msd_n_items[2];                      // work items of the level-1 / level-2 segmentation
 	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves, leaf-count
+	uint32_t leaf_group_sum[64];                  // emitted records per group of 1024 leaves
 };
 
 struct Slot {
@@ -614,9 +615,9 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	la.leaf_prefix = block_bits ? block_prefix * plan.n_leaves : 0u;          // n_leaves is a power of two
 	la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
 	la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
-	la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
+	la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.group_sum = s.zero->leaf_group_sum; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
 	if (int rc = DISPATCH_SLOTS(ctx, launch_leaves, WORDS, ctx, la, st)) return rc;
-	leaf_scan_kernel<<<1, 1024, 0, st>>>(s.leaf_emit, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags);
+	leaf_scan_kernel<<<(plan.n_leaves + 1023) / 1024, 1024, 0, st>>>(s.leaf_emit, s.zero->leaf_group_sum, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags);
 	leaf_gather_kernel<<<(plan.n_leaves + 7) / 8, 256, 0, st>>>(s.leaf_tmp, plan.start, s.leaf_emit, s.leaf_off, plan.n_leaves, ob, d_out, d_result, flags);
 	ctx->launches += 2;
 	int iv = s.n_passes_run;

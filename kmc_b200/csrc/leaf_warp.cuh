@@ -41,7 +41,13 @@ constexpr int kLwWarps = 4;                      // warps per CTA (independent o
 #endif
 constexpr uint32_t kLwGroupBits = KMCB200_LW_GROUP_BITS;              // slots per group = 64: a real k-mer and its error variants share a group, groups must absorb such clumps
 constexpr int kLwList = 256;                     // u16 list of survivors, one step of the emission
-constexpr uint32_t kLwRing = 256;                // ring of compacted k-mers (WORDS == 1, multi-round leaves)
+#ifndef KMCB200_LW_RING
+#define KMCB200_LW_RING 256
+#endif
+#ifndef KMCB200_LW_MINBLOCKS
+#define KMCB200_LW_MINBLOCKS 7
+#endif
+constexpr uint32_t kLwRing = KMCB200_LW_RING;                // ring of compacted k-mers (WORDS == 1, multi-round leaves)
 constexpr uint32_t kLwMaxLeaf = 65534;           // records of a warp-counted leaf (count field >= 16 bits)
 constexpr uint32_t kLwMaxSplit = 12;             // extra split bits a round may descend
 constexpr uint64_t kLwEmpty = ~0ull;
@@ -56,6 +62,7 @@ struct LeafArgs {
 	uint32_t k, lut_prefix_len, cutoff_min, cutoff_max, counter_max, counter_bytes, suffix_bytes;
 	uint8_t* tmp;                // leaf L writes its records, padded to a multiple of 8 bytes, at tmp + start[L] * pad
 	uint32_t* leaf_emit;         // [n_leaves] emitted records
+	uint32_t* group_sum;         // [n_leaves / 1024] their sums (zero-initialised)
 	uint64_t* lut;
 	uint64_t* result;            // [0] n_unique [1] n_cutoff_min [2] n_cutoff_max
 	uint32_t* ticket;
@@ -197,7 +204,7 @@ __device__ KMCB200_LW_INSERT_ATTR void lw_insert1(const LwRound& t, const uint64
 }
 
 template <int WORDS, int SLOT_BITS>
-__global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafArgs a)
+__global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp_kernel(const LeafArgs a)
 {
 	using R = Rec<WORDS>;
 	using SM = LwSmem<SLOT_BITS>;
@@ -445,6 +452,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 		}
 		if (lane == 0) {
 			a.leaf_emit[leaf] = failed ? 0u : emit_base;
+			if (emit_base && !failed) atomicAdd(&a.group_sum[leaf >> 10], emit_base);          // for leaf_scan_kernel
 			t_emit += emit_base;
 			if (one_prefix && emit_base && !failed)
 				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + ((a.leaf_prefix | leaf) >> (prefix_shift - a.low_bits)), (unsigned long long)emit_base);      // leaf = k-mer >> low_bits
@@ -467,38 +475,38 @@ __global__ void __launch_bounds__(32 * kLwWarps, 7) leaf_warp_kernel(const LeafA
 	}
 }
 
-// exclusive scan of the per-leaf record counts (single CTA; a warp owns 2048 consecutive leaves and scans them 32 at a time), total -> result[4]
-__global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_emit, uint32_t n_leaves, uint64_t* leaf_off, uint64_t* result, uint64_t out_capacity, uint32_t ob, const uint32_t* flags)
+// exclusive scan of the per-leaf record counts: one CTA per group of 1024 leaves; the groups' sums were accumulated by the leaf kernel
+// (one atomicAdd per leaf), so a CTA's base is a sum over <= 64 numbers.  total -> result[4], capacity check -> result[5]
+__global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_emit, const uint32_t* group_sum, uint32_t n_leaves, uint64_t* leaf_off,
+	uint64_t* result, uint64_t out_capacity, uint32_t ob, const uint32_t* flags)
 {
-	__shared__ uint64_t s_w[32];
+	__shared__ uint32_t s_w[32];
+	__shared__ unsigned long long s_base;
 	if (*flags & kMsdFlagFallback) return;
-	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t per = ((n_leaves + 1023) / 1024) * 32;          // leaves per warp (multiple of 32)
-	const uint32_t w0 = warp * per;
-	uint64_t sum = 0;
-	for (uint32_t i = lane; i < per; i += 32) sum += (w0 + i < n_leaves) ? leaf_emit[w0 + i] : 0u;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = blockIdx.x, n_groups = gridDim.x;
+	if (warp == 0) {
+		unsigned long long b = 0, t = 0;
+		for (uint32_t j = lane; j < n_groups; j += 32) { const uint32_t v = group_sum[j]; t += v; if (j < g) b += v; }
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-	if (lane == 0) s_w[warp] = sum;
-	__syncthreads();
-	uint64_t base = 0, tot = 0;
-	for (uint32_t w = 0; w < 32; ++w) { if (w < warp) base += s_w[w]; tot += s_w[w]; }
-	for (uint32_t i0 = 0; i0 < per; i0 += 32) {
-		const uint32_t i = w0 + i0 + lane;
-		const uint32_t v = i < n_leaves ? leaf_emit[i] : 0u;
-		uint32_t inc = v;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= (uint32_t)o) inc += t;
+		for (int o = 16; o > 0; o >>= 1) { b += __shfl_xor_sync(0xffffffffu, b, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+		if (lane == 0) {
+			s_base = b;
+			if (g == 0) { result[4] = t; if (t * ob > out_capacity) result[5] = 1; }
 		}
-		if (i < n_leaves) leaf_off[i] = base + inc - v;
-		base += __shfl_sync(0xffffffffu, inc, 31);
 	}
-	if (tid == 0) {
-		result[4] = tot;
-		if (tot * ob > out_capacity) result[5] = 1;
+	const uint32_t i = g * 1024 + tid;
+	const uint32_t v = i < n_leaves ? leaf_emit[i] : 0u;
+	uint32_t inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= (uint32_t)o) inc += t;
 	}
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads();
+	unsigned long long base = s_base;
+	for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
+	if (i < n_leaves) leaf_off[i] = base + inc - v;
 }
 
 // one warp per leaf: its padded temporary records -> packed records at their final place

@@ -327,6 +327,20 @@ __global__ void __launch_bounds__(512) msd_count_kernel(const MsdCountArgs p)
 // flat exclusive scan over u16 cells -> u32 (three small kernels; the number of cells lives on the device)
 constexpr int kCellChunk = 4096;     // cells per block
 
+// 16 consecutive cells of a thread as two 16-byte loads (a vector that starts inside the array may end <= 15 cells behind it: the cell
+// array is over-allocated by an eighth, and those values are masked)
+__device__ __forceinline__ void cell_load16(const uint16_t* cells, uint64_t c, uint64_t n_cells, uint32_t (&v)[16])
+{
+	uint4 a = make_uint4(0, 0, 0, 0), b = a;
+	if (c < n_cells) { a = __ldg(reinterpret_cast<const uint4*>(cells + c)); b = __ldg(reinterpret_cast<const uint4*>(cells + c) + 1); }
+	const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		v[2 * i] = c + 2 * i < n_cells ? (w[i] & 0xFFFFu) : 0u;
+		v[2 * i + 1] = c + 2 * i + 1 < n_cells ? (w[i] >> 16) : 0u;
+	}
+}
+
 __global__ void __launch_bounds__(256) cell_reduce_kernel(const uint16_t* cells, const uint32_t* n_items, uint32_t nd, uint32_t* block_sums, const uint32_t* flags)
 {
 	__shared__ uint32_t s_w[8];
@@ -334,12 +348,11 @@ __global__ void __launch_bounds__(256) cell_reduce_kernel(const uint16_t* cells,
 	const uint64_t n_cells = (uint64_t)nd * *n_items;
 	const uint64_t c0 = (uint64_t)blockIdx.x * kCellChunk;
 	if (c0 >= n_cells) return;
+	uint32_t v[16];
+	cell_load16(cells, c0 + (uint64_t)threadIdx.x * 16, n_cells, v);
 	uint32_t sum = 0;
 #pragma unroll
-	for (int i = 0; i < kCellChunk / 256; ++i) {
-		const uint64_t c = c0 + i * 256 + threadIdx.x;
-		if (c < n_cells) sum += cells[c];
-	}
+	for (int i = 0; i < 16; ++i) sum += v[i];
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
 	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
@@ -383,21 +396,19 @@ __global__ void __launch_bounds__(1024) cell_scan_sums_kernel(uint32_t* block_su
 
 __global__ void __launch_bounds__(256) cell_scan_kernel(const uint16_t* cells, const uint32_t* n_items, uint32_t nd, const uint32_t* block_sums, uint32_t* out, const uint32_t* flags)
 {
+	static_assert(kCellChunk == 256 * 16, "16 consecutive cells per thread");
 	__shared__ uint32_t s_w[8];
+	__shared__ uint32_t s_t[kCellChunk + kCellChunk / 16];       // the chunk's prefixes, padded (index i lives at i + i / 16): transposed for coalesced stores
 	if (*flags & kMsdFlagFallback) return;
 	const uint64_t n_cells = (uint64_t)nd * *n_items;
 	const uint64_t c0 = (uint64_t)blockIdx.x * kCellChunk;
 	if (c0 >= n_cells) return;
-	constexpr int PER = kCellChunk / 256;      // 16 consecutive cells per thread
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	uint32_t v[PER];
+	uint32_t v[16];
+	cell_load16(cells, c0 + (uint64_t)tid * 16, n_cells, v);
 	uint32_t sum = 0;
 #pragma unroll
-	for (int i = 0; i < PER; ++i) {
-		const uint64_t c = c0 + (uint64_t)tid * PER + i;
-		v[i] = c < n_cells ? cells[c] : 0;
-		sum += v[i];
-	}
+	for (int i = 0; i < 16; ++i) sum += v[i];
 	uint32_t inc = sum;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
@@ -409,10 +420,15 @@ __global__ void __launch_bounds__(256) cell_scan_kernel(const uint16_t* cells, c
 	uint32_t base = block_sums[blockIdx.x] + inc - sum;
 	for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
 #pragma unroll
-	for (int i = 0; i < PER; ++i) {
-		const uint64_t c = c0 + (uint64_t)tid * PER + i;
-		if (c < n_cells) out[c] = base;
+	for (int i = 0; i < 16; ++i) {           // thread t owns padded words 17 t .. 17 t + 15: conflict-free
+		s_t[tid * 17 + i] = base;
 		base += v[i];
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < 16; ++i) {
+		const uint32_t j = i * 256 + tid;
+		if (c0 + j < n_cells) out[c0 + j] = s_t[j + (j >> 4)];
 	}
 }
 
