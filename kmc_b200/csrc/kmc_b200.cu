@@ -27,6 +27,7 @@ constexpr int kHistRows = kMaxPasses + 1;
 constexpr int kCounterSlots = kMaxPasses + 8;     // tile counters: one per pass + [kMaxPasses] for count_emit
 constexpr uint32_t kEpochLimit = (1u << 22) - 2;
 constexpr int kStageRing = 4;
+constexpr size_t kMaxLeaves = 256 * 1024;          // level 1: 8 bits, level 2: up to 10 bits
 
 thread_local std::string g_create_error;
 
@@ -37,7 +38,7 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint32_t msd_flags[4];                        // [0] kMsdFlagFallback (leaves too large -> LSD passes), [1] always 0
 	uint32_t msd_n_items[2];                      // work items of the level-1 / level-2 segmentation
 	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves, leaf-count
-	uint32_t leaf_group_sum[64];                  // emitted records per group of 1024 leaves
+	uint32_t leaf_group_sum[kMaxLeaves / 1024];   // emitted records per group of 1024 leaves
 };
 
 struct Slot {
@@ -60,7 +61,7 @@ struct Slot {
 	// hybrid MSD sort: bucket boundaries and work-item tables
 	uint64_t* msd_seg1 = nullptr;                           // [2]      {0, n}
 	uint64_t* msd_start2 = nullptr;                         // [257]    level-1 buckets
-	uint64_t* msd_start3 = nullptr;                         // [65537]  level-2 buckets
+	uint64_t* msd_start3 = nullptr;                         // [kMaxLeaves + 1]  level-2 buckets
 	uint32_t* msd_item_base1 = nullptr;                     // [2]
 	uint32_t* msd_item_base2 = nullptr;                     // [257]
 	uint32_t* msd_item_seg2 = nullptr; size_t msd_item_seg2_cap = 0;
@@ -71,7 +72,7 @@ struct Slot {
 	uint32_t* msd_block_sums = nullptr; size_t msd_block_sums_cap = 0;
 	// leaf-count path
 	uint8_t* leaf_tmp = nullptr; size_t leaf_tmp_cap = 0;
-	uint32_t* leaf_emit = nullptr; uint64_t* leaf_off = nullptr;          // [65536]
+	uint32_t* leaf_emit = nullptr; uint64_t* leaf_off = nullptr;          // [kMaxLeaves]
 	const char* pass_names[kMaxPasses + 8] = {};
 	uint32_t last_n_packs = 1;
 	uint64_t* cdesc = nullptr; size_t cdesc_cap = 0;        // count look-back descriptors
@@ -101,7 +102,8 @@ struct kmcb200_ctx {
 	uint32_t key_bytes = 0, suffix_bytes = 0, counter_bytes = 0;
 	uint64_t lut_entries = 0;
 	int sm_count = 0;
-	int occ_radix = 1, occ_expand = 1, occ_msd_part = 1, occ_msd_local = 1;
+	int occ_radix = 1, occ_expand = 1, occ_msd_part = 1, occ_msd_part_wide = 1, occ_msd_local = 1;
+	uint32_t force_b2 = 0;                                  // KMCB200_L2_BITS: bits of the second partition level (0: chosen from the bin size)
 	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
@@ -195,6 +197,9 @@ int setup_kernels(kmcb200_ctx* ctx)
 	CU(cudaFuncSetAttribute(count_emit_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
 	CU(cudaFuncSetAttribute(msd_partition_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MsdSmem<WORDS>::kBytes));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_part, msd_partition_kernel<WORDS>, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS>::kBytes));
+	CU(cudaFuncSetAttribute(msd_partition_kernel<WORDS, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, MsdSmem<WORDS, 1024>::kBytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_part_wide, msd_partition_kernel<WORDS, 1024>, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS, 1024>::kBytes));
+	if (ctx->occ_msd_part_wide < 1) ctx->occ_msd_part_wide = 1;
 	const int local_smem = msd_local_cap<WORDS>() * 8 * WORDS + (MsdLocalCfg<WORDS>::kThreads / 32) * 1024;
 	CU(cudaFuncSetAttribute(msd_local_sort_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, local_smem));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_msd_local, msd_local_sort_kernel<WORDS>, MsdLocalCfg<WORDS>::kThreads, local_smem));
@@ -225,16 +230,31 @@ __global__ void msd_setup_kernel(uint64_t* seg1, uint32_t* item_base1, uint32_t*
 	*n_items1 = nt;
 }
 
+// bits of the second partition level: leaves of ~1 K records.  Counted leaves (the bin path) are streamed by one warp and may be any
+// size, but a leaf beyond one table round costs extra rounds, so the level takes up to 10 bits; sorted leaves (seam #1) must fit on chip,
+// and canonical k-mers crowd into the low prefixes (largest leaf ~4.4x the mean): aim at a fifth of the capacity, 8 bits at most.
+template <int WORDS>
+uint32_t choose_b2(const kmcb200_ctx* ctx, uint64_t n, bool counted_leaves)
+{
+	const uint64_t target = counted_leaves ? 1024 : std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64);
+	uint32_t lg = 0;
+	while ((1ull << lg) < (n + target - 1) / target) ++lg;
+	uint32_t b2 = lg > 8 ? std::min(lg - 8, counted_leaves ? 10u : 8u) : 0;
+	if (counted_leaves && ctx->force_b2) b2 = ctx->force_b2;          // (tests: the wide second level on small bins)
+	return b2;
+}
+template <int WORDS> uint32_t choose_nd2(const kmcb200_ctx* ctx, uint64_t n, bool counted_leaves) { return 1u << choose_b2<WORDS>(ctx, n, counted_leaves); }
+
 // upper bound of the level-1 work items of a bin
 size_t msd_max_items1(uint64_t n_rec, uint32_t n_packs) { return (size_t)(n_rec / kExpandMinTile) + n_packs + 2; }
 
 template <int WORDS>
-int ensure_msd(kmcb200_ctx* ctx, Slot& s, uint64_t n, uint32_t n_packs)
+int ensure_msd(kmcb200_ctx* ctx, Slot& s, uint64_t n, uint32_t n_packs, uint32_t nd2 = 256)
 {
 	static_assert(msd_tile<WORDS>() >= ExpandCfg<WORDS>::kTile, "a partition tile must hold an expand tile");
 	const size_t items1 = std::max(msd_max_items1(n, n_packs), (size_t)(n / msd_tile<WORDS>()) + 2);
 	const size_t items2 = (size_t)(n / msd_tile<WORDS>()) + 260;
-	const size_t cells = 256 * std::max(items1, items2);
+	const size_t cells = std::max(256 * items1, (size_t)std::max(nd2, 256u) * items2);
 	if (int rc = ensure(ctx, s.msd_item_lo1, s.msd_item_lo1_cap, items1)) return rc;
 	if (int rc = ensure(ctx, s.msd_item_cnt1, s.msd_item_cnt1_cap, items1)) return rc;
 	if (int rc = ensure(ctx, s.msd_item_seg2, s.msd_item_seg2_cap, std::max(items1, items2))) return rc;
@@ -308,7 +328,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 	const bool msd = ctx->use_msd && key_bits >= 24 && n >= (1u << 16);
 	const uint32_t top_shift = key_bits - 8;
 	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
-	if (msd) if (int rc = ensure_msd<WORDS>(ctx, s, n, n_packs)) return rc;
+	if (msd) if (int rc = ensure_msd<WORDS>(ctx, s, n, n_packs, choose_nd2<WORDS>(ctx, n, plan != nullptr))) return rc;      // (sized alike by stage_expand: no reallocation here when its cells are in use)
 
 	if (!hist_ready) if (int rc = zero_async(ctx, s.zero, sizeof(ZeroBlock), st)) return rc;
 	int iv = 0;      // timed interval index
@@ -316,13 +336,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 	void* lsd_in = a; void* lsd_out = b;
 	const uint32_t* lsd_flag = nullptr;
 	if (msd) {
-		// leaves of ~1 K records: b2 = bits of the second partition level
-		// counted leaves (k <= 32) are streamed and may be any size; sorted leaves must fit on chip, and canonical k-mers crowd
-		// into the low prefixes (largest leaf ~4.4x the mean): aim at a fifth of the capacity
-		const uint64_t target = plan ? 1024 : std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64);
-		uint32_t lg = 0;
-		while ((1ull << lg) < (n + target - 1) / target) ++lg;
-		const uint32_t b2 = lg > 8 ? std::min(lg - 8, 8u) : 0;
+		const uint32_t b2 = choose_b2<WORDS>(ctx, n, plan != nullptr);
 		const uint32_t nd2 = 1u << b2;
 		const uint32_t cap = plan ? kLwMaxLeaf : (uint32_t)msd_local_cap<WORDS>();      // counted leaves are streamed by one warp: only a very loose limit
 		const bool final_in_b = (key_bytes % 2) == 0;                 // where the LSD passes (started from b) end; the leaves go to the same place
@@ -332,7 +346,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		const size_t max_items1 = hist_ready ? msd_max_items1(n, n_packs) : (size_t)(n / MTILE) + 2;
 		const size_t max_items2 = (size_t)(n / MTILE) + 260;
 		const uint32_t pgrid1 = (uint32_t)std::min<size_t>(max_items1, (size_t)ctx->sm_count * ctx->occ_msd_part);
-		const uint32_t pgrid2 = (uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * ctx->occ_msd_part);
+		const uint32_t pgrid2 = (uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * (nd2 > 256 ? ctx->occ_msd_part_wide : ctx->occ_msd_part));
 		const int local_smem = msd_local_cap<WORDS>() * 8 * WORDS + (MsdLocalCfg<WORDS>::kThreads / 32) * 1024;
 
 		MsdItems items1{};
@@ -365,7 +379,8 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			MsdItems items2{};
 			items2.seg_start = s.msd_start2; items2.item_base = s.msd_item_base2; items2.item_seg = s.msd_item_seg2; items2.n_items = &s.zero->msd_n_items[1];
 			MsdCountArgs c2{b, items2, top_shift - b2, nd2, s.msd_cells, flags};
-			msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
+			if (nd2 > 256) msd_count_kernel<WORDS, 1024><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
+			else msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
 			ctx->launches++;
 			if (int rc = launch_cell_scan(ctx, s, items2.n_items, nd2, max_items2, flags, st)) return rc;
 			MsdBoundsArgs bb{};
@@ -376,7 +391,8 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			MsdPartArgs p2{};
 			p2.in = b; p2.out = a; p2.items = items2; p2.cell_scan = s.msd_cell_scan; p2.shift = top_shift - b2; p2.nd = nd2;
 			p2.flags = flags;
-			msd_partition_kernel<WORDS><<<pgrid2, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS>::kBytes, st>>>(p2);
+			if (nd2 > 256) msd_partition_kernel<WORDS, 1024><<<pgrid2, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS, 1024>::kBytes, st>>>(p2);
+			else msd_partition_kernel<WORDS><<<pgrid2, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS>::kBytes, st>>>(p2);
 			ctx->launches++;
 			s.pass_names[iv] = "msd_partition_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 		}
@@ -519,7 +535,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.recs = d_recs;
 	a.mode = em.mode; a.fshift = em.fshift; a.fprefix = em.fprefix; a.fmask = em.fmask; a.hist12 = em.hist12; a.out_counter = em.out_counter;
 	if (em.mode == kExpandAll) {
-		if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np)) return rc;
+		if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np, DISPATCH_WORDS(ctx, choose_nd2, ctx, n_rec, ctx->use_leaf))) return rc;
 		a.cells1 = s.msd_cells; a.item_lo1 = s.msd_item_lo1; a.item_cnt1 = s.msd_item_cnt1;
 	} else { a.cells1 = nullptr; a.item_lo1 = nullptr; a.item_cnt1 = nullptr; }
 	a.top_shift = std::max(2u * k, 8u) - 8u;
@@ -817,6 +833,7 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
 	if (const char* e = getenv("KMCB200_MAX_BLOCK_RECORDS")) { const long long v = atoll(e); if (v >= 1024) ctx->max_block_records = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_MAX_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= (1 << 17) && v < (1ll << 31)) ctx->max_chunk_bytes = (uint64_t)v; }
+	if (const char* e = getenv("KMCB200_L2_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 10) ctx->force_b2 = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_ROUND_PCT")) { const int v = atoi(e); if (v >= 50 && v <= 1000) ctx->leaf_round_pct = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_SLOT_BITS")) { const int b = atoi(e); if (b == 8 || b == 9 || b == 10) ctx->leaf_slot_bits = b; }
 	ctx->slots.resize(prm->n_slots);
@@ -835,10 +852,10 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 		ok = ok && cudaMemset(s.zero, 0, sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_lut), ctx->lut_entries * 8) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_seg1), 2 * 8) == cudaSuccess;
-		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.leaf_emit), 65536 * 4) == cudaSuccess;
-		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.leaf_off), 65536 * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.leaf_emit), kMaxLeaves * 4) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.leaf_off), kMaxLeaves * 8) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_start2), 257 * 8) == cudaSuccess;
-		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_start3), 65537 * 8) == cudaSuccess;
+		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_start3), (kMaxLeaves + 1) * 8) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_item_base1), 2 * 4) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.msd_item_base2), 257 * 4) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_result), 64) == cudaSuccess;

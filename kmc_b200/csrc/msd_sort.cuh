@@ -112,20 +112,22 @@ __device__ __forceinline__ MsdItemGeom msd_item_geom(const MsdItems& it, uint32_
 // 0.272 ms; this pipeline: 0.265 ms; cursors precomputed from the cells by the producer (position = atomicAdd(&cursor[digit], 1)
 // straight into a staging buffer, no histogram / scan, two barriers instead of five): 0.33 ms - fewer instructions, but slower.
 // ncu: the kernel is bound by the latency of the shared-memory pipeline (48 % short-scoreboard stalls), not by HBM.
-template <int WORDS>
+// NDMAX = 256 or 1024 digits: the second level of a large bin uses up to 10 bits, so that a leaf still holds ~1 K records
+// (the wider variant has one TMA buffer less: shared memory).
+template <int WORDS, int NDMAX = 256>
 struct MsdSmem {
 	static constexpr int kThreads = MsdCfg<WORDS>::kThreads;          // consumer threads
 	static constexpr int kKpt = MsdCfg<WORDS>::kKpt;
 	static constexpr int kTile = kThreads * kKpt;
 	static constexpr int kRecBytes = 8 * WORDS;
-	static constexpr int kStages = 3;
+	static constexpr int kStages = NDMAX > 256 ? 2 : 3;
 	static constexpr int kBufStride = ((kTile + 2) * kRecBytes + 127) & ~127;   // + 2: the aligned load may start one record early / end one late
 	static constexpr int oBuf = 0;
-	static constexpr int oHist = kStages * kBufStride;             // u32 [256]
-	static constexpr int oExcl = oHist + 1024;                     // u32 [256]
-	static constexpr int oGoff = oExcl + 1024;                     // u32 [256]
-	static constexpr int oBase = oGoff + 1024;                     // u32 [kStages][256] output base of (item, digit)
-	static constexpr int oWarpTot = oBase + kStages * 1024;        // u32 [8]
+	static constexpr int oHist = kStages * kBufStride;             // u32 [NDMAX]
+	static constexpr int oExcl = oHist + 4 * NDMAX;                // u32 [NDMAX]
+	static constexpr int oGoff = oExcl + 4 * NDMAX;                // u32 [NDMAX]
+	static constexpr int oBase = oGoff + 4 * NDMAX;                // u32 [kStages][NDMAX] output base of (item, digit)
+	static constexpr int oWarpTot = oBase + kStages * 4 * NDMAX;   // u32 [8]
 	static constexpr int oGeom = oWarpTot + 64;                    // u32 [kStages][4]: head, valid
 	static constexpr int oMbar = oGeom + kStages * 16;             // u64 full[kStages], empty[kStages]
 	static constexpr int kBytes = oMbar + 2 * kStages * 8;
@@ -143,12 +145,13 @@ struct MsdPartArgs {
 	const uint32_t* flags;
 };
 
-template <int WORDS>
+template <int WORDS, int NDMAX = 256>
 __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::kMinBlocks) msd_partition_kernel(const MsdPartArgs p)
 {
-	using S = MsdSmem<WORDS>;
+	using S = MsdSmem<WORDS, NDMAX>;
 	using R = Rec<WORDS>;
 	constexpr int THREADS = S::kThreads, KPT = S::kKpt, STAGES = S::kStages;
+	constexpr int DPT = NDMAX / 256;               // digits per scanning thread (threads 0..255)
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint32_t* hist = reinterpret_cast<uint32_t*>(smem + S::oHist);
 	uint32_t* tile_excl = reinterpret_cast<uint32_t*>(smem + S::oExcl);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 		for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
 		fence_mbar_init();
 	}
-	if (tid < 256) hist[tid] = 0;
+	for (uint32_t d = tid; d < (uint32_t)NDMAX; d += blockDim.x) hist[d] = 0;
 	__syncthreads();
 
 	if (tid >= (uint32_t)THREADS) {
@@ -182,10 +185,10 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 			const uint32_t st = it % STAGES;
 			if (it >= (uint32_t)STAGES) mbar_wait(&empty[st], ((it / STAGES) - 1u) & 1u);      // the consumers are done with this buffer
 			const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item, p.nd);
-#pragma unroll
-			for (int i = 0; i < 8; ++i) {
+#pragma unroll 8
+			for (int i = 0; i < NDMAX / 32; ++i) {
 				const uint32_t d = i * 32 + lane;
-				s_base[st * 256 + d] = d < p.nd ? __ldg(p.cell_scan + g.cell0 + (uint64_t)d * g.cell_stride) : 0u;
+				s_base[st * NDMAX + d] = d < p.nd ? __ldg(p.cell_scan + g.cell0 + (uint64_t)d * g.cell_stride) : 0u;
 			}
 			if (lane == 0) { s_geom[st * 4 + 0] = (uint32_t)(g.lo - g.lo_al); s_geom[st * 4 + 1] = (uint32_t)(g.hi - g.lo); }
 			__syncwarp();
@@ -221,12 +224,12 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 		}
 		bar_sync_named(1, THREADS);
 
-		// ---- exclusive scan of the 256 digit counts (warps 0..7); every thread zeroes its own bin for the next item
-		uint32_t cnt = 0, inc = 0;
+		// ---- exclusive scan of the digit counts (warps 0..7, DPT consecutive digits per thread); every thread zeroes its own bins for the next item
+		uint32_t cnt[DPT], tot = 0, inc = 0;
 		if (tid < 256) {
-			cnt = hist[tid];
-			hist[tid] = 0;
-			inc = cnt;
+#pragma unroll
+			for (int i = 0; i < DPT; ++i) { cnt[i] = hist[tid * DPT + i]; hist[tid * DPT + i] = 0; tot += cnt[i]; }
+			inc = tot;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
 				const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -236,12 +239,15 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 		}
 		bar_sync_named(1, THREADS);
 		if (tid < 256) {
-			uint32_t wb = 0;
+			uint32_t texcl = inc - tot;
 #pragma unroll
-			for (int w = 0; w < 8; ++w) if ((uint32_t)w < warp) wb += warp_tot[w];
-			const uint32_t texcl = wb + inc - cnt;
-			tile_excl[tid] = texcl;
-			goff[tid] = s_base[st * 256 + tid] - texcl;          // global index of tile-sorted position q is goff[d] + q
+			for (int w = 0; w < 8; ++w) if ((uint32_t)w < warp) texcl += warp_tot[w];
+#pragma unroll
+			for (int i = 0; i < DPT; ++i) {
+				tile_excl[tid * DPT + i] = texcl;
+				goff[tid * DPT + i] = s_base[st * NDMAX + tid * DPT + i] - texcl;          // global index of tile-sorted position q is goff[d] + q
+				texcl += cnt[i];
+			}
 		}
 		bar_sync_named(1, THREADS);
 
@@ -278,18 +284,18 @@ struct MsdCountArgs {
 	const uint32_t* flags;
 };
 
-template <int WORDS>
+template <int WORDS, int NDMAX = 256>
 __global__ void __launch_bounds__(512) msd_count_kernel(const MsdCountArgs p)
 {
 	using R = Rec<WORDS>;
-	__shared__ uint32_t sh[2][256];
+	__shared__ uint32_t sh[2][NDMAX];
 	if (*p.flags & kMsdFlagFallback) return;
 	const R* __restrict__ g = reinterpret_cast<const R*>(p.in);
 	const uint32_t n_items = *p.items.n_items;
 	const uint32_t mask = p.nd - 1;
 	const uint32_t tid = threadIdx.x;
 	constexpr int U = (msd_tile<WORDS>() + 511) / 512;
-	if (tid < 256) { sh[0][tid] = 0; sh[1][tid] = 0; }
+	for (uint32_t d = tid; d < (uint32_t)NDMAX; d += 512) { sh[0][d] = 0; sh[1][d] = 0; }
 	// software pipeline: the records of the next item are in flight while this one is counted; one barrier per item
 	uint32_t item = blockIdx.x;
 	MsdItemGeom gm{};
@@ -315,9 +321,9 @@ __global__ void __launch_bounds__(512) msd_count_kernel(const MsdCountArgs p)
 			for (int u = 0; u < U; ++u) { const uint32_t j = u * 512 + tid; if (j < m) k[u] = g[gm.lo + j]; }
 		}
 		__syncthreads();
-		if (tid < 256) {          // (a bin is read and zeroed by its own thread; it is used again two items later, a barrier in between)
-			if (tid < p.nd) p.cells[done.cell0 + (uint64_t)tid * done.cell_stride] = (uint16_t)sh[cur][tid];
-			sh[cur][tid] = 0;
+		for (uint32_t d = tid; d < (uint32_t)NDMAX; d += 512) {          // (a bin is read and zeroed by its own thread; it is used again two items later, a barrier in between)
+			if (d < p.nd) p.cells[done.cell0 + (uint64_t)d * done.cell_stride] = (uint16_t)sh[cur][d];
+			sh[cur][d] = 0;
 		}
 		cur ^= 1;
 	}

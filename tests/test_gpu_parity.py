@@ -71,6 +71,16 @@ def test_leaf_path_all_widths(oracle, monkeypatch, slot_bits, k, both, cmin, p_l
     _check_bin(oracle, synth_bin(31 + k, k, 14000, genome_len=9000, err=0.01), p)
 
 
+@pytest.mark.parametrize("l2_bits", [3, 9, 10])
+@pytest.mark.parametrize("k,both,cmin,p_len", [(31, True, 2, 7), (31, False, 1, 11), (55, True, 2, 7), (70, True, 1, 6), (128, True, 1, 8), (17, True, 1, 5)])
+def test_wide_second_partition_level(oracle, monkeypatch, l2_bits, k, both, cmin, p_len):
+    """Bins of more than 2^26 k-mers partition their second level on 9-10 bits (512 / 1024 digits: the wide variants of the count and
+    scatter kernels, 2^17-2^18 leaves) so that a leaf keeps ~1 K records; forced here on a small bin."""
+    monkeypatch.setenv("KMCB200_L2_BITS", str(l2_bits))
+    p = Params(k=k, both_strands=both, cutoff_min=cmin, lut_prefix_len=p_len)
+    _check_bin(oracle, synth_bin(41 + k, k, 14000, genome_len=9000, err=0.01), p)
+
+
 @pytest.mark.parametrize("k,p_len", [(31, 7), (55, 7), (100, 8)])
 def test_leaf_path_without_duplicates(oracle, k, p_len):
     """Every k-mer distinct (no coverage): the rounds of a leaf overflow their tables and are split on further bits."""
