@@ -91,7 +91,7 @@ constexpr int kWalkSegs = 256;                                   // threads per 
 constexpr int kWalkChunk = kWalkSegBytes * kWalkSegs;            // 64 KiB
 constexpr int kWalkSpec = 1024;
 
-__global__ void __launch_bounds__(kWalkSegs) walk_packs_parallel_kernel(const ExpandArgs a, uint32_t* pack_done)
+__global__ void __launch_bounds__(kWalkSegs, 3) walk_packs_parallel_kernel(const ExpandArgs a, uint32_t* pack_done)
 {
 	extern __shared__ __align__(16) uint8_t wsm[];               // the pack (+ 16 bytes of slack)
 	__shared__ uint32_t s_entry[kWalkSegs], s_exit[kWalkSegs], s_w[16];
@@ -106,7 +106,14 @@ __global__ void __launch_bounds__(kWalkSegs) walk_packs_parallel_kernel(const Ex
 		const uintptr_t g0a = g0 & ~(uintptr_t)15;
 		const uint32_t shift = (uint32_t)(g0 - g0a);
 		const uint32_t nvec = (len + shift + 15) >> 4;
-		for (uint32_t v = tid; v < nvec; v += kWalkSegs) reinterpret_cast<uint4*>(wsm)[v] = __ldg(reinterpret_cast<const uint4*>(g0a) + v);
+		// (8 independent loads in flight per thread: a loop of load -> store pairs would pay the DRAM latency 16 times in a row)
+		for (uint32_t v0 = tid; v0 < nvec; v0 += 8 * kWalkSegs) {
+			uint4 r[8];
+#pragma unroll
+			for (int i = 0; i < 8; ++i) { const uint32_t v = v0 + i * kWalkSegs; r[i] = v < nvec ? __ldg(reinterpret_cast<const uint4*>(g0a) + v) : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+			for (int i = 0; i < 8; ++i) { const uint32_t v = v0 + i * kWalkSegs; if (v < nvec) reinterpret_cast<uint4*>(wsm)[v] = r[i]; }
+		}
 		if (tid == 0) s_bad = 0;
 		__syncthreads();
 		// byte i of the pack is wsm[shift + i]

@@ -26,7 +26,7 @@
 //
 // Entry formats (64 bit, EMPTY = all ones):
 //   WORDS == 1   [ key bits below the group bits (<= 47) | count ]     the k-mer is rebuilt from leaf, round, group and entry
-//   WORDS >= 2   [ index of the first copy inside the leaf (32) | count (32) ]   equality is checked against that record
+//   WORDS >= 2   [ index of the first copy inside the leaf (16) | hash tag (16) | count (32) ]   equality is checked against that record (only when the tags agree)
 #pragma once
 #include "common.cuh"
 #include "expand.cuh"
@@ -328,32 +328,34 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 								for (int i = 0; i < WORDS; ++i) key[u].w[i] = 0;
 							}
 						}
-						uint32_t slot[U];
-						unsigned long long old[U];
+						uint32_t slot[U], tag[U];
+						unsigned long long old[U], mine[U];
 						uint32_t live = 0;
 #pragma unroll
 						for (int u = 0; u < U; ++u) {              // both first probes are issued before any result is looked at
 							const uint32_t j = j0 + u * 32 + lane;
 							bool in = j < m;
 							if (e && rec_bits<WORDS>(key[u], sub_shift, emask) != r) in = false;      // another round's k-mer
-							slot[u] = (rec_bits<WORDS>(key[u], gshift, NG - 1) << kLwGroupBits) | (lw_hash<WORDS>(key[u]) & ((1u << kLwGroupBits) - 1u));
+							const uint32_t h = lw_hash<WORDS>(key[u]);
+							slot[u] = (rec_bits<WORDS>(key[u], gshift, NG - 1) << kLwGroupBits) | (h & ((1u << kLwGroupBits) - 1u));
+							tag[u] = (h >> 8) & 0xFFFFu;                 // 16 further hash bits: an occupied slot with another tag needs no look at its record
+							mine[u] = ((unsigned long long)j << 48) | ((unsigned long long)tag[u] << 32) | 1ull;      // j <= 65533: never the EMPTY pattern
 							old[u] = 0;
 							if (in) {
-								old[u] = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[slot[u]]), (unsigned long long)kLwEmpty, ((unsigned long long)j << 32) | 1ull);
+								old[u] = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[slot[u]]), (unsigned long long)kLwEmpty, mine[u]);
 								live |= 1u << u;
 							}
 						}
 #pragma unroll
 						for (int u = 0; u < U; ++u) {          // (the probe loop only looks for the slot, as in lw_insert1)
 							const bool act = (live >> u) & 1u;
-							const uint32_t j = j0 + u * 32 + lane;
 							uint32_t s = slot[u];
 							unsigned long long o = act ? old[u] : kLwEmpty;
 							uint32_t probe = 0;
-							while (o != kLwEmpty && !rec_equal<WORDS>(lw_load<WORDS>(recs + lo + (uint32_t)(o >> 32)), key[u])) {
+							while (o != kLwEmpty && !(((uint32_t)(o >> 32) & 0xFFFFu) == tag[u] && rec_equal<WORDS>(lw_load<WORDS>(recs + lo + (uint32_t)(o >> 48)), key[u]))) {
 								if (++probe > ((1u << kLwGroupBits) - 1u)) break;
 								s = (s & ~((1u << kLwGroupBits) - 1u)) | ((s + 1u) & ((1u << kLwGroupBits) - 1u));
-								o = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[s]), (unsigned long long)kLwEmpty, ((unsigned long long)j << 32) | 1ull);
+								o = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[s]), (unsigned long long)kLwEmpty, mine[u]);
 							}
 							if (probe > ((1u << kLwGroupBits) - 1u)) ok = false;
 							else if (act) {
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 				auto entry_key = [&](uint32_t s, uint64_t ent) -> R {
 					R kk;
 					if (WORDS == 1) kk.w[0] = key_hi | ((uint64_t)(s >> kLwGroupBits) << gshift) | ((ent >> cb) & rem_mask);
-					else kk = lw_load<WORDS>(recs + lo + (uint32_t)(ent >> 32));
+					else kk = lw_load<WORDS>(recs + lo + (uint32_t)(ent >> 48));
 					return kk;
 				};
 				// ---- reached & ~over is the result: prefix popcounts of the words = positions of the groups
@@ -522,9 +524,20 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, co
 	const uint8_t* src = tmp + start[leaf] * pad;
 	uint8_t* dst = out + leaf_off[leaf] * ob;
 	const uint32_t magic = 0xFFFFFFFFu / ob + 1;          // p / ob == umulhi(p, magic) for p < 2^16 ... checked: larger leaves take the division
-	for (uint32_t p = lane; p < nbytes; p += 32) {
-		const uint32_t r = nbytes < 65536u ? __umulhi(p, magic) : p / ob;
-		dst[p] = src[(size_t)r * pad + (p - r * ob)];
+	// (4 independent byte loads in flight per lane: the loop is bound by the latency of its loads)
+	for (uint32_t p0 = lane; p0 < nbytes; p0 += 128) {
+		uint8_t v[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const uint32_t p = p0 + 32 * i;
+			const uint32_t r = nbytes < 65536u ? __umulhi(p, magic) : p / ob;
+			v[i] = p < nbytes ? __ldg(src + (size_t)r * pad + (p - r * ob)) : (uint8_t)0;
+		}
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const uint32_t p = p0 + 32 * i;
+			if (p < nbytes) dst[p] = v[i];
+		}
 	}
 }
 
