@@ -14,7 +14,7 @@ import numpy as np
 from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmc_b200.so")
+LIB_PATH = os.path.abspath(os.environ["KMCB200_LIB"]) if os.environ.get("KMCB200_LIB") else os.path.join(_HERE, "libkmc_b200.so")      # KMCB200_LIB: experiment builds (kmc_b200.build.build_variant)
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_BIN_FORMAT, ERR_CAPACITY, ERR_BUSY = 0, -1, -2, -3, -4, -5, -6
 

@@ -111,7 +111,10 @@ __device__ __forceinline__ MsdItemGeom msd_item_geom(const MsdItems& it, uint32_
 // Measured alternatives (B200, 2^26 8-byte records, per pass): thread 0 claiming tickets and issuing the copies itself, two buffers:
 // 0.272 ms; this pipeline: 0.265 ms; cursors precomputed from the cells by the producer (position = atomicAdd(&cursor[digit], 1)
 // straight into a staging buffer, no histogram / scan, two barriers instead of five): 0.33 ms - fewer instructions, but slower.
-// ncu: the kernel is bound by the latency of the shared-memory pipeline (48 % short-scoreboard stalls), not by HBM.
+// ncu: the kernel is bound by the shared-memory pipeline (48 % short-scoreboard stalls, ~2100 wavefronts per 4096-record item), not by HBM.
+// Also measured and dropped: the same cursors with in-place regrouping and three buffers (0.39 ms: the single producer warp cannot gather
+// 768 values per item fast enough); loads / atomics / stores of a phase issued in separate batches for more memory-level parallelism
+// (0.29 ms: the pipeline is throughput-, not latency-bound).
 // NDMAX = 256 or 1024 digits: the second level of a large bin uses up to 10 bits, so that a leaf still holds ~1 K records
 // (the wider variant has one TMA buffer less: shared memory).
 template <int WORDS, int NDMAX = 256>
