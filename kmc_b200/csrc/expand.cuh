@@ -89,7 +89,10 @@ __device__ __forceinline__ uint64_t tile_first_base(uint64_t pack_start, uint32_
 constexpr int kWalkSegBytes = 256;
 constexpr int kWalkSegs = 256;                                   // threads per CTA = segments per pack
 constexpr int kWalkChunk = kWalkSegBytes * kWalkSegs;            // 64 KiB
-constexpr int kWalkSpec = 1024;
+#ifndef KMCB200_WALK_SPEC
+#define KMCB200_WALK_SPEC 1024
+#endif
+constexpr int kWalkSpec = KMCB200_WALK_SPEC;
 
 __global__ void __launch_bounds__(kWalkSegs, 3) walk_packs_parallel_kernel(const ExpandArgs a, uint32_t* pack_done)
 {

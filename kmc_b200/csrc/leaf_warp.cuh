@@ -41,6 +41,9 @@ constexpr int kLwWarps = 4;                      // warps per CTA (independent o
 #endif
 constexpr uint32_t kLwGroupBits = KMCB200_LW_GROUP_BITS;              // slots per group = 64: a real k-mer and its error variants share a group, groups must absorb such clumps
 constexpr int kLwList = 256;                     // u16 list of survivors, one step of the emission
+#ifndef KMCB200_LW_HASH32
+#define KMCB200_LW_HASH32 1
+#endif
 #ifndef KMCB200_LW_RING
 #define KMCB200_LW_RING 256
 #endif
@@ -174,7 +177,11 @@ __device__ KMCB200_LW_INSERT_ATTR void lw_insert1(const LwRound& t, const uint64
 #pragma unroll
 	for (int v = 0; v < V; ++v) {
 		const uint64_t rem = kk[v] & t.rem_mask;
+#if KMCB200_LW_HASH32
+		slot[v] = ((((uint32_t)(kk[v] >> t.gshift)) & t.gmask) << kLwGroupBits) | ((((uint32_t)rem ^ (uint32_t)(rem >> 27)) * 0x9E3779B1u) >> (32 - kLwGroupBits));
+#else
 		slot[v] = ((((uint32_t)(kk[v] >> t.gshift)) & t.gmask) << kLwGroupBits) | (uint32_t)((rem * 0x9E3779B97F4A7C15ull) >> (64 - kLwGroupBits));
+#endif
 		ent[v] = (rem << t.cb) | 1ull;
 		old[v] = kLwEmpty;
 		if ((vmask >> v) & 1u) old[v] = atomicCAS(reinterpret_cast<unsigned long long*>(&t.main[slot[v]]), (unsigned long long)kLwEmpty, ent[v]);
