@@ -17,6 +17,15 @@
  * kmcb200_last_error() gives the message.  A context is bound to one GPU and may be used by one host
  * thread at a time (KMC runs one sorter thread per context).  There is NO CPU fallback: without a usable
  * sm_100 device kmcb200_create fails with KMCB200_ERR_NO_DEVICE.
+ *
+ * Environment knobs read by kmcb200_create (development / tests; the defaults are the measured best):
+ *   KMCB200_SORT=lsd               plain 8-bit LSD passes instead of the hybrid MSD sort
+ *   KMCB200_LEAF=sort              sort the leaves on chip + count_emit instead of counting them in hash tables
+ *   KMCB200_LEAF_SLOT_BITS=8|9|10  slots of a warp's leaf table (default 10)
+ *   KMCB200_LEAF_ROUND_PCT=n       records per table round in percent of the slots (default 100)
+ *   KMCB200_L2_BITS=1..10          bits of the second partition level (default: from the bin size, <= 10)
+ *   KMCB200_MAX_BLOCK_RECORDS=n    a bin with more k-mers is counted key block by key block (default 2^28)
+ *   KMCB200_MAX_CHUNK_BYTES=n      ... and expanded in chunks of at most n bytes (default 2^30)
  */
 #ifndef KMC_B200_H
 #define KMC_B200_H
