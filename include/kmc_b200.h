@@ -116,8 +116,10 @@ int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, ui
 /* ---- device-level entry points (pointers are DEVICE pointers, `stream` is a cudaStream_t or NULL) ---
  * All work is enqueued on `stream` (NULL = the context's compute stream) and is asynchronous with respect to the host. */
 
-/* Expand + sort + count one bin that already lives in HBM.  d_superkmers must be 8-byte aligned and readable
- * up to the next multiple of 8 past size.  pack_bytes is a HOST array.  d_result receives 8 x uint64:
+/* Expand + sort + count one bin that already lives in HBM.  d_superkmers must be 8-byte aligned and READABLE FOR 32 BYTES PAST
+ * `size` (the walk and the staging use 16-byte vector loads on the absolute 16-byte grid); likewise the record buffers given to
+ * kmcb200_dev_sort / kmcb200_dev_count must be readable for one record past n (the TMA tile loads round an odd count up to an
+ * even one).  The values read there are never used.  pack_bytes is a HOST array.  d_result receives 8 x uint64:
  * [0..3] stats, [4] emitted records, [5] capacity error flag, [6] bin-format error bits,
  * [7] 1 when the hybrid MSD / leaf-count path gave up (skew) and the LSD fallback produced the (identical) result. */
 int kmcb200_dev_process_bin(kmcb200_ctx* ctx, uint32_t slot,
@@ -146,14 +148,6 @@ int kmcb200_stage_times(kmcb200_ctx* ctx, uint32_t slot, float* ms, uint32_t cap
 /* Comma-separated names of the timed sort intervals ms[3..] of kmcb200_stage_times ("msd_partition_L1,msd_count_L2,...").
  * Returns their number. */
 int kmcb200_stage_names(kmcb200_ctx* ctx, uint32_t slot, char* buf, uint32_t capacity);
-
-/* Synthetic bin in stage 1's output format (kb_collector.cpp:34-90) for tests and benchmarks: super-k-mers are
- * substrings (random strand, `err_ppm` substitutions per million symbols) of a random genome of genome_len
- * symbols, with `a` ~ geometric(mean mean_extra), capped at 255, until exactly n_rec k-mers exist.
- * Two-call protocol: with data == NULL it only returns the sizes.  pack_bytes holds one entry per <= 64 KiB pack. */
-int kmcb200_synth_bin(uint64_t seed, uint32_t kmer_len, uint64_t n_rec, uint64_t genome_len, double mean_extra,
-	uint32_t err_ppm, uint8_t* data, uint64_t data_capacity, uint64_t* size,
-	uint64_t* pack_bytes, uint32_t pack_capacity, uint32_t* n_packs, uint64_t* n_super_kmers);
 
 #ifdef __cplusplus
 }

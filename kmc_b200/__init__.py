@@ -34,7 +34,7 @@ EXPORTS = [
     "kmcb200_create", "kmcb200_destroy", "kmcb200_last_error", "kmcb200_out_rec_bytes", "kmcb200_out_capacity", "kmcb200_lut_entries",
     "kmcb200_host_alloc", "kmcb200_host_free", "kmcb200_process_bin", "kmcb200_submit_bin", "kmcb200_wait_bin", "kmcb200_sort_records",
     "kmcb200_dev_process_bin", "kmcb200_dev_expand", "kmcb200_dev_sort", "kmcb200_dev_count", "kmcb200_kernel_launches",
-    "kmcb200_stage_times", "kmcb200_stage_names", "kmcb200_synth_bin",
+    "kmcb200_stage_times", "kmcb200_stage_names",
 ]
 
 _lib = None
@@ -76,7 +76,6 @@ def load_library(build_if_needed=True):
     L.kmcb200_kernel_launches.restype = u64
     L.kmcb200_stage_times.argtypes = [vp, u32, C.POINTER(C.c_float), u32]
     L.kmcb200_stage_names.argtypes = [vp, u32, C.c_char_p, u32]
-    L.kmcb200_synth_bin.argtypes = [u64, u32, u64, u64, C.c_double, u32, vp, u64, C.POINTER(u64), vp, u32, C.POINTER(u32), C.POINTER(u64)]
     _lib = L
     return L
 
@@ -119,24 +118,6 @@ class BinResult:
     @property
     def stats(self):
         return (self.n_unique, self.n_cutoff_min, self.n_cutoff_max, self.n_total)
-
-
-def synth_bin(seed, kmer_len, n_rec, genome_len=None, mean_extra=11.0, err_ppm=10000, pinned_ctx=None) -> SuperKmerBin:
-    """Synthetic bin in the collector's format (kb_collector.cpp:34-90); duplicate-rich when genome_len << n_rec."""
-    L = load_library()
-    if genome_len is None:
-        genome_len = max(n_rec // 30, kmer_len + 256)
-    size, n_packs, n_sk = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
-    rc = L.kmcb200_synth_bin(seed, kmer_len, n_rec, genome_len, mean_extra, err_ppm, None, 0, C.byref(size), None, 0, C.byref(n_packs), C.byref(n_sk))
-    if rc != 0:
-        raise KmcB200Error(rc, "kmcb200_synth_bin (sizing)")
-    data = np.zeros(size.value + 64, dtype=np.uint8)
-    packs = np.zeros(max(n_packs.value, 1), dtype=np.uint64)
-    rc = L.kmcb200_synth_bin(seed, kmer_len, n_rec, genome_len, mean_extra, err_ppm, data.ctypes.data, data.size, C.byref(size),
-                             packs.ctypes.data, packs.size, C.byref(n_packs), C.byref(n_sk))
-    if rc != 0:
-        raise KmcB200Error(rc, "kmcb200_synth_bin")
-    return SuperKmerBin(data=data[:size.value], n_rec=n_rec, pack_bytes=packs[:n_packs.value], n_super_kmers=n_sk.value, kmer_len=kmer_len)
 
 
 class Stage2Context:

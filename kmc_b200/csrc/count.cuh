@@ -15,6 +15,7 @@
 //     window) before it touches global memory.
 #pragma once
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace kmcb {
 
@@ -34,7 +35,8 @@ struct CountArgs {
 	uint64_t* desc;          // [n_tiles] look-back chain
 	uint32_t epoch;
 	uint32_t* tile_counter;  // zero-initialised
-	const uint32_t* run_flag; // nullptr: always run; else only when (*run_flag & 1) - fallback of the leaf-count path
+	const uint32_t* run_flag; // nullptr: always run; else only when (*run_flag & kRunMask) == run_need (radix_sort.cuh)
+	uint32_t run_need;
 };
 
 template <int WORDS> struct CountCfg { static constexpr int kThreads = 256, kIpt = (WORDS == 1 ? 8 : WORDS == 2 ? 4 : 2); };
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 	__shared__ uint32_t s_tile, s_warp[WARPS], s_total;
 	__shared__ uint64_t s_run_head0, s_base;
 
-	if (a.run_flag && !(*a.run_flag & 1u)) return;
+	if (!run_allowed(a.run_flag, a.run_need)) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const R* __restrict__ g = reinterpret_cast<const R*>(a.recs);
 

@@ -54,8 +54,10 @@ struct ExpandArgs {
 	uint32_t* pack_nk;           // [n_packs]
 	uint64_t* pack_kbase;        // [n_packs + 1]
 	uint32_t* pack_tbase;        // [n_packs + 1]
-	uint32_t* tile_pack;         // [n_rec / kExpandTile + n_packs + 1]
-	uint32_t* status;            // [0] error bits, [1] total tiles
+	uint32_t* tile_pack;         // [tile_pack_cap]
+	uint64_t tile_pack_cap;      // n_rec / kExpandMinTile + n_packs + 2 (sized from the CALLER's n_rec: writes are clamped to it)
+	uint32_t* status;            // [0] error bits, [1] total tiles (0 when the bin is malformed: nothing is expanded)
+	uint32_t* flags;             // msd_sort.cuh: [0] / [1] get kMsdFlagAbort when the bin is malformed, so that no kernel behind touches the records
 	// output
 	void* recs;
 	// level-1 work items of the MSD partition = the output tiles of this kernel (msd_sort.cuh)
@@ -73,6 +75,7 @@ enum : uint32_t { kExpandAll = 0, kExpandCount12 = 1, kExpandFilter = 2 };
 constexpr uint64_t kExpandUnknownRecs = ~0ull;      // n_rec of a chunk: not checked
 
 enum : uint32_t { kErrPackWalk = 1, kErrRecCount = 2 };
+constexpr uint32_t kExpandAbortFlag = 2;      // = kMsdFlagAbort (msd_sort.cuh)
 
 __device__ __forceinline__ uint64_t tile_first_base(uint64_t pack_start, uint32_t p, uint32_t tile) { return pack_start * 4 / tile + p; }
 
@@ -161,7 +164,10 @@ __global__ void __launch_bounds__(kWalkSegs, 3) walk_packs_parallel_kernel(const
 		}
 		if (lane == 31) { s_w[warp] = ir; s_w[8 + warp] = ik; }
 		__syncthreads();
-		if (s_bad) { if (tid == 0) pack_done[p] = 0; return; }          // left to walk_packs_kernel
+		if (s_bad) {          // the repaired chain IS the exact chain: its last record does not end with the pack -> the bin is malformed
+			if (tid == 0) { atomicOr(a.status, kErrPackWalk); a.pack_nsk[p] = 0; a.pack_nk[p] = 0; pack_done[p] = 1; }
+			return;
+		}
 		uint32_t br = ir - nrec, bk = ik - nk, tr = 0, tk = 0;
 #pragma unroll
 		for (int w = 0; w < 8; ++w) { if ((uint32_t)w < warp) { br += s_w[w]; bk += s_w[8 + w]; } tr += s_w[w]; tk += s_w[8 + w]; }
@@ -263,7 +269,10 @@ __global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) { carry_k = 0; carry_t = 0; }
 	__syncthreads();
-	for (uint32_t base = 0; base < a.n_packs; base += 1024) {
+	// A malformed bin (a pack that does not end on a record boundary, more / fewer k-mers than n_rec) must not reach the kernels
+	// behind: their buffers are sized from the caller's n_rec.  It is stopped here: no tiles, and the abort flag for the sort / count.
+	const bool walk_failed = (a.status[0] & kErrPackWalk) != 0;
+	for (uint32_t base = 0; base < a.n_packs && !walk_failed; base += 1024) {
 		const uint32_t p = base + tid;
 		const uint32_t nk = p < a.n_packs ? a.pack_nk[p] : 0;
 		const uint32_t nt = (nk + a.tile - 1) / a.tile;
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
 		if (p < a.n_packs) {
 			a.pack_kbase[p] = ek;
 			a.pack_tbase[p] = et;
-			for (uint32_t t = 0; t < nt; ++t) a.tile_pack[et + t] = p;
+			for (uint32_t t = 0; t < nt && (uint64_t)et + t < a.tile_pack_cap; ++t) a.tile_pack[et + t] = p;
 		}
 		__syncthreads();
 		if (tid == 1023) { carry_k = ek + nk; carry_t = et + nt; }
@@ -294,8 +303,11 @@ __global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
 	if (tid == 0) {
 		a.pack_kbase[a.n_packs] = carry_k;
 		a.pack_tbase[a.n_packs] = carry_t;
-		a.status[1] = carry_t;
-		if (a.n_rec != kExpandUnknownRecs && carry_k != a.n_rec) atomicOr(a.status, kErrRecCount);
+		bool bad = walk_failed;
+		if (a.n_rec != kExpandUnknownRecs && carry_k != a.n_rec) { atomicOr(a.status, kErrRecCount); bad = true; }
+		if ((uint64_t)carry_t > a.tile_pack_cap) bad = true;
+		a.status[1] = bad ? 0u : carry_t;
+		if (bad && a.flags) { atomicOr(&a.flags[0], kExpandAbortFlag); atomicOr(&a.flags[1], kExpandAbortFlag); }
 	}
 }
 

@@ -41,6 +41,8 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint32_t leaf_group_sum[kMaxLeaves / 1024];   // emitted records per group of 1024 leaves
 };
 
+static_assert(sizeof(ZeroBlock) % 4 == 0, "zeroed word by word");
+
 struct Slot {
 	cudaStream_t stream = nullptr;
 	// records
@@ -158,6 +160,15 @@ int zero_async(kmcb200_ctx* ctx, void* ptr, size_t bytes, cudaStream_t st)
 	return 0;
 }
 
+// start of a bin: the slot's ZeroBlock, and (when given) the LUT and the 8 result words, in ONE launch
+__global__ void bin_init_kernel(uint32_t* zero_block, uint32_t zero_words, uint32_t* lut, size_t lut_words, uint32_t* result)
+{
+	const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	for (size_t i = i0; i < zero_words; i += stride) zero_block[i] = 0u;
+	if (lut) for (size_t i = i0; i < lut_words; i += stride) lut[i] = 0u;
+	if (result && i0 < 16) result[i0] = 0u;
+}
+
 uint32_t byte_log(uint64_t x) { return x < (1u << 8) ? 1 : x < (1u << 16) ? 2 : x < (1u << 24) ? 3 : 4; }   // defs.h:121
 
 template <typename T>
@@ -173,17 +184,21 @@ int ensure(kmcb200_ctx* ctx, T*& p, size_t& cap, size_t need_elems, bool zero = 
 	return 0;
 }
 
-uint32_t next_epoch(kmcb200_ctx* ctx)
+// `count` consecutive epochs for the look-back descriptors of the next launches
+int next_epoch(kmcb200_ctx* ctx, uint32_t* out, uint32_t count = 1)
 {
-	if (ctx->epoch >= kEpochLimit) {           // wrap: forget every descriptor ever written
+	if (ctx->epoch + count >= kEpochLimit) {   // wrap: forget every descriptor ever written - but only once nothing is spinning on them any more
+		CU(cudaDeviceSynchronize());
 		for (auto& s : ctx->slots) {
-			if (s.desc) cudaMemset(s.desc, 0, s.desc_cap * sizeof(uint64_t));
-			if (s.cdesc) cudaMemset(s.cdesc, 0, s.cdesc_cap * sizeof(uint64_t));
+			if (s.desc) CU(cudaMemset(s.desc, 0, s.desc_cap * sizeof(uint64_t)));
+			if (s.cdesc) CU(cudaMemset(s.cdesc, 0, s.cdesc_cap * sizeof(uint64_t)));
 		}
-		cudaDeviceSynchronize();
+		CU(cudaDeviceSynchronize());
 		ctx->epoch = 1;
 	}
-	return ctx->epoch++;
+	*out = ctx->epoch;
+	ctx->epoch += count;
+	return 0;
 }
 
 // --------------------------------------------------------------------------------------------- per-WORDS launchers
@@ -191,7 +206,8 @@ template <int WORDS>
 int setup_kernels(kmcb200_ctx* ctx)
 {
 	CU(cudaFuncSetAttribute(radix_pass_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortSmem<WORDS>::kBytes));
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_radix, radix_pass_kernel<WORDS>, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes));
+	CU(cudaFuncSetAttribute(lsd_sort_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortSmem<WORDS>::kBytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_radix, lsd_sort_kernel<WORDS>, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_expand, expand_kernel<WORDS>, ExpandCfg<WORDS>::kThreads, 0));
 	const size_t cs = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	CU(cudaFuncSetAttribute(count_emit_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
@@ -275,34 +291,24 @@ int launch_cell_scan(kmcb200_ctx* ctx, Slot& s, const uint32_t* n_items, uint32_
 	return 0;
 }
 
-// key_bytes 8-bit LSD passes from `in` (ping-pong with `out`); run_flag != nullptr: every pass returns at once unless the flag is raised
+// All key_bytes 8-bit LSD passes from `in` (ping-pong with `out`) in ONE cooperative launch (radix_sort.cuh).  run_flag / run_need:
+// the launch returns at once unless (*run_flag & 3) == run_need.  reset_lut != nullptr: the fallback of the leaf-count path first
+// forgets what the leaves added to the LUT and the statistics.
 template <int WORDS>
-int launch_lsd_passes(kmcb200_ctx* ctx, Slot& s, void* in, void* out, uint64_t n, uint32_t key_bytes, const uint32_t* run_flag, bool timed, int& iv, cudaStream_t st)
+int launch_lsd_sort(kmcb200_ctx* ctx, Slot& s, void* in, void* out, uint64_t n, uint32_t key_bytes, const uint32_t* run_flag, uint32_t run_need,
+	uint64_t* reset_lut, uint64_t* reset_result, cudaStream_t st)
 {
 	constexpr int TILE = SortSmem<WORDS>::kTile;
-	const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
-	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix));
-	{          // the histogram of the first digit (hist[0] is zero: the ZeroBlock is cleared once per bin / sort)
-		const uint32_t hgrid = (uint32_t)std::min<uint64_t>((n + 511) / 512, (uint64_t)ctx->sm_count * 4);
-		digit_histogram_kernel<WORDS><<<hgrid, 512, 0, st>>>(in, n, 0, s.zero->hist[0], run_flag);
-		ctx->launches++;
-	}
-	for (uint32_t pass = 0; pass < key_bytes; ++pass) {
-		SortPass p;
-		p.in = in; p.out = out; p.n = n; p.n_tiles = n_tiles; p.byte = pass;
-		p.next_byte = pass + 1 < key_bytes ? (int32_t)(pass + 1) : -1;
-		p.hist = s.zero->hist[pass];
-		p.hist_next = s.zero->hist[pass + 1];
-		p.desc = s.desc;
-		p.epoch = next_epoch(ctx);
-		p.tile_counter = &s.zero->counters[pass];
-		p.run_flag = run_flag;
-		radix_pass_kernel<WORDS><<<grid, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes, st>>>(p);
-		ctx->launches++;
-		if (timed) { s.pass_names[iv] = "radix_pass"; CU(cudaEventRecord(s.ev_pass[++iv], st)); }
-		std::swap(in, out);
-	}
-	CU(cudaGetLastError());
+	LsdSortArgs a{};
+	a.a = in; a.b = out; a.n = n; a.n_tiles = (uint32_t)((n + TILE - 1) / TILE); a.key_bytes = key_bytes;
+	a.hist = &s.zero->hist[0][0]; a.desc = s.desc; a.tile_counters = s.zero->counters;
+	if (int rc = next_epoch(ctx, &a.epoch0, key_bytes)) return rc;
+	a.run_flag = run_flag; a.run_need = run_need;
+	a.reset_lut = reset_lut; a.reset_lut_entries = ctx->lut_entries; a.reset_result = reset_result;
+	const uint32_t grid = std::max(1u, std::min<uint32_t>(a.n_tiles, (uint32_t)(ctx->sm_count * ctx->occ_radix)));
+	void* params[] = {&a};
+	CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lsd_sort_kernel<WORDS>), dim3(grid), dim3(SortCfg<WORDS>::kThreads), params, SortSmem<WORDS>::kBytes, st));
+	ctx->launches++;
 	return 0;
 }
 
@@ -418,9 +424,10 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		s.n_passes_run = iv;
 		return 0;
 	}
-	// 8-bit LSD passes: the whole sort when the hybrid path is off, otherwise its fallback (they return at once unless flagged)
-	if (int rc = launch_lsd_passes<WORDS>(ctx, s, lsd_in, lsd_out, n, key_bytes, lsd_flag, !msd, iv, st)) return rc;
-	if (msd) { s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st)); }
+	// 8-bit LSD passes (one cooperative launch): the whole sort when the hybrid path is off (unless the bin is malformed: flags[1]),
+	// otherwise its fallback (returns at once unless flagged)
+	if (int rc = launch_lsd_sort<WORDS>(ctx, s, lsd_in, lsd_out, n, key_bytes, msd ? lsd_flag : &s.zero->msd_flags[1], msd ? kMsdFlagFallback : 0u, nullptr, nullptr, st)) return rc;
+	s.pass_names[iv] = msd ? "lsd_fallback(all passes)" : "lsd_sort(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 	CU(cudaGetLastError());
 	s.n_passes_run = iv;
 	return 0;
@@ -428,7 +435,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 
 template <int WORDS>
 int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
-	uint64_t* d_lut, uint64_t* d_result, const uint32_t* run_flag, cudaStream_t st)
+	uint64_t* d_lut, uint64_t* d_result, const uint32_t* run_flag, uint32_t run_need, cudaStream_t st)
 {
 	constexpr int TILE = count_tile<WORDS>();
 	const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
@@ -438,8 +445,9 @@ int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint
 	a.cutoff_min = ctx->prm.cutoff_min; a.cutoff_max = ctx->prm.cutoff_max; a.counter_max = ctx->prm.counter_max;
 	a.counter_bytes = ctx->counter_bytes; a.suffix_bytes = ctx->suffix_bytes;
 	a.out = d_out; a.out_capacity = out_capacity; a.lut = d_lut; a.result = d_result;
-	a.desc = s.cdesc; a.epoch = next_epoch(ctx); a.tile_counter = &s.zero->counters[kMaxPasses];
-	a.run_flag = run_flag;
+	a.desc = s.cdesc; a.tile_counter = &s.zero->counters[kMaxPasses];
+	if (int rc = next_epoch(ctx, &a.epoch)) return rc;
+	a.run_flag = run_flag; a.run_need = run_need;
 	const size_t smem = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	count_emit_kernel<WORDS><<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 6), CountCfg<WORDS>::kThreads, smem, st>>>(a);
 	ctx->launches++;
@@ -512,7 +520,8 @@ int upload_packs(kmcb200_ctx* ctx, Slot& s, uint64_t size, const uint64_t* pack_
 }
 
 int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec,
-	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st, const ExpandMode& em = ExpandMode(), bool packs_uploaded = false)
+	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st, const ExpandMode& em = ExpandMode(), bool packs_uploaded = false,
+	uint64_t* zero_lut = nullptr, uint64_t* zero_result = nullptr)
 {
 	if (size >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin of %llu bytes: bins of 4 GiB or more are not supported", (unsigned long long)size);
 	const uint32_t k = ctx->prm.kmer_len;
@@ -531,7 +540,8 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.both_strands = ctx->prm.both_strands; a.n_rec = n_rec;
 	a.tile = ctx->words == 1 ? ExpandCfg<1>::kTile : ExpandCfg<2>::kTile;
 	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
-	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.status = s.zero->status;
+	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.tile_pack_cap = n_bound / kExpandMinTile + np + 2;
+	a.status = s.zero->status; a.flags = s.zero->msd_flags;
 	a.recs = d_recs;
 	a.mode = em.mode; a.fshift = em.fshift; a.fprefix = em.fprefix; a.fmask = em.fmask; a.hist12 = em.hist12; a.out_counter = em.out_counter;
 	if (em.mode == kExpandAll) {
@@ -541,39 +551,51 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.top_shift = std::max(2u * k, 8u) - 8u;
 	s.last_n_packs = np;
 
-	if (int rc = zero_async(ctx, s.zero, sizeof(ZeroBlock), st)) return rc;
+	bin_init_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint32_t*>(s.zero), (uint32_t)(sizeof(ZeroBlock) / 4), reinterpret_cast<uint32_t*>(zero_lut),
+		(size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(zero_result));
 	walk_packs_parallel_kernel<<<np, kWalkSegs, kWalkChunk + 32, st>>>(a, s.pack_done);
-	walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a, s.pack_done);
-	ctx->launches++;
-	scan_packs_kernel<<<1, 1024, 0, st>>>(a);
 	ctx->launches += 2;
+	// a pack of more than 64 KiB (not a collector flush: a caller-made pack, or the whole bin as one pack) is left to the exact warp-per-pack walker
+	bool big_pack = !(n_packs && pack_bytes) && size > (uint64_t)kWalkChunk;
+	if (n_packs && pack_bytes) for (uint32_t i = 0; i < n_packs && !big_pack; ++i) big_pack = pack_bytes[i] > (uint64_t)kWalkChunk;
+	if (big_pack) {
+		walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a, s.pack_done);
+		ctx->launches++;
+	}
+	scan_packs_kernel<<<1, 1024, 0, st>>>(a);
+	ctx->launches++;
 	CU(cudaGetLastError());
 	return DISPATCH_WORDS(ctx, launch_expand, ctx, a, st);
 }
 
+// outputs_zeroed: the bin's init kernel has already cleared the LUT, the result words and the ZeroBlock (run_bin);
+// guarded: skip when the bin was found malformed (flags[1], set by scan_packs_kernel)
 int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
-	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st)
+	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool outputs_zeroed = false, bool guarded = false)
 {
-	if (int rc = zero_async(ctx, d_lut, ctx->lut_entries * 8, st)) return rc;
-	if (int rc = zero_async(ctx, d_result, 8 * sizeof(uint64_t), st)) return rc;
-	if (int rc = zero_async(ctx, &s.zero->counters[kMaxPasses], sizeof(uint32_t), st)) return rc;
+	if (!outputs_zeroed) {
+		bin_init_kernel<<<64, 256, 0, st>>>(&s.zero->counters[kMaxPasses], 1u, reinterpret_cast<uint32_t*>(d_lut), (size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(d_result));
+		ctx->launches++;
+		CU(cudaGetLastError());
+	}
 	if (n == 0) return 0;
-	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, nullptr, st);
+	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, guarded ? &s.zero->msd_flags[1] : nullptr, 0u, st);
 }
 
 // the 8 result words -> pinned host memory, written by the GPU itself (zero-copy): the host-buffer path then needs no copy-engine
 // operation that WAITS for the kernels - such a pending wait can hold up the copies of other bins queued behind it on the engine
-__global__ void mirror_result_kernel(const uint64_t* result, volatile uint64_t* host_result)
+__global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uint32_t* status, const uint32_t* msd_flags, volatile uint64_t* host_result)
 {
-	if (threadIdx.x < 8) host_result[threadIdx.x] = result[threadIdx.x];
-	__threadfence_system();
-}
-
-__global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uint32_t* status, const uint32_t* msd_flags = nullptr)
-{
-	result[3] = n_rec;              // n_total = n_rec (kb_sorter.h:1166)
-	result[6] = status ? status[0] : 0;
-	result[7] = msd_flags ? msd_flags[0] : 0;       // 1: the hybrid MSD / leaf-count path gave up and the LSD fallback produced the result
+	if (threadIdx.x == 0) {
+		result[3] = n_rec;              // n_total = n_rec (kb_sorter.h:1166)
+		result[6] = status ? status[0] : 0;
+		result[7] = msd_flags ? (msd_flags[0] & 1u) : 0;       // 1: the hybrid MSD / leaf-count path gave up and the LSD fallback produced the result
+	}
+	__syncwarp();
+	if (host_result) {
+		if (threadIdx.x < 8) host_result[threadIdx.x] = result[threadIdx.x];
+		__threadfence_system();
+	}
 }
 
 template <int WORDS, int SLOT_BITS>
@@ -606,7 +628,7 @@ template <int WORDS> int setup_leaves_w(kmcb200_ctx* ctx) { return DISPATCH_SLOT
 // stand behind as the device-flagged fallback (they return at once unless a leaf could not be counted).
 template <int WORDS>
 int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np_eff, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st,
-	bool from_blocks = false, uint32_t block_bits = 0, uint32_t block_prefix = 0)
+	bool from_blocks = false, uint32_t block_bits = 0, uint32_t block_prefix = 0, bool outputs_zeroed = false)
 {
 	// block_bits > 0: the records are one key block of an oversized bin (all share their top block_bits bits = block_prefix):
 	// the sort starts below those bits, and nobody has counted the first digit yet
@@ -617,13 +639,15 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 		CU(cudaEventRecord(s.ev_sort, st));
 		s.ran_sort = true;
 		const void* sorted = in_b ? s.recs_b : s.recs_a;
-		return stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st);
+		return stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st, outputs_zeroed, true);
 	}
 	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
 	const size_t pad = (size_t)((ob + 7) / 8) * 8;
 	if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * pad + 64)) return rc;
-	if (int rc = zero_async(ctx, d_lut, ctx->lut_entries * 8, st)) return rc;
-	if (int rc = zero_async(ctx, d_result, 8 * sizeof(uint64_t), st)) return rc;
+	if (!outputs_zeroed) {
+		bin_init_kernel<<<64, 256, 0, st>>>(nullptr, 0u, reinterpret_cast<uint32_t*>(d_lut), (size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(d_result));
+		ctx->launches++;
+	}
 	uint32_t* flags = s.zero->msd_flags;
 	LeafArgs la{};
 	la.recs = plan.recs; la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
@@ -638,22 +662,20 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	ctx->launches += 2;
 	int iv = s.n_passes_run;
 	s.pass_names[iv] = "leaf_count"; CU(cudaEventRecord(s.ev_pass[++iv], st));
-	// fallback (returns at once unless a leaf could not be counted): LSD passes from the level-1 output, then the classic count
-	if (int rc = launch_lsd_passes<WORDS>(ctx, s, s.recs_b, s.recs_a, n_rec, ctx->key_bytes, flags, false, iv, st)) return rc;
-	leaf_reset_kernel<<<64, 256, 0, st>>>(d_lut, ctx->lut_entries, d_result, flags);
-	ctx->launches++;
+	// fallback (two launches that return at once unless a leaf could not be counted): all LSD passes from the level-1 output in one
+	// cooperative kernel (which first forgets what the leaves added to the LUT / statistics), then the classic count
+	if (int rc = launch_lsd_sort<WORDS>(ctx, s, s.recs_b, s.recs_a, n_rec, ctx->key_bytes, flags, kMsdFlagFallback, d_lut, d_result, st)) return rc;
 	s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 	s.n_passes_run = iv;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true;
 	const void* sorted = (ctx->key_bytes % 2 == 0) ? s.recs_b : s.recs_a;
-	if (int rc = zero_async(ctx, &s.zero->counters[kMaxPasses], sizeof(uint32_t), st)) return rc;
-	return launch_count<WORDS>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, st);
+	return launch_count<WORDS>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, kMsdFlagFallback, st);
 }
 
 // Expand -> Sort -> Compact on device buffers; records live in the slot workspace
 int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
-	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool packs_uploaded = false)
+	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool packs_uploaded = false, uint64_t* host_result = nullptr)
 {
 	const size_t rec_bytes = (size_t)ctx->words * 8;
 	s.ran_expand = s.ran_sort = s.ran_count = false;
@@ -661,27 +683,28 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	if (n_rec == 0 || size == 0) {
 		if (n_rec != 0 || size != 0) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin with size=%llu but n_rec=%llu", (unsigned long long)size, (unsigned long long)n_rec);
 		if (int rc = stage_count(ctx, s, nullptr, 0, d_out, out_capacity, d_lut, d_result, st)) return rc;
+		if (host_result) { finish_result_kernel<<<1, 32, 0, st>>>(d_result, 0, nullptr, nullptr, host_result); ctx->launches++; }
 		CU(cudaEventRecord(s.ev_expand, st)); CU(cudaEventRecord(s.ev_sort, st)); CU(cudaEventRecord(s.ev_count, st));
 		s.n_passes_run = 0;
 		return 0;
 	}
 	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, n_rec * rec_bytes)) return rc;
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n_rec * rec_bytes)) return rc;
-	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st, ExpandMode(), packs_uploaded)) return rc;
+	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st, ExpandMode(), packs_uploaded, d_lut, d_result)) return rc;
 	CU(cudaEventRecord(s.ev_expand, st));
 	s.ran_expand = true;
 	bool in_b = false;
 	const uint32_t np_eff = (n_packs && pack_bytes) ? n_packs : 1u;
 	if (ctx->use_leaf) {
-		if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, n_rec, np_eff, d_out, out_capacity, d_lut, d_result, st)) return rc;
+		if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, n_rec, np_eff, d_out, out_capacity, d_lut, d_result, st, false, 0u, 0u, true)) return rc;
 	} else {
 		if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b)) return rc;
 		CU(cudaEventRecord(s.ev_sort, st));
 		s.ran_sort = true;
 		const void* sorted = in_b ? s.recs_b : s.recs_a;
-		if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st)) return rc;
+		if (int rc = stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st, true, true)) return rc;
 	}
-	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status, s.zero->msd_flags);
+	finish_result_kernel<<<1, 32, 0, st>>>(d_result, n_rec, s.zero->status, s.zero->msd_flags, host_result);
 	ctx->launches++;
 	CU(cudaEventRecord(s.ev_count, st));
 	s.ran_count = true;
@@ -942,9 +965,7 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	if (with_packs) if (int rc = upload_packs(ctx, s, size, pack_bytes, n_packs, st)) return rc;      // on the copy stream, next to the bin
 	CU(cudaEventRecord(s.ev_h2d, st));
 	CU(cudaStreamWaitEvent(ctx->compute, s.ev_h2d, 0));
-	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute, with_packs)) return rc;
-	mirror_result_kernel<<<1, 32, 0, ctx->compute>>>(s.d_result, s.h_result_dev);
-	ctx->launches++;
+	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute, with_packs, s.h_result_dev)) return rc;
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(s.ev_result, ctx->compute));
 	s.busy = true;
@@ -1037,7 +1058,7 @@ int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkm
 	if (int rc = stage_expand(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_recs, st)) return rc;
 	if (d_result) {
 		if (int rc = zero_async(ctx, d_result, 64, st)) return rc;
-		finish_result_kernel<<<1, 1, 0, st>>>(d_result, n_rec, s.zero->status);
+		finish_result_kernel<<<1, 32, 0, st>>>(d_result, n_rec, s.zero->status, nullptr, nullptr);
 		ctx->launches++;
 	}
 	CU(cudaEventRecord(s.ev_expand, st));
@@ -1072,7 +1093,7 @@ int kmcb200_dev_count(kmcb200_ctx* ctx, uint32_t slot, const void* d_sorted, uin
 	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
 	CU(cudaEventRecord(s.ev_sort, st));
 	if (int rc = stage_count(ctx, s, d_sorted, n, d_out, out_capacity, d_lut, d_result, st)) return rc;
-	finish_result_kernel<<<1, 1, 0, st>>>(d_result, n, nullptr);
+	finish_result_kernel<<<1, 32, 0, st>>>(d_result, n, nullptr, nullptr, nullptr);
 	ctx->launches++;
 	CU(cudaEventRecord(s.ev_count, st));
 	s.ran_count = true; s.ran_expand = false; s.ran_sort = false;
@@ -1107,70 +1128,6 @@ int kmcb200_stage_names(kmcb200_ctx* ctx, uint32_t slot, char* buf, uint32_t cap
 	for (int p = 0; p < s.n_passes_run; ++p) { if (p) out += ","; out += s.pass_names[p] ? s.pass_names[p] : "?"; }
 	snprintf(buf, capacity, "%s", out.c_str());
 	return s.n_passes_run;
-}
-
-// ---- synthetic bins (host only; mirrors the byte format of CKmerBinCollector::PutExtendedKmer, kb_collector.cpp:34-90)
-static inline uint64_t splitmix64(uint64_t& x)
-{
-	uint64_t z = (x += 0x9E3779B97F4A7C15ull);
-	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-	return z ^ (z >> 31);
-}
-
-int kmcb200_synth_bin(uint64_t seed, uint32_t k, uint64_t n_rec, uint64_t genome_len, double mean_extra, uint32_t err_ppm,
-	uint8_t* data, uint64_t data_capacity, uint64_t* size, uint64_t* pack_bytes, uint32_t pack_capacity, uint32_t* n_packs, uint64_t* n_super_kmers)
-{
-	if (k < 1 || k > 256 || !size || !n_packs) return KMCB200_ERR_INVALID;
-	if (genome_len < (uint64_t)k + 256) genome_len = (uint64_t)k + 256;
-	uint64_t rs = seed * 0x2545F4914F6CDD1Dull + 0x1234567;
-	std::vector<uint8_t> genome(genome_len);
-	for (uint64_t i = 0; i < genome_len; i += 32) {
-		uint64_t r = splitmix64(rs);
-		for (uint64_t j = i; j < std::min(genome_len, i + 32); ++j) { genome[j] = r & 3; r >>= 2; }
-	}
-	const double pgeo = 1.0 / (mean_extra + 1.0);
-	const double log1mp = std::log(1.0 - std::min(pgeo, 0.999999));
-	const uint64_t err_thr = (uint64_t)((double)err_ppm * 1e-6 * 18446744073709551615.0);
-	uint64_t pos_out = 0, made = 0, n_sk = 0;
-	uint32_t np = 0;
-	uint64_t pack_fill = 0;
-	uint8_t symbuf[256 + 256 + 8];
-	while (made < n_rec) {
-		double u = (double)(splitmix64(rs) >> 11) * (1.0 / 9007199254740992.0);
-		uint64_t a = pgeo >= 0.999999 ? 0 : (uint64_t)(std::log(1.0 - u) / log1mp);
-		if (a > 255) a = 255;
-		if (a + 1 > n_rec - made) a = n_rec - made - 1;
-		const uint32_t n = k + (uint32_t)a;
-		const uint64_t p = splitmix64(rs) % (genome_len - n + 1);
-		const bool rc = splitmix64(rs) & 1;
-		for (uint32_t i = 0; i < n; ++i) {
-			uint8_t s = rc ? (uint8_t)(3 - genome[p + n - 1 - i]) : genome[p + i];
-			if (err_thr && splitmix64(rs) < err_thr) s = (uint8_t)((s + 1 + splitmix64(rs) % 3) & 3);
-			symbuf[i] = s;
-		}
-		const uint32_t bytes = 1 + (n + 3) / 4;
-		if (pack_fill + bytes > (1u << 16)) {               // collector flush (kb_collector.cpp:44-55)
-			if (pack_bytes && np < pack_capacity) pack_bytes[np] = pack_fill;
-			++np;
-			pack_fill = 0;
-		}
-		if (data) {
-			if (pos_out + bytes > data_capacity) return KMCB200_ERR_CAPACITY;
-			data[pos_out] = (uint8_t)a;
-			for (uint32_t i = 0; i < (n + 3) / 4; ++i) {
-				uint8_t b = 0;
-				for (uint32_t j = 0; j < 4; ++j) { const uint32_t q = 4 * i + j; b = (uint8_t)((b << 2) | (q < n ? symbuf[q] : 0)); }
-				data[pos_out + 1 + i] = b;
-			}
-		}
-		pos_out += bytes; pack_fill += bytes; made += a + 1; ++n_sk;
-	}
-	if (pack_fill) { if (pack_bytes && np < pack_capacity) pack_bytes[np] = pack_fill; ++np; }
-	*size = pos_out; *n_packs = np;
-	if (n_super_kmers) *n_super_kmers = n_sk;
-	if (pack_bytes && np > pack_capacity) return KMCB200_ERR_CAPACITY;
-	return 0;
 }
 
 }  // extern "C"

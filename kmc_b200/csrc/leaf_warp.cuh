@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 	static_assert(NW <= 32 && NW >= 4, "one bitmap word per lane");
 	extern __shared__ __align__(16) uint8_t lw_dsm[];
 	SM& S = reinterpret_cast<SM*>(lw_dsm)[threadIdx.x >> 5];
-	if (*a.flags & kMsdFlagFallback) return;
+	if (*a.flags & kMsdFlagStop) return;
 	const uint32_t lane = threadIdx.x & 31u, lt = lanemask_lt();
 	const uint32_t ROUND = (uint32_t)SLOTS * a.round_pct / 100u;          // a round that overflows a group is split on the next bit: optimism costs one wasted round
 	const R* __restrict__ recs = reinterpret_cast<const R*>(a.recs);
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_em
 {
 	__shared__ uint32_t s_w[32];
 	__shared__ unsigned long long s_base;
-	if (*flags & kMsdFlagFallback) return;
+	if (*flags & kMsdFlagStop) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = blockIdx.x, n_groups = gridDim.x;
 	if (warp == 0) {
 		unsigned long long b = 0, t = 0;
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_em
 __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, const uint64_t* start, const uint32_t* leaf_emit, const uint64_t* leaf_off,
 	uint32_t n_leaves, uint32_t ob, uint8_t* out, const uint64_t* result, const uint32_t* flags)
 {
-	if (*flags & kMsdFlagFallback) return;
+	if (*flags & kMsdFlagStop) return;
 	if (result[5]) return;                        // capacity error: nothing is written
 	const uint32_t leaf = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
 	if (leaf >= n_leaves) return;
@@ -531,13 +531,14 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, co
 	const uint8_t* src = tmp + start[leaf] * pad;
 	uint8_t* dst = out + leaf_off[leaf] * ob;
 	const uint32_t magic = 0xFFFFFFFFu / ob + 1;          // p / ob == umulhi(p, magic) for p < 2^16 ... checked: larger leaves take the division
+	const bool use_magic = nbytes < 65536u && ob > 1;     // (ob == 1: magic wraps to 0, and p / 1 needs no trick)
 	// (4 independent byte loads in flight per lane: the loop is bound by the latency of its loads)
 	for (uint32_t p0 = lane; p0 < nbytes; p0 += 128) {
 		uint8_t v[4];
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			const uint32_t p = p0 + 32 * i;
-			const uint32_t r = nbytes < 65536u ? __umulhi(p, magic) : p / ob;
+			const uint32_t r = use_magic ? __umulhi(p, magic) : p / ob;
 			v[i] = p < nbytes ? __ldg(src + (size_t)r * pad + (p - r * ob)) : (uint8_t)0;
 		}
 #pragma unroll
@@ -546,14 +547,6 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, co
 			if (p < nbytes) dst[p] = v[i];
 		}
 	}
-}
-
-// when the hybrid path gave up after the leaves had already touched lut / result: start over for the fallback
-__global__ void leaf_reset_kernel(uint64_t* lut, uint64_t lut_entries, uint64_t* result, const uint32_t* flags)
-{
-	if (!(*flags & kMsdFlagFallback)) return;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < lut_entries; i += (uint64_t)gridDim.x * blockDim.x) lut[i] = 0;
-	if (blockIdx.x == 0 && threadIdx.x < 6) result[threadIdx.x] = 0;
 }
 
 }  // namespace kmcb

@@ -22,7 +22,9 @@
 
 namespace kmcb {
 
-constexpr uint32_t kMsdFlagFallback = 1;      // flags[0]: leaves too large -> LSD passes take over
+constexpr uint32_t kMsdFlagFallback = 1;      // flags[0] bit 0: leaves too large -> the LSD passes take over
+constexpr uint32_t kMsdFlagAbort = 2;         // flags[0] and flags[1] bit 1: the bin is malformed (expand.cuh): nothing downstream may run
+constexpr uint32_t kMsdFlagStop = kMsdFlagFallback | kMsdFlagAbort;
 
 // bits [shift, shift+nbits) of a record (nbits <= 8... 32), record = little-endian multi-word integer
 template <int WORDS>
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 	uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::oMbar);
 	uint64_t* empty = full + STAGES;
 
-	if (*p.flags & kMsdFlagFallback) return;
+	if (*p.flags & kMsdFlagStop) return;
 	const uint32_t tid = threadIdx.x;
 	const R* __restrict__ gin = reinterpret_cast<const R*>(p.in);
 	R* __restrict__ gout = reinterpret_cast<R*>(p.out);
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(512) msd_count_kernel(const MsdCountArgs p)
 {
 	using R = Rec<WORDS>;
 	__shared__ uint32_t sh[2][NDMAX];
-	if (*p.flags & kMsdFlagFallback) return;
+	if (*p.flags & kMsdFlagStop) return;
 	const R* __restrict__ g = reinterpret_cast<const R*>(p.in);
 	const uint32_t n_items = *p.items.n_items;
 	const uint32_t mask = p.nd - 1;
@@ -353,7 +355,7 @@ __device__ __forceinline__ void cell_load16(const uint16_t* cells, uint64_t c, u
 __global__ void __launch_bounds__(256) cell_reduce_kernel(const uint16_t* cells, const uint32_t* n_items, uint32_t nd, uint32_t* block_sums, const uint32_t* flags)
 {
 	__shared__ uint32_t s_w[8];
-	if (*flags & kMsdFlagFallback) return;
+	if (*flags & kMsdFlagStop) return;
 	const uint64_t n_cells = (uint64_t)nd * *n_items;
 	const uint64_t c0 = (uint64_t)blockIdx.x * kCellChunk;
 	if (c0 >= n_cells) return;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(1024) cell_scan_sums_kernel(uint32_t* block_su
 {
 	__shared__ uint32_t s_w[32];
 	__shared__ uint32_t carry;
-	if (*flags & kMsdFlagFallback) return;
+	if (*flags & kMsdFlagStop) return;
 	const uint64_t n_cells = (uint64_t)nd * *n_items;
 	const uint32_t nb = (uint32_t)((n_cells + kCellChunk - 1) / kCellChunk);
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(256) cell_scan_kernel(const uint16_t* cells, c
 	static_assert(kCellChunk == 256 * 16, "16 consecutive cells per thread");
 	__shared__ uint32_t s_w[8];
 	__shared__ uint32_t s_t[kCellChunk + kCellChunk / 16];       // the chunk's prefixes, padded (index i lives at i + i / 16): transposed for coalesced stores
-	if (*flags & kMsdFlagFallback) return;
+	if (*flags & kMsdFlagStop) return;
 	const uint64_t n_cells = (uint64_t)nd * *n_items;
 	const uint64_t c0 = (uint64_t)blockIdx.x * kCellChunk;
 	if (c0 >= n_cells) return;
@@ -461,7 +463,7 @@ struct MsdBoundsArgs {
 // boundaries + oversize check only (any number of CTAs): used when no item table is needed
 __global__ void __launch_bounds__(256) msd_bounds_flat_kernel(const MsdBoundsArgs a)
 {
-	if (*a.flags & kMsdFlagFallback) return;
+	if (*a.flags & kMsdFlagStop) return;
 	const uint32_t M = a.S * a.nd;
 	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
 	if (m > M) return;
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(1024) msd_bounds_kernel(const MsdBoundsArgs a)
 	__shared__ uint32_t s_i[32];
 	__shared__ uint32_t carry_i;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (*a.flags & kMsdFlagFallback) return;
+	if (*a.flags & kMsdFlagStop) return;
 	const uint32_t M = a.S * a.nd;
 	// pass 1: boundaries.  Buckets of an empty segment (no items, no cells) collapse onto the segment start.
 	for (uint32_t m = tid; m <= M; m += 1024) {
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(MsdLocalCfg<WORDS>::kThreads) msd_local_sort_k
 	__shared__ uint64_t warp_tot[8];
 	__shared__ uint32_t s_bucket;
 
-	if (*p.flags & kMsdFlagFallback) return;
+	if (*p.flags & kMsdFlagStop) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const R* __restrict__ gin = reinterpret_cast<const R*>(p.in);
 	R* __restrict__ gout = reinterpret_cast<R*>(p.out);

@@ -18,6 +18,7 @@
 //     depend on their order), so no pass ever re-reads the data just to count:  traffic = 2*N*W / pass.
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace kmcb {
 
@@ -33,8 +34,11 @@ struct SortPass {
 	uint64_t* desc;          // [n_tiles][256] look-back descriptors (epoch-tagged, see common.cuh)
 	uint32_t epoch;          // unique per launch
 	uint32_t* tile_counter;  // zero-initialised
-	const uint32_t* run_flag; // nullptr: always run; else run only when (*run_flag & 1): the hybrid MSD path gave up (msd_sort.cuh)
+	const uint32_t* run_flag; // nullptr: always run; else run only when (*run_flag & kRunMask) == run_need (msd_sort.cuh: bit 0 = the hybrid
+	uint32_t run_need;        // MSD path gave up, bit 1 = the bin is malformed and nothing may run)
 };
+constexpr uint32_t kRunMask = 3u;
+__device__ __forceinline__ bool run_allowed(const uint32_t* flag, uint32_t need) { return !flag || (*flag & kRunMask) == need; }
 
 template <int WORDS> struct SortCfg;
 template <> struct SortCfg<1> { static constexpr int kThreads = 512, kKpt = 8, kMinBlocks = 2; };
@@ -86,13 +90,14 @@ __device__ __forceinline__ uint64_t block_excl_scan_256(uint64_t v, uint64_t* wa
 	return base + inc - v;
 }
 
+// One pass over all tiles by this CTA (persistent: tiles are claimed from p.tile_counter).  The mbarriers live across passes
+// (phase0 / phase1 are the caller's running parities); nhist must be zero on entry and is left zero on exit.
 template <int WORDS>
-__global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMinBlocks) radix_pass_kernel(const SortPass p)
+__device__ __forceinline__ void radix_pass_body(const SortPass& p, uint8_t* smem, uint32_t& phase0, uint32_t& phase1)
 {
 	using S = SortSmem<WORDS>;
 	using R = Rec<WORDS>;
 	constexpr int THREADS = S::kThreads, WARPS = S::kWarps, KPT = S::kKpt, TILE = S::kTile;
-	extern __shared__ __align__(128) uint8_t smem[];
 	uint32_t* whist = reinterpret_cast<uint32_t*>(smem + S::oWhist);
 	uint32_t* tile_excl = reinterpret_cast<uint32_t*>(smem + S::oTileExcl);
 	uint64_t* goff = reinterpret_cast<uint64_t*>(smem + S::oGoff);
@@ -101,18 +106,11 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 	uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + S::oMbar);
 	volatile uint32_t* s_tile = reinterpret_cast<volatile uint32_t*>(smem + S::oTileId);
 
-	if (p.run_flag && !(*p.run_flag & 1u)) return;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const R* __restrict__ gin = reinterpret_cast<const R*>(p.in);
 	R* __restrict__ gout = reinterpret_cast<R*>(p.out);
 	uint64_t* desc = p.desc;
 
-	if (tid < 256) nhist[tid] = 0;
-	if (tid == 0) {
-		mbar_init(&mbar[0], 1);
-		mbar_init(&mbar[1], 1);
-		fence_mbar_init();
-	}
 	// bucket bases of this pass: exclusive scan of the digit histogram (thread d <-> digit d)
 	uint64_t bucket_base = block_excl_scan_256(tid < 256 ? p.hist[tid] : 0, warp_tot, nullptr);
 
@@ -136,7 +134,7 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 	}
 	__syncthreads();
 
-	uint32_t phase0 = 0, phase1 = 0, cnt_real = 0;
+	uint32_t cnt_real = 0;
 	int cur = 0;
 	while (true) {
 		const uint32_t tile = s_tile[cur];
@@ -243,18 +241,46 @@ __global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMin
 		cur ^= 1;
 	}
 
-	if (p.next_byte >= 0 && tid < 256) {
+	if (tid < 256) {
 		const uint32_t c = nhist[tid];
-		if (c) atomicAdd(reinterpret_cast<unsigned long long*>(p.hist_next) + tid, (unsigned long long)c);
+		if (p.next_byte >= 0 && c) atomicAdd(reinterpret_cast<unsigned long long*>(p.hist_next) + tid, (unsigned long long)c);
+		nhist[tid] = 0;
 	}
+	__syncthreads();
+}
+
+template <int WORDS>
+__device__ __forceinline__ void radix_pass_init(uint8_t* smem)
+{
+	using S = SortSmem<WORDS>;
+	uint32_t* nhist = reinterpret_cast<uint32_t*>(smem + S::oNhist);
+	uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + S::oMbar);
+	if (threadIdx.x < 256) nhist[threadIdx.x] = 0;
+	if (threadIdx.x == 0) {
+		mbar_init(&mbar[0], 1);
+		mbar_init(&mbar[1], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+}
+
+// a single pass (kmcb200_dev_sort with KMCB200_SORT=lsd times its passes one by one)
+template <int WORDS>
+__global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMinBlocks) radix_pass_kernel(const SortPass p)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	if (!run_allowed(p.run_flag, p.run_need)) return;
+	radix_pass_init<WORDS>(smem);
+	uint32_t phase0 = 0, phase1 = 0;
+	radix_pass_body<WORDS>(p, smem, phase0, phase1);
 }
 
 // histogram of the first digit over N records, in front of the LSD passes (run_flag as in SortPass)
 template <int WORDS>
-__global__ void __launch_bounds__(512) digit_histogram_kernel(const void* in, uint64_t n, uint32_t byte, uint64_t* hist, const uint32_t* run_flag)
+__global__ void __launch_bounds__(512) digit_histogram_kernel(const void* in, uint64_t n, uint32_t byte, uint64_t* hist, const uint32_t* run_flag, uint32_t run_need)
 {
 	__shared__ uint32_t sh[256];
-	if (run_flag && !(*run_flag & 1u)) return;
+	if (!run_allowed(run_flag, run_need)) return;
 	const Rec<WORDS>* __restrict__ g = reinterpret_cast<const Rec<WORDS>*>(in);
 	if (threadIdx.x < 256) sh[threadIdx.x] = 0;
 	__syncthreads();
@@ -264,6 +290,70 @@ __global__ void __launch_bounds__(512) digit_histogram_kernel(const void* in, ui
 		atomicAdd(&sh[rec_byte<WORDS>(g[i], byte)], 1u);
 	__syncthreads();
 	if (threadIdx.x < 256) { uint32_t c = sh[threadIdx.x]; if (c) atomicAdd((unsigned long long*)hist + threadIdx.x, (unsigned long long)c); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// All key_bytes LSD passes in ONE cooperative launch (grid-wide barrier between the passes).  This is the whole sort of small
+// bins / KMCB200_SORT=lsd, and the device-flagged fallback of the hybrid MSD path: enqueued behind it, it returns at once unless
+// the flag says that the hybrid path gave up - one no-op launch instead of one per pass.
+struct LsdSortArgs {
+	void* a;                 // pass 0 reads a and writes b, pass 1 the other way round, ...
+	void* b;
+	uint64_t n;
+	uint32_t n_tiles;
+	uint32_t key_bytes;
+	uint64_t* hist;          // [key_bytes + 1][256], zero-initialised
+	uint64_t* desc;          // [n_tiles][256]
+	uint32_t epoch0;         // pass i uses epoch0 + i
+	uint32_t* tile_counters; // [key_bytes], zero-initialised
+	const uint32_t* run_flag;
+	uint32_t run_need;
+	// fallback of the leaf-count path: forget what the leaves have already added to the LUT / the statistics
+	uint64_t* reset_lut;     // nullptr: nothing to reset
+	uint64_t reset_lut_entries;
+	uint64_t* reset_result;  // [6]
+};
+
+template <int WORDS>
+__global__ void __launch_bounds__(SortCfg<WORDS>::kThreads, SortCfg<WORDS>::kMinBlocks) lsd_sort_kernel(const LsdSortArgs a)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	if (!run_allowed(a.run_flag, a.run_need)) return;          // (every CTA takes the same decision: nobody waits at a grid barrier)
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	using S = SortSmem<WORDS>;
+	const uint32_t tid = threadIdx.x;
+	radix_pass_init<WORDS>(smem);
+	{	// histogram of digit 0 (+ the resets)
+		uint32_t* sh = reinterpret_cast<uint32_t*>(smem + S::oWhist);
+		if (tid < 256) sh[tid] = 0;
+		__syncthreads();
+		const Rec<WORDS>* __restrict__ g = reinterpret_cast<const Rec<WORDS>*>(a.a);
+		const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+		for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < a.n; i += stride) atomicAdd(&sh[rec_byte<WORDS>(g[i], 0)], 1u);
+		__syncthreads();
+		if (tid < 256) { const uint32_t c = sh[tid]; if (c) atomicAdd(reinterpret_cast<unsigned long long*>(a.hist) + tid, (unsigned long long)c); }
+		if (a.reset_lut) {
+			for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < a.reset_lut_entries; i += stride) a.reset_lut[i] = 0;
+			if (blockIdx.x == 0 && tid < 6) a.reset_result[tid] = 0;
+		}
+		__syncthreads();
+	}
+	grid.sync();
+	uint32_t phase0 = 0, phase1 = 0;
+	for (uint32_t pass = 0; pass < a.key_bytes; ++pass) {
+		SortPass p;
+		p.in = (pass & 1u) ? a.b : a.a;
+		p.out = (pass & 1u) ? a.a : a.b;
+		p.n = a.n; p.n_tiles = a.n_tiles; p.byte = pass;
+		p.next_byte = pass + 1 < a.key_bytes ? (int32_t)(pass + 1) : -1;
+		p.hist = a.hist + 256 * pass;
+		p.hist_next = a.hist + 256 * (pass + 1);
+		p.desc = a.desc; p.epoch = a.epoch0 + pass;
+		p.tile_counter = a.tile_counters + pass;
+		p.run_flag = nullptr; p.run_need = 0;
+		radix_pass_body<WORDS>(p, smem, phase0, phase1);
+		if (pass + 1 < a.key_bytes) grid.sync();
+	}
 }
 
 }  // namespace kmcb

@@ -26,6 +26,7 @@
 #endif
 
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -93,7 +94,10 @@ int run_bins(int k, int both_strands, uint32_t cutoff_min, uint32_t cutoff_max, 
 	int64_t total = 0;
 	for (auto& s : sorted) total += s.second;
 	int64_t max_mem = MAX(total, (int64_t)16 << 20);
-	int64_t cap = (int64_t)48 << 30;                  // keep the harness inside this box's RAM
+	// keep the harness inside this box's RAM: KMCREF_ARENA_GB (bench.py sets it from MemAvailable and sweeps it - the arena size is
+	// what decides how many bins the reference works on at the same time, like kmc's -m), default 48 GB
+	int64_t cap = (int64_t)48 << 30;
+	if (const char* e = getenv("KMCREF_ARENA_GB")) { long long g = atoll(e); if (g >= 1) cap = (int64_t)g << 30; }
 	if (max_mem > cap) max_mem = MAX(cap, sorted.front().second);
 	// The arena is kept across calls (a real stage 2 allocates it once for all its bins, kmc.h:1510, so later bins run on
 	// pages that are already faulted in); the warm-up steps of bench.py play the role of the earlier bins.

@@ -8,6 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import kmc_b200
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+from kmc_testlib import fast_bin
 
 K, P = 31, 7
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 27
@@ -35,7 +37,7 @@ def run(n_rec, seed, env):
     ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(K, True, 2, 10 ** 9, 255, P), device=0, n_slots=1)
     for k_ in env:
         del os.environ[k_]
-    sk = kmc_b200.synth_bin(seed, K, n_rec)
+    sk = fast_bin(seed, K, n_rec)
     t0 = time.perf_counter()
     r = ctx.process_bin(sk)
     dt = time.perf_counter() - t0

@@ -1,3 +1,4 @@
+import os, sys
 """Development probe: time of the index + expand stage alone (kmcb200_dev_expand) for the library named by KMCB200_LIB."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -5,7 +6,7 @@ sys.path.insert(0, ROOT)
 import torch, kmc_b200
 n_rec = 1 << 26
 dev = torch.device("cuda", 0)
-hb = kmc_b200.synth_bin(1000, 31, n_rec)
+hb = fast_bin(1000, 31, n_rec)
 d_bin = torch.zeros(hb.size + 64, dtype=torch.uint8, device=dev); d_bin[:hb.size] = torch.from_numpy(hb.data).to(dev)
 d_recs = torch.zeros(n_rec, dtype=torch.int64, device=dev)
 d_res = torch.zeros(8, dtype=torch.int64, device=dev)

@@ -7,6 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import kmc_b200
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+from kmc_testlib import fast_bin
 if os.environ.get("KMCB200_LIB"):
     kmc_b200.LIB_PATH = os.path.abspath(os.environ["KMCB200_LIB"])
 
@@ -15,7 +17,7 @@ K = int(sys.argv[2]) if len(sys.argv) > 2 else 31
 P = {31: 7, 55: 7, 28: 8}.get(K, K % 4 if K % 4 else 4)
 n_rec = 1 << lg
 dev = torch.device("cuda", 0)
-bins = [kmc_b200.synth_bin(1000 + j, K, n_rec) for j in range(2)]
+bins = [fast_bin(1000 + j, K, n_rec) for j in range(2)]
 d_bins = []
 for hb in bins:
     t = torch.zeros(hb.size + 64, dtype=torch.uint8, device=dev)

@@ -1,3 +1,4 @@
+import os, sys
 """Development probe: where does the host-buffer path spend its time?"""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -6,7 +7,7 @@ import numpy as np, torch, kmc_b200
 
 n_rec = 1 << 26
 ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(31, True, 2, 10 ** 9, 255, 7), device=0, n_slots=2)
-hb = kmc_b200.synth_bin(1, 31, n_rec)
+hb = fast_bin(1, 31, n_rec)
 cap = ctx.out_capacity(n_rec) + 64
 pin_bin = torch.from_numpy(hb.data.copy()).pin_memory()
 pin_out = torch.zeros(cap, dtype=torch.uint8).pin_memory()

@@ -1,3 +1,4 @@
+import os, sys
 import torch, time, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 n = 66 * 1024 * 1024
@@ -12,7 +13,7 @@ for name, fn in [("H2D", lambda: d.copy_(h, non_blocking=True)), ("D2H", lambda:
 import kmc_b200, numpy as np
 n_rec = 1 << 26
 ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(31, True, 2, 10 ** 9, 255, 7), device=0, n_slots=3)
-hbs = [kmc_b200.synth_bin(1 + j, 31, n_rec) for j in range(2)]
+hbs = [fast_bin(1 + j, 31, n_rec) for j in range(2)]
 cap = ctx.out_capacity(n_rec) + 64
 pin_bins = [torch.from_numpy(hb.data.copy()).pin_memory() for hb in hbs]
 for nslots in (1, 2, 3):

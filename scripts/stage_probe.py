@@ -1,3 +1,4 @@
+import os, sys
 """Development probe: per-stage / per-pass CUDA-event times of one resident bin (k=31, 2^26 k-mers by default)."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,7 +10,7 @@ k = int(sys.argv[2]) if len(sys.argv) > 2 else 31
 p = {31: 7, 55: 7, 28: 4}.get(k, 7)
 ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(k, True, 2, 10 ** 9, 255, p), device=0, n_slots=1)
 seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-hb = kmc_b200.synth_bin(seed, k, n_rec)
+hb = fast_bin(seed, k, n_rec)
 cap = ctx.out_capacity(n_rec) + 64
 dev = torch.device("cuda", 0)
 d_bin = torch.zeros(hb.size + 64, dtype=torch.uint8, device=dev); d_bin[:hb.size] = torch.from_numpy(hb.data).to(dev)

@@ -180,6 +180,57 @@ def synth_bin(seed, k, n_super_kmers, genome_len=None, mean_extra=11.0, err=0.01
     return Bin(data=data, n_rec=int((a + 1).sum()), n_super_kmers=n_super_kmers, pack_bytes=pb, pack_recs=pr, k=k, extras=a, pack_first=pf)
 
 
+SYNTH_DIR = os.path.join(ROOT, "tests", "synth")
+SYNTH_SO = os.path.join(SYNTH_DIR, "libkmc_synth.so")
+_synth = None
+
+
+def _synth_lib():
+    """tests/synth/libkmc_synth.so: the C generator (test infrastructure; the product library does not contain it)."""
+    global _synth
+    if _synth is None:
+        src = os.path.join(SYNTH_DIR, "synth_bin.cpp")
+        if (not os.path.exists(SYNTH_SO)) or os.path.getmtime(SYNTH_SO) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", SYNTH_DIR], stdout=subprocess.DEVNULL)
+        L = C.CDLL(SYNTH_SO)
+        L.kmcsynth_bin.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32, C.c_void_p, C.c_uint64,
+                                   C.POINTER(C.c_uint64), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        _synth = L
+    return _synth
+
+
+def fast_bin(seed, k, n_rec, genome_len=None, mean_extra=11.0, err_ppm=10000) -> Bin:
+    """A bin of exactly n_rec k-mers from the C generator (seconds for 2^28 k-mers): 30x duplicate-rich by default
+    (genome_len = n_rec / 30), all-distinct with genome_len >= n_rec."""
+    L = _synth_lib()
+    if genome_len is None:
+        genome_len = max(n_rec // 30, k + 256)
+    size, n_packs, n_sk = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
+    # one pass into a generous buffer (a k-mer costs ~1 byte at ~12 k-mers per super-k-mer); the sizing call only when that was too small
+    guess = int(n_rec * (1.0 + (1 + (k + 3) // 4) / (mean_extra + 1.0)) * 0.25 * 1.15) + (1 << 16) if mean_extra >= 1 else 0
+    data = np.empty(guess + 64, dtype=np.uint8)
+    packs = np.zeros(guess // 32768 + 64, dtype=np.uint64)
+    rc = L.kmcsynth_bin(seed, k, n_rec, genome_len, mean_extra, err_ppm, data.ctypes.data, guess, C.byref(size),
+                        packs.ctypes.data, packs.size, C.byref(n_packs), C.byref(n_sk)) if guess else -5
+    if rc == -5:
+        rc = L.kmcsynth_bin(seed, k, n_rec, genome_len, mean_extra, err_ppm, None, 0, C.byref(size), None, 0, C.byref(n_packs), C.byref(n_sk))
+        assert rc == 0, rc
+        data = np.zeros(size.value + 64, dtype=np.uint8)
+        packs = np.zeros(max(n_packs.value, 1), dtype=np.uint64)
+        rc = L.kmcsynth_bin(seed, k, n_rec, genome_len, mean_extra, err_ppm, data.ctypes.data, data.size, C.byref(size),
+                            packs.ctypes.data, packs.size, C.byref(n_packs), C.byref(n_sk))
+    assert rc == 0, rc
+    data[size.value:size.value + 64] = 0
+    pb = packs[:n_packs.value]
+    return Bin(data=data[:size.value], n_rec=n_rec, n_super_kmers=int(n_sk.value), pack_bytes=pb, pack_recs=pb, k=k)
+
+
+def to_skb(b: "Bin"):
+    """Bin -> the package's SuperKmerBin (what Stage2Context.process_bin takes)."""
+    import kmc_b200
+    return kmc_b200.SuperKmerBin(data=b.data, n_rec=b.n_rec, pack_bytes=b.pack_bytes, n_super_kmers=b.n_super_kmers, kmer_len=b.k)
+
+
 def bin_from_reads(k, reads):
     """Put whole reads (strings over ACGT) into one bin as super-k-mers of <= k+255 symbols overlapping by k-1.
     (Stage 1 would cut by minimizer, splitter.cpp:557-677; for stage 2 only the multiset of k-mers matters.)"""

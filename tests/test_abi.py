@@ -26,10 +26,16 @@ def test_library_exports_every_declared_symbol():
     assert sorted(kmc_b200.EXPORTS) == syms
 
 
-def test_synth_bin_host_only_and_oracle_walk(oracle):
+def test_product_library_holds_no_test_code():
+    """The synthetic-bin generator lives in tests/synth (the reference arm of bench.py must not map product code for it)."""
     import kmc_b200
-    from kmc_testlib import Bin
-    sk = kmc_b200.synth_bin(42, 31, 100000, genome_len=5000)
+    L = kmc_b200.load_library()
+    assert not hasattr(L, "kmcb200_synth_bin") and not hasattr(L, "kmcsynth_bin")
+
+
+def test_synth_generator_and_oracle_walk(oracle):
+    from kmc_testlib import Bin, fast_bin
+    sk = fast_bin(42, 31, 100000, genome_len=5000)
     assert sk.n_rec == 100000 and sk.pack_bytes.sum() == sk.size and np.all(sk.pack_bytes <= 1 << 16)
     b = Bin(data=sk.data, n_rec=sk.n_rec, n_super_kmers=sk.n_super_kmers, pack_bytes=sk.pack_bytes, pack_recs=sk.pack_bytes, k=31)
     assert oracle.walk(b) == (sk.n_super_kmers, sk.n_rec)
@@ -40,7 +46,7 @@ def test_synth_bin_host_only_and_oracle_walk(oracle):
         assert oracle.walk(sub)[0] > 0
         pos += int(pb)
     # deterministic
-    sk2 = kmc_b200.synth_bin(42, 31, 100000, genome_len=5000)
+    sk2 = fast_bin(42, 31, 100000, genome_len=5000)
     assert np.array_equal(sk.data, sk2.data)
 
 

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from kmc_testlib import Params, Bin, synth_bin, pack_superkmers, choose_lut_prefix_len, bin_from_reads
+from kmc_testlib import Params, Bin, synth_bin, fast_bin, pack_superkmers, choose_lut_prefix_len, bin_from_reads
 
 pytestmark = pytest.mark.gpu
 
@@ -253,10 +253,8 @@ def test_large_bin_properties_and_parity(oracle):
     import kmc_b200
     p = Params(k=31, cutoff_min=2, lut_prefix_len=7)
     ctx = _ctx(p)
-    sk = kmc_b200.synth_bin(12345, 31, 1 << 22)
-    b = Bin(data=sk.data, n_rec=sk.n_rec, n_super_kmers=sk.n_super_kmers, pack_bytes=sk.pack_bytes, pack_recs=sk.pack_bytes, k=31)
-    _check_bin(oracle, b, p, ctx)
-    sk = kmc_b200.synth_bin(999, 31, 1 << 26)
+    _check_bin(oracle, fast_bin(12345, 31, 1 << 22), p, ctx)
+    sk = fast_bin(999, 31, 1 << 26)
     r = ctx.process_bin(sk)
     assert r.n_total == 1 << 26
     n_emit = r.payload.size // ctx.out_rec_bytes
@@ -325,3 +323,145 @@ def test_leaf_count_crowded_leaf_and_heavy_kmer(oracle):
     rest = [rng.integers(0, 4, k + 40) for _ in range(3000)]
     p = Params(k=k, both_strands=False, cutoff_min=1, lut_prefix_len=7)
     _check_bin(oracle, pack_superkmers(k, crowded + heavy + rest), p)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Round 2: parity at benchmark scale, against the reference itself (oracle/_ref/libkmc_ref.so travels to the GPU box)
+def _reference_or_skip():
+    from kmc_testlib import Reference, reference_available
+    if not reference_available():
+        pytest.skip("oracle/_ref/libkmc_ref.so not built")
+    return Reference()
+
+
+def _assert_same(r, e, what=""):
+    assert r.stats == tuple(e.stats), what
+    assert np.array_equal(r.lut, e.lut), what
+    assert r.payload.tobytes() == e.payload, what
+
+
+@pytest.mark.parametrize("k,p_len", [(31, 7), (55, 7)])
+def test_benchmark_scale_bit_exact_vs_reference(k, p_len):
+    """One bin of 2^26 k-mers (BASELINE configs[1] / the benchmark's bin size): payload, LUT and statistics byte for byte
+    against the unmodified CKmerBinSorter<SIZE>::ProcessBins + RADULS (k=55: against the reference's (k,x)-mer path)."""
+    import os
+    R = _reference_or_skip()
+    p = Params(k=k, cutoff_min=2, lut_prefix_len=p_len)
+    b = fast_bin(2600 + k, k, 1 << 26)
+    ctx = _ctx(p)
+    r = ctx.process_bin(b)
+    e = R.process_bin(b, p, n_sorters=os.cpu_count() or 8)
+    _assert_same(r, e, "k=%d" % k)
+    assert r.n_total == 1 << 26
+    ctx.close()
+
+
+def test_large_second_level_bit_exact_vs_reference():
+    """A bin of the target workload's size (1.2e8 k-mers: 9-bit second partition level, 2^17 leaves) against the reference."""
+    import os
+    R = _reference_or_skip()
+    p = Params(k=31, cutoff_min=2, lut_prefix_len=7)
+    b = fast_bin(117, 31, 117_000_000)
+    ctx = _ctx(p)
+    r = ctx.process_bin(b)
+    _assert_same(r, R.process_bin(b, p, n_sorters=os.cpu_count() or 8))
+    ctx.close()
+
+
+def _golden():
+    import glob, os
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "bins_*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden(), ids=[__import__("os").path.basename(p)[5:-4] for p in _golden()])
+def test_golden_fixtures_through_gpu(path):
+    """The committed reference-generated vectors (tests/golden/make_golden.py), expected bytes straight from the fixture."""
+    from test_oracle_golden import load_golden
+    prm, b, payload, lut, stats = load_golden(path)
+    ctx = _ctx(prm)
+    r = ctx.process_bin(b)
+    assert r.stats == stats and np.array_equal(r.lut, lut) and r.payload.tobytes() == payload
+    ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["all_distinct", "coverage_2x", "coverage_2x_ci1"])
+def test_low_coverage_bins_2_24(oracle, kind):
+    """2^24 k-mers with (nearly) no duplicates / coverage 2: the rounds of the leaf tables overflow and are split, nothing or
+    half of the k-mers survive the cutoff - the opposite regime of the 30x benchmark bins."""
+    n = 1 << 24
+    if kind == "all_distinct":
+        b, p = fast_bin(51, 31, n, genome_len=4 * n, err_ppm=0), Params(k=31, cutoff_min=1, lut_prefix_len=7)
+    elif kind == "coverage_2x":
+        b, p = fast_bin(52, 31, n, genome_len=n // 2), Params(k=31, cutoff_min=2, lut_prefix_len=7)
+    else:
+        b, p = fast_bin(53, 31, n, genome_len=n // 2), Params(k=31, cutoff_min=1, lut_prefix_len=11)
+    _check_bin(oracle, b, p)
+
+
+def test_key_blocks_equal_one_shot_2_27(monkeypatch):
+    """2^27 k-mers: the oversized-bin path (key blocks of <= 2^24 k-mers, 16 MiB chunks) must give the bytes of the one-shot path."""
+    p = Params(k=31, cutoff_min=2, lut_prefix_len=7)
+    b = fast_bin(4711, 31, 1 << 27)
+    ctx = _ctx(p)
+    a = ctx.process_bin(b)
+    ctx.close()
+    monkeypatch.setenv("KMCB200_MAX_BLOCK_RECORDS", str(1 << 24))
+    monkeypatch.setenv("KMCB200_MAX_CHUNK_BYTES", str(1 << 24))
+    ctx = _ctx(p)
+    c = ctx.process_bin(b)
+    ctx.close()
+    assert a.n_total == 1 << 27 and a.stats == c.stats and np.array_equal(a.lut, c.lut) and a.payload.tobytes() == c.payload.tobytes()
+
+
+def test_wrong_n_rec_is_fatal_on_the_device(oracle):
+    """a bin that holds MORE k-mers than n_rec says (buffers are sized from n_rec) must stop on the device - no kernel
+    behind the index may touch the records - and the context must stay usable."""
+    import kmc_b200
+    p = Params(k=31, cutoff_min=1, lut_prefix_len=7)
+    ctx = _ctx(p, n_slots=2)
+    good = synth_bin(5, 31, 9000, genome_len=20000)
+    for n_true, n_claimed in [(300000, 100000), (300000, 299999), (100000, 300000), (2_000_000, 70000)]:
+        b = fast_bin(77, 31, n_true)
+        lie = kmc_b200.SuperKmerBin(data=b.data, n_rec=n_claimed, pack_bytes=b.pack_bytes, n_super_kmers=b.n_super_kmers, kmer_len=31)
+        with pytest.raises(kmc_b200.KmcB200Error) as ei:
+            ctx.process_bin(lie)
+        assert ei.value.code == kmc_b200.ERR_BIN_FORMAT
+        _check_bin(oracle, good, p, ctx)                 # neighbouring allocations were not scribbled on
+    # a pack boundary in the middle of a record, in a bin large enough for the hybrid path
+    b = fast_bin(78, 31, 400000)
+    bad = b.pack_bytes.copy()
+    bad[0] -= 3
+    bad[1] += 3
+    with pytest.raises(kmc_b200.KmcB200Error) as ei:
+        ctx.process_bin(kmc_b200.SuperKmerBin(data=b.data, n_rec=b.n_rec, pack_bytes=bad, kmer_len=31))
+    assert ei.value.code == kmc_b200.ERR_BIN_FORMAT
+    _check_bin(oracle, good, p, ctx)
+    _check_bin(oracle, b, p, ctx)
+    ctx.close()
+
+
+def test_one_byte_records(oracle):
+    """k - p = 4 with counter_max = 1 -> emitted records of ONE byte (no counter); leaves that emit many records."""
+    p = Params(k=13, cutoff_min=1, counter_max=1, lut_prefix_len=9)
+    assert p.out_rec_bytes == 1
+    _check_bin(oracle, fast_bin(13, 13, 300000, genome_len=100000), p)
+    p = Params(k=17, both_strands=False, cutoff_min=1, counter_max=1, lut_prefix_len=13)
+    _check_bin(oracle, fast_bin(17, 17, 200000, genome_len=150000), p)
+
+
+def test_lsd_fallback_is_one_cooperative_launch(oracle, monkeypatch):
+    """The device-flagged fallback (a leaf that cannot be counted on chip) through the whole-bin path: same bytes as the oracle."""
+    rng = np.random.default_rng(4)
+    k = 31
+    heavy_one = rng.integers(0, 4, k)
+    heavy = [heavy_one.copy() for _ in range(70000)]               # one k-mer 70000 times: beyond a warp-counted leaf
+    rest = [rng.integers(0, 4, k + 60) for _ in range(4000)]
+    p = Params(k=k, both_strands=False, cutoff_min=1, lut_prefix_len=7)
+    b = pack_superkmers(k, heavy + rest)
+    ctx = _ctx(p)
+    r = ctx.process_bin(_to_skb(b))
+    e = oracle.process_bin(b, p)
+    assert r.stats == e.stats and np.array_equal(r.lut, e.lut) and r.payload.tobytes() == e.payload
+    ctx.close()
+    monkeypatch.setenv("KMCB200_SORT", "lsd")                      # and the plain LSD sort (the same cooperative kernel, always on)
+    _check_bin(oracle, fast_bin(9, 31, 250000), Params(k=31, cutoff_min=2, lut_prefix_len=7))
