@@ -94,9 +94,8 @@ def gen_bin(seed, k, n_rec, pool=None):
     parts = list(pool.map(fn, pieces)) if pool is not None else [fn(p) for p in pieces]
     if len(parts) == 1:
         return parts[0]
-    pb = np.concatenate([p.pack_bytes for p in parts])
     return Bin(data=np.concatenate([p.data for p in parts]), n_rec=n_rec, n_super_kmers=sum(p.n_super_kmers for p in parts),
-               pack_bytes=pb, pack_recs=pb, k=k)
+               pack_bytes=np.concatenate([p.pack_bytes for p in parts]), pack_recs=np.concatenate([p.pack_recs for p in parts]), k=k)
 
 
 def make_pool(scale, threads=None):

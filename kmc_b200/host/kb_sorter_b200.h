@@ -25,10 +25,36 @@
 #include "kmc_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <list>
 #include <sstream>
 #include <string>
 #include <vector>
+
+// Which GPU each sorter object of this run drives: KMC_B200_DEVICES="0,1,2,..." (default "0"), each repeated
+// KMC_B200_SORTERS_PER_GPU times (default 1; 2 overlaps one bin's PCIe copies with the other's kernels).  One entry = one
+// CKmerBinSorterB200 object = one writer of CKmerQueue (kmc.h:1564), all pulling from the same CBinQueue in get_sorted_req_sizes order.
+inline std::vector<int> kmcb200_devices_from_env()
+{
+	std::vector<int> devs;
+	const char* e = std::getenv("KMC_B200_DEVICES");
+	std::string s = e && *e ? e : "0";
+	size_t pos = 0;
+	while (pos < s.size())
+	{
+		size_t c = s.find(',', pos);
+		if (c == std::string::npos) c = s.size();
+		if (c > pos) devs.push_back(std::atoi(s.substr(pos, c - pos).c_str()));
+		pos = c + 1;
+	}
+	if (devs.empty()) devs.push_back(0);
+	int per = 1;
+	if (const char* p = std::getenv("KMC_B200_SORTERS_PER_GPU")) per = std::max(1, std::min(4, std::atoi(p)));
+	std::vector<int> out;
+	for (int r = 0; r < per; ++r)
+		for (int d : devs) out.push_back(d);
+	return out;
+}
 
 template <unsigned SIZE> class CKmerBinSorterB200
 {
@@ -40,6 +66,7 @@ template <unsigned SIZE> class CKmerBinSorterB200
 	uint32 max_x;
 	uint32 lut_prefix_len;
 	kmcb200_ctx* ctx;
+	uint64 sum_n_rec = 0, sum_n_plus_x_rec = 0;
 
 	void fail(const char* what)
 	{
@@ -81,6 +108,13 @@ public:
 
 	~CKmerBinSorterB200() { kmcb200_destroy(ctx); }
 
+	// kb_sorter.h:118-122 (read by CKMC::ProcessStage2_impl for its statistics, kmc.h:1736-1741)
+	void GetDebugStats(uint64& _sum_n_recs, uint64& _sum_n_plus_x_recs)
+	{
+		_sum_n_recs = sum_n_rec;
+		_sum_n_plus_x_recs = sum_n_plus_x_rec;
+	}
+
 	CKmerBinSorterB200(const CKmerBinSorterB200&) = delete;
 	CKmerBinSorterB200& operator=(const CKmerBinSorterB200&) = delete;
 
@@ -99,6 +133,8 @@ public:
 			std::string desc;
 			uint64 tmp_size, tmp_n_rec, n_plus_x_recs;
 			bd->read(bin_id, file, desc, tmp_size, tmp_n_rec, n_plus_x_recs);
+			sum_n_rec += n_rec;
+			sum_n_plus_x_rec += n_plus_x_recs;
 
 			std::list<std::pair<uint64, uint64>> packs;
 			epd->pop(bin_id, packs);
@@ -151,6 +187,7 @@ public:
 	{
 		kbs = std::make_unique<CKmerBinSorterB200<SIZE>>(Params, Queues, device);
 	}
+	void GetDebugStats(uint64& _sum_n_recs, uint64& _sum_n_plus_x_recs) { kbs->GetDebugStats(_sum_n_recs, _sum_n_plus_x_recs); }
 	void operator()() { kbs->ProcessBins(); }
 };
 

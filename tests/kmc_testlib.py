@@ -194,7 +194,7 @@ def _synth_lib():
             subprocess.check_call(["make", "-C", SYNTH_DIR], stdout=subprocess.DEVNULL)
         L = C.CDLL(SYNTH_SO)
         L.kmcsynth_bin.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32, C.c_void_p, C.c_uint64,
-                                   C.POINTER(C.c_uint64), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+                                   C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         _synth = L
     return _synth
 
@@ -210,19 +210,21 @@ def fast_bin(seed, k, n_rec, genome_len=None, mean_extra=11.0, err_ppm=10000) ->
     guess = int(n_rec * (1.0 + (1 + (k + 3) // 4) / (mean_extra + 1.0)) * 0.25 * 1.15) + (1 << 16) if mean_extra >= 1 else 0
     data = np.empty(guess + 64, dtype=np.uint8)
     packs = np.zeros(guess // 32768 + 64, dtype=np.uint64)
+    precs = np.zeros(packs.size, dtype=np.uint64)
     rc = L.kmcsynth_bin(seed, k, n_rec, genome_len, mean_extra, err_ppm, data.ctypes.data, guess, C.byref(size),
-                        packs.ctypes.data, packs.size, C.byref(n_packs), C.byref(n_sk)) if guess else -5
+                        packs.ctypes.data, precs.ctypes.data, packs.size, C.byref(n_packs), C.byref(n_sk)) if guess else -5
     if rc == -5:
-        rc = L.kmcsynth_bin(seed, k, n_rec, genome_len, mean_extra, err_ppm, None, 0, C.byref(size), None, 0, C.byref(n_packs), C.byref(n_sk))
+        rc = L.kmcsynth_bin(seed, k, n_rec, genome_len, mean_extra, err_ppm, None, 0, C.byref(size), None, None, 0, C.byref(n_packs), C.byref(n_sk))
         assert rc == 0, rc
         data = np.zeros(size.value + 64, dtype=np.uint8)
         packs = np.zeros(max(n_packs.value, 1), dtype=np.uint64)
+        precs = np.zeros(packs.size, dtype=np.uint64)
         rc = L.kmcsynth_bin(seed, k, n_rec, genome_len, mean_extra, err_ppm, data.ctypes.data, data.size, C.byref(size),
-                            packs.ctypes.data, packs.size, C.byref(n_packs), C.byref(n_sk))
+                            packs.ctypes.data, precs.ctypes.data, packs.size, C.byref(n_packs), C.byref(n_sk))
     assert rc == 0, rc
     data[size.value:size.value + 64] = 0
-    pb = packs[:n_packs.value]
-    return Bin(data=data[:size.value], n_rec=n_rec, n_super_kmers=int(n_sk.value), pack_bytes=pb, pack_recs=pb, k=k)
+    # pack_recs = k-mers per pack: a safe upper bound of its (k+x)-mers in canonical mode (kb_sorter.h:605-633); -b mode needs Bin.extras
+    return Bin(data=data[:size.value], n_rec=n_rec, n_super_kmers=int(n_sk.value), pack_bytes=packs[:n_packs.value], pack_recs=precs[:n_packs.value], k=k)
 
 
 def to_skb(b: "Bin"):

@@ -22,7 +22,7 @@ static inline uint64_t splitmix64(uint64_t& x)
 }
 
 int kmcsynth_bin(uint64_t seed, uint32_t k, uint64_t n_rec, uint64_t genome_len, double mean_extra, uint32_t err_ppm,
-	uint8_t* data, uint64_t data_capacity, uint64_t* size, uint64_t* pack_bytes, uint32_t pack_capacity, uint32_t* n_packs, uint64_t* n_super_kmers)
+	uint8_t* data, uint64_t data_capacity, uint64_t* size, uint64_t* pack_bytes, uint64_t* pack_recs, uint32_t pack_capacity, uint32_t* n_packs, uint64_t* n_super_kmers)
 {
 	if (k < 1 || k > 256 || !size || !n_packs) return -1;
 	if (genome_len < (uint64_t)k + 256) genome_len = (uint64_t)k + 256;
@@ -46,7 +46,7 @@ int kmcsynth_bin(uint64_t seed, uint32_t k, uint64_t n_rec, uint64_t genome_len,
 	uint64_t to_err = next_gap();
 	uint64_t pos_out = 0, made = 0, n_sk = 0;
 	uint32_t np = 0;
-	uint64_t pack_fill = 0;
+	uint64_t pack_fill = 0, pack_kmers = 0;          // pack_recs[i] = k-mers of pack i (CExpanderPackDesc's second field is an upper bound of its (k+x)-mers)
 	uint8_t symbuf[256 + 256 + 8];
 	while (made < n_rec) {
 		double u = (double)(splitmix64(rs) >> 11) * (1.0 / 9007199254740992.0);
@@ -64,8 +64,9 @@ int kmcsynth_bin(uint64_t seed, uint32_t k, uint64_t n_rec, uint64_t genome_len,
 		const uint32_t bytes = 1 + (n + 3) / 4;
 		if (pack_fill + bytes > (1u << 16)) {               // collector flush (kb_collector.cpp:44-55)
 			if (pack_bytes && np < pack_capacity) pack_bytes[np] = pack_fill;
+			if (pack_recs && np < pack_capacity) pack_recs[np] = pack_kmers;
 			++np;
-			pack_fill = 0;
+			pack_fill = 0; pack_kmers = 0;
 		}
 		if (data) {
 			if (pos_out + bytes > data_capacity) return -5;
@@ -76,9 +77,9 @@ int kmcsynth_bin(uint64_t seed, uint32_t k, uint64_t n_rec, uint64_t genome_len,
 				data[pos_out + 1 + i] = b;
 			}
 		}
-		pos_out += bytes; pack_fill += bytes; made += a + 1; ++n_sk;
+		pos_out += bytes; pack_fill += bytes; pack_kmers += a + 1; made += a + 1; ++n_sk;
 	}
-	if (pack_fill) { if (pack_bytes && np < pack_capacity) pack_bytes[np] = pack_fill; ++np; }
+	if (pack_fill) { if (pack_bytes && np < pack_capacity) pack_bytes[np] = pack_fill; if (pack_recs && np < pack_capacity) pack_recs[np] = pack_kmers; ++np; }
 	*size = pos_out; *n_packs = np;
 	if (n_super_kmers) *n_super_kmers = n_sk;
 	if (pack_bytes && np > pack_capacity) return -5;
