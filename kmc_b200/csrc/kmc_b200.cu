@@ -246,17 +246,23 @@ __global__ void msd_setup_kernel(uint64_t* seg1, uint32_t* item_base1, uint32_t*
 	*n_items1 = nt;
 }
 
-// bits of the second partition level: leaves of ~1 K records.  Counted leaves (the bin path) are streamed by one warp and may be any
-// size, but a leaf beyond one table round costs extra rounds, so the level takes up to 10 bits; sorted leaves (seam #1) must fit on chip,
-// and canonical k-mers crowd into the low prefixes (largest leaf ~4.4x the mean): aim at a fifth of the capacity, 8 bits at most.
+// bits of the second partition level.  Counted leaves (the bin path) are streamed by one warp and may be any size: a leaf beyond one
+// table round only costs extra rounds, while the 512 / 1024-digit partition kernels are ~1.3x / 1.7x slower per record than the
+// 256-digit one (measured, B200: 1.2e8 k-mers 3.19 ms with 8 bits vs 3.22 with 9; 2^28 k-mers 7.86 ms with 9 bits vs 8.11 with 10;
+// 2^26 k-mers 1.79 ms with 8 bits vs 1.88 with 9).  So: leaves of ~1 K records while that takes <= 8 bits, then ~2 K-record leaves.
+// Sorted leaves (seam #1) must fit on chip, and canonical k-mers crowd into the low prefixes (largest leaf ~4.4x the mean): aim at a
+// fifth of the capacity, 8 bits at most.
 template <int WORDS>
 uint32_t choose_b2(const kmcb200_ctx* ctx, uint64_t n, bool counted_leaves)
 {
-	const uint64_t target = counted_leaves ? 1024 : std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64);
-	uint32_t lg = 0;
-	while ((1ull << lg) < (n + target - 1) / target) ++lg;
-	uint32_t b2 = lg > 8 ? std::min(lg - 8, counted_leaves ? 10u : 8u) : 0;
-	if (counted_leaves && ctx->force_b2) b2 = ctx->force_b2;          // (tests: the wide second level on small bins)
+	auto bits_for = [&](uint64_t target) { uint32_t lg = 0; while ((1ull << lg) < (n + target - 1) / target) ++lg; return lg > 8 ? lg - 8 : 0u; };
+	uint32_t b2;
+	if (counted_leaves) {
+		b2 = bits_for(1024);
+		if (b2 > 8) b2 = std::max(8u, std::min(bits_for(2048), 10u));
+		if (ctx->force_b2) b2 = ctx->force_b2;          // (tests: the wide second level on small bins)
+	} else
+		b2 = std::min(bits_for(std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64)), 8u);
 	return b2;
 }
 template <int WORDS> uint32_t choose_nd2(const kmcb200_ctx* ctx, uint64_t n, bool counted_leaves) { return 1u << choose_b2<WORDS>(ctx, n, counted_leaves); }
@@ -385,7 +391,8 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			MsdItems items2{};
 			items2.seg_start = s.msd_start2; items2.item_base = s.msd_item_base2; items2.item_seg = s.msd_item_seg2; items2.n_items = &s.zero->msd_n_items[1];
 			MsdCountArgs c2{b, items2, top_shift - b2, nd2, s.msd_cells, flags};
-			if (nd2 > 256) msd_count_kernel<WORDS, 1024><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
+			if (nd2 > 512) msd_count_kernel<WORDS, 1024><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
+			else if (nd2 > 256) msd_count_kernel<WORDS, 512><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
 			else msd_count_kernel<WORDS><<<(uint32_t)std::min<size_t>(max_items2, (size_t)ctx->sm_count * 4), 512, 0, st>>>(c2);
 			ctx->launches++;
 			if (int rc = launch_cell_scan(ctx, s, items2.n_items, nd2, max_items2, flags, st)) return rc;
@@ -397,7 +404,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 			MsdPartArgs p2{};
 			p2.in = b; p2.out = a; p2.items = items2; p2.cell_scan = s.msd_cell_scan; p2.shift = top_shift - b2; p2.nd = nd2;
 			p2.flags = flags;
-			if (nd2 > 256) msd_partition_kernel<WORDS, 1024><<<pgrid2, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS, 1024>::kBytes, st>>>(p2);
+			if (nd2 > 256) msd_partition_kernel<WORDS, 1024><<<pgrid2, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS, 1024>::kBytes, st>>>(p2);      // (a 512-digit instance with a third TMA buffer measured slower: 0.61 vs 0.57 ms at 1.2e8 records)
 			else msd_partition_kernel<WORDS><<<pgrid2, MsdCfg<WORDS>::kThreads + 32, MsdSmem<WORDS>::kBytes, st>>>(p2);
 			ctx->launches++;
 			s.pass_names[iv] = "msd_partition_L2"; CU(cudaEventRecord(s.ev_pass[++iv], st));
