@@ -4,6 +4,7 @@
 #include "../../include/kmc_b200.h"
 #include "common.cuh"
 #include "expand.cuh"
+#include "expand_fused.cuh"
 #include "radix_sort.cuh"
 #include "count.cuh"
 #include "msd_sort.cuh"
@@ -31,6 +32,8 @@ constexpr size_t kMaxLeaves = 256 * 1024;          // level 1: 8 bits, level 2: 
 
 thread_local std::string g_create_error;
 
+enum { kHistNone = 0, kHistTiles = 1, kHistAligned = 2 };      // level-1 cells: none yet / per expand tile (expand.cuh) / per aligned tile (expand_fused.cuh)
+
 struct ZeroBlock {                                // zeroed with one memset at the start of every bin
 	uint64_t hist[kHistRows][256];
 	uint32_t counters[kCounterSlots];
@@ -38,6 +41,7 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint32_t msd_flags[4];                        // [0] kMsdFlagFallback (leaves too large -> LSD passes), [1] always 0
 	uint32_t msd_n_items[2];                      // work items of the level-1 / level-2 segmentation
 	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves, leaf-count
+	uint32_t pack_ticket[4];                      // fused expansion: packs are taken in order
 	uint32_t leaf_group_sum[kMaxLeaves / 1024];   // emitted records per group of 1024 leaves
 };
 
@@ -78,6 +82,8 @@ struct Slot {
 	const char* pass_names[kMaxPasses + 8] = {};
 	uint32_t last_n_packs = 1;
 	uint64_t* cdesc = nullptr; size_t cdesc_cap = 0;        // count look-back descriptors
+	uint64_t* pdesc = nullptr; size_t pdesc_cap = 0;        // pack look-back descriptors of the fused expansion
+	int hist_mode = 0;                                      // what the last expansion left for the sort: kHistNone / kHistTiles / kHistAligned
 	// outputs of the host-buffer path
 	uint8_t* d_out = nullptr; size_t out_cap = 0;
 	uint64_t* d_lut = nullptr;
@@ -107,6 +113,7 @@ struct kmcb200_ctx {
 	int occ_radix = 1, occ_expand = 1, occ_msd_part = 1, occ_msd_part_wide = 1, occ_msd_local = 1;
 	uint32_t force_b2 = 0;                                  // KMCB200_L2_BITS: bits of the second partition level (0: chosen from the bin size)
 	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
+	bool use_fused = true;                                  // KMCB200_EXPAND=index: the index-based expansion (walk + scan + expand kernels) for every bin
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
 	uint64_t max_block_records = 1ull << 28;                // KMCB200_MAX_BLOCK_RECORDS: a bin with more k-mers is counted key block by key block
@@ -161,12 +168,20 @@ int zero_async(kmcb200_ctx* ctx, void* ptr, size_t bytes, cudaStream_t st)
 }
 
 // start of a bin: the slot's ZeroBlock, and (when given) the LUT and the 8 result words, in ONE launch
-__global__ void bin_init_kernel(uint32_t* zero_block, uint32_t zero_words, uint32_t* lut, size_t lut_words, uint32_t* result)
+struct InitExtra {            // the fused expansion (expand_fused.cuh): zeroed level-1 cells, the level-1 items are the aligned tiles of [0, n)
+	uint32_t* cells = nullptr; size_t cell_words = 0;
+	uint32_t* item_seg = nullptr; size_t item_seg_words = 0;
+	uint64_t* seg1 = nullptr; uint32_t* item_base1 = nullptr; uint64_t n = 0; uint32_t n_tiles = 0;
+};
+__global__ void bin_init_kernel(uint32_t* zero_block, uint32_t zero_words, uint32_t* lut, size_t lut_words, uint32_t* result, const InitExtra x)
 {
 	const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	for (size_t i = i0; i < zero_words; i += stride) zero_block[i] = 0u;
 	if (lut) for (size_t i = i0; i < lut_words; i += stride) lut[i] = 0u;
 	if (result && i0 < 16) result[i0] = 0u;
+	if (x.cells) for (size_t i = i0; i < x.cell_words; i += stride) x.cells[i] = 0u;
+	if (x.item_seg) for (size_t i = i0; i < x.item_seg_words; i += stride) x.item_seg[i] = 0u;
+	if (x.seg1 && i0 == 0) { x.seg1[0] = 0; x.seg1[1] = x.n; x.item_base1[0] = 0; x.item_base1[1] = x.n_tiles; }
 }
 
 uint32_t byte_log(uint64_t x) { return x < (1u << 8) ? 1 : x < (1u << 16) ? 2 : x < (1u << 24) ? 3 : 4; }   // defs.h:121
@@ -192,6 +207,7 @@ int next_epoch(kmcb200_ctx* ctx, uint32_t* out, uint32_t count = 1)
 		for (auto& s : ctx->slots) {
 			if (s.desc) CU(cudaMemset(s.desc, 0, s.desc_cap * sizeof(uint64_t)));
 			if (s.cdesc) CU(cudaMemset(s.cdesc, 0, s.cdesc_cap * sizeof(uint64_t)));
+			if (s.pdesc) CU(cudaMemset(s.pdesc, 0, s.pdesc_cap * sizeof(uint64_t)));
 		}
 		CU(cudaDeviceSynchronize());
 		ctx->epoch = 1;
@@ -209,6 +225,7 @@ int setup_kernels(kmcb200_ctx* ctx)
 	CU(cudaFuncSetAttribute(lsd_sort_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortSmem<WORDS>::kBytes));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_radix, lsd_sort_kernel<WORDS>, SortCfg<WORDS>::kThreads, SortSmem<WORDS>::kBytes));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_expand, expand_kernel<WORDS>, ExpandCfg<WORDS>::kThreads, 0));
+	CU(cudaFuncSetAttribute(expand_fused_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FxSmem<WORDS>::kBytes));
 	const size_t cs = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	CU(cudaFuncSetAttribute(count_emit_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
 	CU(cudaFuncSetAttribute(msd_partition_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MsdSmem<WORDS>::kBytes));
@@ -329,7 +346,7 @@ struct LeafPlan {
 // Sorts n records from `a` (with `b` as the second buffer).  *result_in_b tells where the sorted records end up.
 // hist_ready: the expand stage has zeroed the slot's ZeroBlock and written the level-1 cells / items.
 template <int WORDS>
-int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, uint32_t key_bits, bool hist_ready, uint32_t n_packs, cudaStream_t st, bool* result_in_b, LeafPlan* plan = nullptr)
+int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_t key_bytes, uint32_t key_bits, int hist_mode, uint32_t n_packs, cudaStream_t st, bool* result_in_b, LeafPlan* plan = nullptr)
 {
 	constexpr int TILE = SortSmem<WORDS>::kTile;
 	constexpr int MTILE = msd_tile<WORDS>();
@@ -342,7 +359,8 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 	if (int rc = ensure(ctx, s.desc, s.desc_cap, (size_t)n_tiles * 256, true)) return rc;
 	if (msd) if (int rc = ensure_msd<WORDS>(ctx, s, n, n_packs, choose_nd2<WORDS>(ctx, n, plan != nullptr))) return rc;      // (sized alike by stage_expand: no reallocation here when its cells are in use)
 
-	if (!hist_ready) if (int rc = zero_async(ctx, s.zero, sizeof(ZeroBlock), st)) return rc;
+	const bool hist_ready = hist_mode == kHistTiles;
+	if (hist_mode == kHistNone) if (int rc = zero_async(ctx, s.zero, sizeof(ZeroBlock), st)) return rc;
 	int iv = 0;      // timed interval index
 	CU(cudaEventRecord(s.ev_pass[0], st));
 	void* lsd_in = a; void* lsd_out = b;
@@ -364,6 +382,8 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 		MsdItems items1{};
 		if (hist_ready) {          // items and cells were written by expand_kernel
 			items1.item_lo = s.msd_item_lo1; items1.item_cnt = s.msd_item_cnt1; items1.n_items = &s.zero->status[1];
+		} else if (hist_mode == kHistAligned) {          // the fused expansion counted per aligned tile; its init kernel wrote the one-segment item tables
+			items1.seg_start = s.msd_seg1; items1.item_base = s.msd_item_base1; items1.item_seg = s.msd_item_seg2; items1.n_items = s.msd_item_base1 + 1;
 		} else {
 			msd_setup_kernel<<<1, 1, 0, st>>>(s.msd_seg1, s.msd_item_base1, &s.zero->msd_n_items[0], n, MTILE);
 			items1.seg_start = s.msd_seg1; items1.item_base = s.msd_item_base1; items1.item_seg = s.msd_item_seg2 /* all zero: see below */;
@@ -536,6 +556,46 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	const uint32_t np = (n_packs && pack_bytes) ? n_packs : 1;
 	if (!packs_uploaded) if (int rc = upload_packs(ctx, s, size, pack_bytes, n_packs, st)) return rc;
 
+	// ---- the default: one fused pass (expand_fused.cuh) when every pack is a collector flush (<= 64 KiB); packs_uploaded or not, the
+	// pack offsets are on the device by now.  Bigger packs, key blocks of oversized bins and KMCB200_EXPAND=index take the index-based kernels.
+	bool big_pack = !(n_packs && pack_bytes) && size > (uint64_t)kWalkChunk;
+	if (n_packs && pack_bytes) for (uint32_t i = 0; i < n_packs && !big_pack; ++i) big_pack = pack_bytes[i] > (uint64_t)kWalkChunk;
+	const bool fused = ctx->use_fused && em.mode == kExpandAll && !big_pack && n_rec != kExpandUnknownRecs && n_rec < (1ull << 32) && n_rec > 0;
+	s.last_n_packs = np;
+	if (fused) {
+		const uint32_t nd2 = DISPATCH_WORDS(ctx, choose_nd2, ctx, n_rec, ctx->use_leaf);
+		if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np, nd2)) return rc;
+		if (int rc = ensure(ctx, s.pdesc, s.pdesc_cap, (size_t)np + 1, true)) return rc;
+		const uint32_t mtile = ctx->words == 1 ? (uint32_t)msd_tile<1>() : (uint32_t)msd_tile<2>();      // (the same for 2..4 words)
+		static_assert(msd_tile<2>() == msd_tile<3>() && msd_tile<2>() == msd_tile<4>(), "one tile size for all wide records");
+		const uint32_t n_tiles = (uint32_t)((n_rec + mtile - 1) / mtile);
+		uint32_t tile_shift = 0;
+		while ((1u << tile_shift) < mtile) ++tile_shift;
+		InitExtra x;
+		x.cells = reinterpret_cast<uint32_t*>(s.msd_cells); x.cell_words = ((size_t)256 * n_tiles + 1) / 2;
+		x.item_seg = s.msd_item_seg2; x.item_seg_words = (size_t)n_tiles + 2;
+		x.seg1 = s.msd_seg1; x.item_base1 = s.msd_item_base1; x.n = n_rec; x.n_tiles = n_tiles;
+		bin_init_kernel<<<296, 256, 0, st>>>(reinterpret_cast<uint32_t*>(s.zero), (uint32_t)(sizeof(ZeroBlock) / 4), reinterpret_cast<uint32_t*>(zero_lut),
+			(size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(zero_result), x);
+		FusedArgs f{};
+		f.bin = d_bin; f.size = size; f.pack_start = s.d_pack_start; f.n_packs = np; f.k = k; f.both_strands = ctx->prm.both_strands; f.n_rec = n_rec;
+		f.recs = d_recs; f.cells1 = reinterpret_cast<uint32_t*>(s.msd_cells); f.n_tiles = n_tiles; f.tile_shift = tile_shift;
+		f.top_shift = std::max(2u * k, 8u) - 8u;
+		f.desc = s.pdesc; f.ticket = &s.zero->pack_ticket[0]; f.status = s.zero->status; f.flags = s.zero->msd_flags;
+		if (int rc = next_epoch(ctx, &f.epoch)) return rc;
+		switch (ctx->words) {
+		case 1: expand_fused_kernel<1><<<np, kFxThreads, FxSmem<1>::kBytes, st>>>(f); break;
+		case 2: expand_fused_kernel<2><<<np, kFxThreads, FxSmem<2>::kBytes, st>>>(f); break;
+		case 3: expand_fused_kernel<3><<<np, kFxThreads, FxSmem<3>::kBytes, st>>>(f); break;
+		default: expand_fused_kernel<4><<<np, kFxThreads, FxSmem<4>::kBytes, st>>>(f); break;
+		}
+		ctx->launches += 2;
+		CU(cudaGetLastError());
+		s.hist_mode = kHistAligned;
+		return 0;
+	}
+	s.hist_mode = em.mode == kExpandAll ? kHistTiles : kHistNone;
+
 	if (int rc = ensure(ctx, s.sk_off, s.sk_off_cap, size / min_rec + 2)) return rc;
 	if (int rc = ensure(ctx, s.sk_kpre, s.sk_kpre_cap, size / min_rec + 2)) return rc;
 	if (int rc = ensure(ctx, s.tile_first, s.tile_first_cap, size * 4 / kExpandMinTile + np + 2)) return rc;
@@ -556,15 +616,12 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 		a.cells1 = s.msd_cells; a.item_lo1 = s.msd_item_lo1; a.item_cnt1 = s.msd_item_cnt1;
 	} else { a.cells1 = nullptr; a.item_lo1 = nullptr; a.item_cnt1 = nullptr; }
 	a.top_shift = std::max(2u * k, 8u) - 8u;
-	s.last_n_packs = np;
 
 	bin_init_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint32_t*>(s.zero), (uint32_t)(sizeof(ZeroBlock) / 4), reinterpret_cast<uint32_t*>(zero_lut),
-		(size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(zero_result));
+		(size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(zero_result), InitExtra());
 	walk_packs_parallel_kernel<<<np, kWalkSegs, kWalkChunk + 32, st>>>(a, s.pack_done);
 	ctx->launches += 2;
 	// a pack of more than 64 KiB (not a collector flush: a caller-made pack, or the whole bin as one pack) is left to the exact warp-per-pack walker
-	bool big_pack = !(n_packs && pack_bytes) && size > (uint64_t)kWalkChunk;
-	if (n_packs && pack_bytes) for (uint32_t i = 0; i < n_packs && !big_pack; ++i) big_pack = pack_bytes[i] > (uint64_t)kWalkChunk;
 	if (big_pack) {
 		walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a, s.pack_done);
 		ctx->launches++;
@@ -581,7 +638,7 @@ int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8
 	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool outputs_zeroed = false, bool guarded = false)
 {
 	if (!outputs_zeroed) {
-		bin_init_kernel<<<64, 256, 0, st>>>(&s.zero->counters[kMaxPasses], 1u, reinterpret_cast<uint32_t*>(d_lut), (size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(d_result));
+		bin_init_kernel<<<64, 256, 0, st>>>(&s.zero->counters[kMaxPasses], 1u, reinterpret_cast<uint32_t*>(d_lut), (size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(d_result), InitExtra());
 		ctx->launches++;
 		CU(cudaGetLastError());
 	}
@@ -641,7 +698,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	// the sort starts below those bits, and nobody has counted the first digit yet
 	bool in_b = false;
 	LeafPlan plan;
-	if (int rc = launch_sort<WORDS>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len - block_bits, !from_blocks, np_eff, st, &in_b, &plan)) return rc;
+	if (int rc = launch_sort<WORDS>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len - block_bits, from_blocks ? (int)kHistNone : s.hist_mode, np_eff, st, &in_b, &plan)) return rc;
 	if (!plan.active) {          // small bin: plain LSD passes, classic count
 		CU(cudaEventRecord(s.ev_sort, st));
 		s.ran_sort = true;
@@ -652,7 +709,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	const size_t pad = (size_t)((ob + 7) / 8) * 8;
 	if (int rc = ensure(ctx, s.leaf_tmp, s.leaf_tmp_cap, (size_t)n_rec * pad + 64)) return rc;
 	if (!outputs_zeroed) {
-		bin_init_kernel<<<64, 256, 0, st>>>(nullptr, 0u, reinterpret_cast<uint32_t*>(d_lut), (size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(d_result));
+		bin_init_kernel<<<64, 256, 0, st>>>(nullptr, 0u, reinterpret_cast<uint32_t*>(d_lut), (size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(d_result), InitExtra());
 		ctx->launches++;
 	}
 	uint32_t* flags = s.zero->msd_flags;
@@ -705,7 +762,7 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	if (ctx->use_leaf) {
 		if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, n_rec, np_eff, d_out, out_capacity, d_lut, d_result, st, false, 0u, 0u, true)) return rc;
 	} else {
-		if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, true, np_eff, st, &in_b)) return rc;
+		if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len, s.hist_mode, np_eff, st, &in_b)) return rc;
 		CU(cudaEventRecord(s.ev_sort, st));
 		s.ran_sort = true;
 		const void* sorted = in_b ? s.recs_b : s.recs_a;
@@ -804,7 +861,7 @@ int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t 
 			if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, b.n, 1u, s.d_out, cap_b, s.d_lut, s.d_result, st, true, b.bits, b.prefix)) return rc;
 		} else {
 			bool in_b = false;
-			if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, b.n, ctx->key_bytes, 2u * k - b.bits, false, 1u, st, &in_b)) return rc;
+			if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, b.n, ctx->key_bytes, 2u * k - b.bits, (int)kHistNone, 1u, st, &in_b)) return rc;
 			CU(cudaEventRecord(s.ev_sort, st));
 			if (int rc = stage_count(ctx, s, in_b ? s.recs_b : s.recs_a, b.n, s.d_out, cap_b, s.d_lut, s.d_result, st)) return rc;
 		}
@@ -861,6 +918,7 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	ctx->sm_count = dp.multiProcessorCount;
 	if (const char* e = getenv("KMCB200_SORT")) ctx->use_msd = std::string(e) != "lsd";
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
+	if (const char* e = getenv("KMCB200_EXPAND")) ctx->use_fused = std::string(e) != "index";
 	if (const char* e = getenv("KMCB200_MAX_BLOCK_RECORDS")) { const long long v = atoll(e); if (v >= 1024) ctx->max_block_records = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_MAX_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= (1 << 17) && v < (1ll << 31)) ctx->max_chunk_bytes = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_L2_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 10) ctx->force_b2 = (uint32_t)v; }
@@ -908,7 +966,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 	for (auto& s : ctx->slots) {
 		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
 				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
-				 (void*)s.cdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
+				 (void*)s.cdesc, (void*)s.pdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
 				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter})
 			if (p) cudaFree(p);
@@ -1037,7 +1095,7 @@ int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, ui
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n * rec_bytes)) return rc;
 	CU(cudaMemcpyAsync(s.recs_a, recs, n * rec_bytes, cudaMemcpyHostToDevice, st));
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, 8u * key_bytes, false, 0u, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, n, key_bytes, 8u * key_bytes, (int)kHistNone, 0u, st, &in_b)) return rc;
 	CU(cudaMemcpyAsync(where ? tmp : recs, in_b ? s.recs_b : s.recs_a, n * rec_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	return where;
@@ -1084,7 +1142,7 @@ int kmcb200_dev_sort(kmcb200_ctx* ctx, uint32_t slot, void* d_recs, void* d_tmp,
 	if (n == 0) return where;
 	if (!hist_ready) CU(cudaEventRecord(s.ev_expand, st));
 	bool in_b = false;
-	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready ? 2u * ctx->prm.kmer_len : 8u * key_bytes, hist_ready != 0, s.last_n_packs, st, &in_b)) return rc;
+	if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, d_recs, d_tmp, n, key_bytes, hist_ready ? 2u * ctx->prm.kmer_len : 8u * key_bytes, hist_ready ? s.hist_mode : (int)kHistNone, s.last_n_packs, st, &in_b)) return rc;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true; s.ran_count = false;
 	if (!hist_ready) s.ran_expand = false;
