@@ -90,7 +90,7 @@ struct Slot {
 	uint64_t* d_result = nullptr; uint64_t* h_result = nullptr; uint64_t* h_result_dev = nullptr;
 	// events
 	cudaEvent_t ev_begin = nullptr, ev_expand = nullptr, ev_sort = nullptr, ev_count = nullptr, ev_result = nullptr;
-	cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;           // copy stream <-> compute stream hand-over
+	cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_walk = nullptr;           // copy stream <-> compute stream hand-over
 	cudaEvent_t ev_pass[kMaxPasses + 8] = {};
 	int n_passes_run = 0;                                   // number of timed sort intervals (ev_pass[i] .. ev_pass[i+1])
 	bool ran_expand = false, ran_sort = false, ran_count = false;
@@ -113,7 +113,8 @@ struct kmcb200_ctx {
 	int occ_radix = 1, occ_expand = 1, occ_msd_part = 1, occ_msd_part_wide = 1, occ_msd_local = 1;
 	uint32_t force_b2 = 0;                                  // KMCB200_L2_BITS: bits of the second partition level (0: chosen from the bin size)
 	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
-	bool use_fused = true;                                  // KMCB200_EXPAND=index: the index-based expansion (walk + scan + expand kernels) for every bin
+	bool use_fused = false;                                 // KMCB200_EXPAND=fused: the single-pass expansion (expand_fused.cuh) - measured slower than the index-based kernels, kept as an option
+	bool overlap_walk = true;                               // KMCB200_OVERLAP_WALK=0: the index kernels of a submitted bin on the compute stream instead of its copy stream
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
 	uint64_t max_block_records = 1ull << 28;                // KMCB200_MAX_BLOCK_RECORDS: a bin with more k-mers is counted key block by key block
@@ -548,21 +549,28 @@ int upload_packs(kmcb200_ctx* ctx, Slot& s, uint64_t size, const uint64_t* pack_
 
 int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec,
 	const uint64_t* pack_bytes, uint32_t n_packs, void* d_recs, cudaStream_t st, const ExpandMode& em = ExpandMode(), bool packs_uploaded = false,
-	uint64_t* zero_lut = nullptr, uint64_t* zero_result = nullptr)
+	uint64_t* zero_lut = nullptr, uint64_t* zero_result = nullptr, cudaStream_t st_walk = nullptr)
 {
+	// st_walk: the slot's copy stream (host-buffer path).  The index of a bin (init + walk + pack scan: ~0.15 ms at 20 % of the SMs, slot-private
+	// buffers only) then runs right behind the bin's H2D copy and overlaps the sort / leaves of the bins before it on the compute stream.
+	cudaStream_t st_expand = st;
+	if (st_walk) st = st_walk;
 	if (size >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin of %llu bytes: bins of 4 GiB or more are not supported", (unsigned long long)size);
 	const uint32_t k = ctx->prm.kmer_len;
 	const uint32_t min_rec = 1 + (k + 3) / 4;
 	const uint32_t np = (n_packs && pack_bytes) ? n_packs : 1;
 	if (!packs_uploaded) if (int rc = upload_packs(ctx, s, size, pack_bytes, n_packs, st)) return rc;
 
-	// ---- the default: one fused pass (expand_fused.cuh) when every pack is a collector flush (<= 64 KiB); packs_uploaded or not, the
-	// pack offsets are on the device by now.  Bigger packs, key blocks of oversized bins and KMCB200_EXPAND=index take the index-based kernels.
+	// ---- KMCB200_EXPAND=fused: one fused pass (expand_fused.cuh) when every pack is a collector flush (<= 64 KiB).  Measured on the B200
+	// (1.2e8 k-mers, k=31): 0.93 ms against 0.80 ms for the index-based kernels below - a lane that walks its own segment executes the
+	// "new record" and the "roll one symbol" paths one after the other (6.0 warp instructions per k-mer against 3.4) - so it is an option
+	// (no per-super-k-mer index in HBM, two launches fewer), not the default.
 	bool big_pack = !(n_packs && pack_bytes) && size > (uint64_t)kWalkChunk;
 	if (n_packs && pack_bytes) for (uint32_t i = 0; i < n_packs && !big_pack; ++i) big_pack = pack_bytes[i] > (uint64_t)kWalkChunk;
 	const bool fused = ctx->use_fused && em.mode == kExpandAll && !big_pack && n_rec != kExpandUnknownRecs && n_rec < (1ull << 32) && n_rec > 0;
 	s.last_n_packs = np;
 	if (fused) {
+		st = st_expand;
 		const uint32_t nd2 = DISPATCH_WORDS(ctx, choose_nd2, ctx, n_rec, ctx->use_leaf);
 		if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np, nd2)) return rc;
 		if (int rc = ensure(ctx, s.pdesc, s.pdesc_cap, (size_t)np + 1, true)) return rc;
@@ -629,7 +637,11 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	scan_packs_kernel<<<1, 1024, 0, st>>>(a);
 	ctx->launches++;
 	CU(cudaGetLastError());
-	return DISPATCH_WORDS(ctx, launch_expand, ctx, a, st);
+	if (st_expand != st) {
+		CU(cudaEventRecord(s.ev_walk, st));
+		CU(cudaStreamWaitEvent(st_expand, s.ev_walk, 0));
+	}
+	return DISPATCH_WORDS(ctx, launch_expand, ctx, a, st_expand);
 }
 
 // outputs_zeroed: the bin's init kernel has already cleared the LUT, the result words and the ZeroBlock (run_bin);
@@ -739,7 +751,8 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 
 // Expand -> Sort -> Compact on device buffers; records live in the slot workspace
 int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
-	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool packs_uploaded = false, uint64_t* host_result = nullptr)
+	uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool packs_uploaded = false, uint64_t* host_result = nullptr,
+	cudaStream_t st_walk = nullptr)
 {
 	const size_t rec_bytes = (size_t)ctx->words * 8;
 	s.ran_expand = s.ran_sort = s.ran_count = false;
@@ -754,7 +767,7 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 	}
 	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, n_rec * rec_bytes)) return rc;
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, n_rec * rec_bytes)) return rc;
-	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st, ExpandMode(), packs_uploaded, d_lut, d_result)) return rc;
+	if (int rc = stage_expand(ctx, s, d_bin, size, n_rec, pack_bytes, n_packs, s.recs_a, st, ExpandMode(), packs_uploaded, d_lut, d_result, st_walk)) return rc;
 	CU(cudaEventRecord(s.ev_expand, st));
 	s.ran_expand = true;
 	bool in_b = false;
@@ -918,7 +931,8 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	ctx->sm_count = dp.multiProcessorCount;
 	if (const char* e = getenv("KMCB200_SORT")) ctx->use_msd = std::string(e) != "lsd";
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
-	if (const char* e = getenv("KMCB200_EXPAND")) ctx->use_fused = std::string(e) != "index";
+	if (const char* e = getenv("KMCB200_OVERLAP_WALK")) ctx->overlap_walk = atoi(e) != 0;
+	if (const char* e = getenv("KMCB200_EXPAND")) ctx->use_fused = std::string(e) == "fused";
 	if (const char* e = getenv("KMCB200_MAX_BLOCK_RECORDS")) { const long long v = atoll(e); if (v >= 1024) ctx->max_block_records = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_MAX_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= (1 << 17) && v < (1ll << 31)) ctx->max_chunk_bytes = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_L2_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 10) ctx->force_b2 = (uint32_t)v; }
@@ -935,7 +949,7 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(KMCB200_ERR_CUDA); }
 	for (auto& s : ctx->slots) {
 		bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
-		for (cudaEvent_t* e : {&s.ev_h2d, &s.ev_done}) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+		for (cudaEvent_t* e : {&s.ev_h2d, &s.ev_done, &s.ev_walk}) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.zero), sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMemset(s.zero, 0, sizeof(ZeroBlock)) == cudaSuccess;
 		ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.d_lut), ctx->lut_entries * 8) == cudaSuccess;
@@ -973,7 +987,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
 		if (s.h_result) cudaFreeHost(s.h_result);
-		for (cudaEvent_t e : {s.ev_begin, s.ev_expand, s.ev_sort, s.ev_count, s.ev_result, s.ev_h2d, s.ev_done}) if (e) cudaEventDestroy(e);
+		for (cudaEvent_t e : {s.ev_begin, s.ev_expand, s.ev_sort, s.ev_count, s.ev_result, s.ev_h2d, s.ev_done, s.ev_walk}) if (e) cudaEventDestroy(e);
 		for (auto e : s.ev_pass) if (e) cudaEventDestroy(e);
 		if (s.stream) cudaStreamDestroy(s.stream);
 	}
@@ -1030,7 +1044,8 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	if (with_packs) if (int rc = upload_packs(ctx, s, size, pack_bytes, n_packs, st)) return rc;      // on the copy stream, next to the bin
 	CU(cudaEventRecord(s.ev_h2d, st));
 	CU(cudaStreamWaitEvent(ctx->compute, s.ev_h2d, 0));
-	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute, with_packs, s.h_result_dev)) return rc;
+	if (int rc = run_bin(ctx, s, s.d_bin, size, n_rec, pack_bytes, n_packs, s.d_out, out_capacity, s.d_lut, s.d_result, ctx->compute, with_packs, s.h_result_dev,
+		ctx->overlap_walk ? st : nullptr)) return rc;
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(s.ev_result, ctx->compute));
 	s.busy = true;
