@@ -37,6 +37,7 @@ struct CountArgs {
 	uint32_t* tile_counter;  // zero-initialised
 	const uint32_t* run_flag; // nullptr: always run; else only when (*run_flag & kRunMask) == run_need (radix_sort.cuh)
 	uint32_t run_need;
+	const uint64_t* out_base; // nullptr or: records already emitted by earlier key blocks of an oversized bin (this launch appends behind them)
 };
 
 template <int WORDS> struct CountCfg { static constexpr int kThreads = 256, kIpt = (WORDS == 1 ? 8 : WORDS == 2 ? 4 : 2); };
@@ -259,10 +260,11 @@ __global__ void __launch_bounds__(CountCfg<WORDS>::kThreads) count_emit_kernel(c
 
 	// ---- one thread per emitted record: (k-p)/4 suffix bytes, most significant first, then the counter, least significant first
 	const uint64_t base = s_base;
-	uint8_t* dst = a.out + base * ob;
+	const uint64_t ob0 = a.out_base ? *a.out_base : 0ull;
+	uint8_t* dst = a.out + (ob0 + base) * ob;
 	const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);     // staging keeps the destination's 16-byte phase
 	uint8_t* stage = stage0 + mis;
-	const bool fits = (base + emit_total) * (uint64_t)ob <= a.out_capacity;
+	const bool fits = (ob0 + base + emit_total) * (uint64_t)ob <= a.out_capacity;
 	const uint32_t prefix_shift = 2u * (a.k - a.lut_prefix_len);
 	const uint32_t pfx0 = rec_prefix<WORDS>(srec[0], prefix_shift);
 	for (uint32_t e0 = 0; e0 < emit_total; e0 += THREADS) {

@@ -96,6 +96,7 @@ struct Slot {
 	bool ran_expand = false, ran_sort = false, ran_count = false;
 	// oversized bins
 	uint64_t* d_hist12 = nullptr; unsigned long long* d_out_counter = nullptr;
+	uint64_t* tot_lut = nullptr; uint64_t* tot_res = nullptr; uint32_t last_blocks = 0;      // totals over the key blocks
 	bool sync_done = false; uint64_t sync_out_bytes = 0; uint64_t sync_stats[4] = {};
 	// pending host-buffer bin
 	bool busy = false;
@@ -117,7 +118,7 @@ struct kmcb200_ctx {
 	bool overlap_walk = true;                               // KMCB200_OVERLAP_WALK=0: the index kernels of a submitted bin on the compute stream instead of its copy stream
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
-	uint64_t max_block_records = 1ull << 28;                // KMCB200_MAX_BLOCK_RECORDS: a bin with more k-mers is counted key block by key block
+	uint64_t max_block_records = 1ull << 28;                // a bin with more k-mers is counted key block by key block: from the free HBM at create (KMCB200_MAX_BLOCK_RECORDS overrides)
 	uint64_t max_chunk_bytes = 1ull << 30;                  // KMCB200_MAX_CHUNK_BYTES: ... and expanded chunk by chunk
 	uint32_t leaf_round_pct = 100;                          // KMCB200_LEAF_ROUND_PCT: records per table round in percent of the slots
 	int leaf_slot_bits = 10;                                // KMCB200_LEAF_SLOT_BITS = 8 | 9 | 10: slots of a warp's leaf table
@@ -463,7 +464,7 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 
 template <int WORDS>
 int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
-	uint64_t* d_lut, uint64_t* d_result, const uint32_t* run_flag, uint32_t run_need, cudaStream_t st)
+	uint64_t* d_lut, uint64_t* d_result, const uint32_t* run_flag, uint32_t run_need, cudaStream_t st, const uint64_t* out_base = nullptr)
 {
 	constexpr int TILE = count_tile<WORDS>();
 	const uint32_t n_tiles = (uint32_t)((n + TILE - 1) / TILE);
@@ -475,7 +476,7 @@ int launch_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint
 	a.out = d_out; a.out_capacity = out_capacity; a.lut = d_lut; a.result = d_result;
 	a.desc = s.cdesc; a.tile_counter = &s.zero->counters[kMaxPasses];
 	if (int rc = next_epoch(ctx, &a.epoch)) return rc;
-	a.run_flag = run_flag; a.run_need = run_need;
+	a.run_flag = run_flag; a.run_need = run_need; a.out_base = out_base;
 	const size_t smem = count_smem_bytes<WORDS>(ctx->suffix_bytes + ctx->counter_bytes);
 	count_emit_kernel<WORDS><<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 6), CountCfg<WORDS>::kThreads, smem, st>>>(a);
 	ctx->launches++;
@@ -647,7 +648,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 // outputs_zeroed: the bin's init kernel has already cleared the LUT, the result words and the ZeroBlock (run_bin);
 // guarded: skip when the bin was found malformed (flags[1], set by scan_packs_kernel)
 int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8_t* d_out, uint64_t out_capacity,
-	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool outputs_zeroed = false, bool guarded = false)
+	uint64_t* d_lut, uint64_t* d_result, cudaStream_t st, bool outputs_zeroed = false, bool guarded = false, const uint64_t* out_base = nullptr)
 {
 	if (!outputs_zeroed) {
 		bin_init_kernel<<<64, 256, 0, st>>>(&s.zero->counters[kMaxPasses], 1u, reinterpret_cast<uint32_t*>(d_lut), (size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(d_result), InitExtra());
@@ -655,7 +656,7 @@ int stage_count(kmcb200_ctx* ctx, Slot& s, const void* sorted, uint64_t n, uint8
 		CU(cudaGetLastError());
 	}
 	if (n == 0) return 0;
-	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, guarded ? &s.zero->msd_flags[1] : nullptr, 0u, st);
+	return DISPATCH_WORDS(ctx, launch_count, ctx, s, sorted, n, d_out, out_capacity, d_lut, d_result, guarded ? &s.zero->msd_flags[1] : nullptr, 0u, st, out_base);
 }
 
 // the 8 result words -> pinned host memory, written by the GPU itself (zero-copy): the host-buffer path then needs no copy-engine
@@ -704,7 +705,7 @@ template <int WORDS> int setup_leaves_w(kmcb200_ctx* ctx) { return DISPATCH_SLOT
 // stand behind as the device-flagged fallback (they return at once unless a leaf could not be counted).
 template <int WORDS>
 int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np_eff, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st,
-	bool from_blocks = false, uint32_t block_bits = 0, uint32_t block_prefix = 0, bool outputs_zeroed = false)
+	bool from_blocks = false, uint32_t block_bits = 0, uint32_t block_prefix = 0, bool outputs_zeroed = false, const uint64_t* out_base = nullptr)
 {
 	// block_bits > 0: the records are one key block of an oversized bin (all share their top block_bits bits = block_prefix):
 	// the sort starts below those bits, and nobody has counted the first digit yet
@@ -715,7 +716,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 		CU(cudaEventRecord(s.ev_sort, st));
 		s.ran_sort = true;
 		const void* sorted = in_b ? s.recs_b : s.recs_a;
-		return stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st, outputs_zeroed, true);
+		return stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st, outputs_zeroed, true, out_base);
 	}
 	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
 	const size_t pad = (size_t)((ob + 7) / 8) * 8;
@@ -733,8 +734,8 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
 	la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.group_sum = s.zero->leaf_group_sum; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
 	if (int rc = DISPATCH_SLOTS(ctx, launch_leaves, WORDS, ctx, la, st)) return rc;
-	leaf_scan_kernel<<<(plan.n_leaves + 1023) / 1024, 1024, 0, st>>>(s.leaf_emit, s.zero->leaf_group_sum, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags);
-	leaf_gather_kernel<<<(plan.n_leaves + 7) / 8, 256, 0, st>>>(s.leaf_tmp, plan.start, s.leaf_emit, s.leaf_off, plan.n_leaves, ob, d_out, d_result, flags);
+	leaf_scan_kernel<<<(plan.n_leaves + 1023) / 1024, 1024, 0, st>>>(s.leaf_emit, s.zero->leaf_group_sum, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags, out_base);
+	leaf_gather_kernel<<<(plan.n_leaves + 7) / 8, 256, 0, st>>>(s.leaf_tmp, plan.start, s.leaf_emit, s.leaf_off, plan.n_leaves, ob, d_out, d_result, flags, out_base);
 	ctx->launches += 2;
 	int iv = s.n_passes_run;
 	s.pass_names[iv] = "leaf_count"; CU(cudaEventRecord(s.ev_pass[++iv], st));
@@ -746,7 +747,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true;
 	const void* sorted = (ctx->key_bytes % 2 == 0) ? s.recs_b : s.recs_a;
-	return launch_count<WORDS>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, kMsdFlagFallback, st);
+	return launch_count<WORDS>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, kMsdFlagFallback, st, out_base);
 }
 
 // Expand -> Sort -> Compact on device buffers; records live in the slot workspace
@@ -790,111 +791,179 @@ int run_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size, uint
 
 // ---------------------------------------------------------------------------------------------
 // Oversized bins (the reference's answer is strict-memory mode, bkb_sorter.h / bkb_merger.h): more k-mers than
-// one sort should take, or 4 GiB and more of bin bytes.  The bin bytes (~1.1 B per k-mer) stay in HBM, the RECORDS (8-32 B per k-mer,
-// twice) are what does not fit, so the k-mer space is cut into aligned key blocks (a prefix of <= 12 bits each) that hold at most
-// max_block_records k-mers: one expansion pass counts the top 12 bits, then every block is expanded again with a filter, sorted and
-// counted on its own.  Blocks are disjoint ranges of the sorted order, so their outputs simply follow each other, the LUTs add up,
-// and the result is bit-identical to the one-shot path.  The input is cut at pack boundaries into chunks (< 2 GiB, u32 offsets).
-int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
-	uint8_t* h_out, uint64_t out_capacity, uint64_t* h_lut, uint64_t* out_bytes, uint64_t stats[4])
+// one sort can take (max_block_records: sized from the free HBM when the context is created - the records, two buffers plus the
+// leaves' temporary one, are what does not fit, 24-96 bytes per k-mer against ~1.1 for the bin bytes), or 4 GiB and more of bin bytes.
+//   * the bin bytes are uploaded once, cut at pack boundaries into chunks of < 2 GiB (32-bit offsets inside a chunk);
+//   * a bin that is only too LONG (>= 4 GiB of bytes, k-mers within the limit) is one key block: no counting pass at all;
+//   * otherwise ONE counting expansion histograms the top 12 bits, the host bisects the histogram into aligned prefixes ("key blocks")
+//     of at most max_block_records k-mers, and every block is expanded with a filter, sorted and counted on its own.  Blocks are
+//     disjoint ranges of the sorted order, so their outputs simply follow each other and the LUTs add up: bit-identical to one shot;
+//   * the whole block loop is ASYNCHRONOUS: a block appends its records behind the earlier ones at a device-side offset (out_base),
+//     LUT and statistics are accumulated on the device (accumulate_block_kernel), and the host synchronises once at the end.
+struct BinChunk { uint32_t pack0, npacks; uint64_t byte0, bytes, dev_off; };
+struct KeyBlock { uint32_t prefix, bits; uint64_t n; };
+
+__global__ void accumulate_block_kernel(uint64_t* tot_lut, const uint64_t* blk_lut, uint64_t lut_entries, uint64_t* tot_res, const uint64_t* blk_res,
+	const unsigned long long* appended, uint64_t expected)
 {
-	cudaStream_t st = ctx->compute;
-	const uint32_t k = ctx->prm.kmer_len;
-	if (2 * k < 24) return fail(ctx, KMCB200_ERR_INVALID, "a bin of %llu k-mers with k = %u: oversized bins need k >= 12", (unsigned long long)n_rec, k);
-	if (!pack_bytes || n_packs == 0) return fail(ctx, KMCB200_ERR_INVALID, "an oversized bin (%llu bytes, %llu k-mers) needs its expander packs", (unsigned long long)size, (unsigned long long)n_rec);
-	struct Chunk { uint32_t pack0, npacks; uint64_t byte0, bytes, dev_off; };
-	std::vector<Chunk> chunks;
-	{
-		Chunk c{0, 0, 0, 0, 0};
-		uint64_t pos = 0, dev = 0;
-		for (uint32_t i = 0; i < n_packs; ++i) {
-			if (pack_bytes[i] >= ctx->max_chunk_bytes) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander pack %u has %llu bytes", i, (unsigned long long)pack_bytes[i]);
-			if (c.npacks && c.bytes + pack_bytes[i] > ctx->max_chunk_bytes) { c.dev_off = dev; dev += (c.bytes + 64 + 15) & ~15ull; chunks.push_back(c); c = Chunk{i, 0, pos, 0, 0}; }
-			c.npacks++; c.bytes += pack_bytes[i]; pos += pack_bytes[i];
-		}
-		if (c.npacks) { c.dev_off = dev; dev += (c.bytes + 64 + 15) & ~15ull; chunks.push_back(c); }
-		if (pos != size) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander packs cover %llu bytes but the bin has %llu", (unsigned long long)pos, (unsigned long long)size);
-		if (int rc = ensure(ctx, s.d_bin, s.bin_cap, dev + 64)) return rc;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < lut_entries; i += (uint64_t)gridDim.x * blockDim.x) tot_lut[i] += blk_lut[i];
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		tot_res[0] += blk_res[0]; tot_res[1] += blk_res[1]; tot_res[2] += blk_res[2];
+		tot_res[5] |= blk_res[5]; tot_res[7] |= blk_res[7];
+		if (*appended != expected) tot_res[6] |= kErrRecCount;          // the filter took another number of k-mers than the counting pass (or n_rec) said
+		tot_res[4] += blk_res[4];                                         // = out_base of the next block
 	}
-	for (const Chunk& c : chunks) CU(cudaMemcpyAsync(s.d_bin + c.dev_off, h_bin + c.byte0, c.bytes, cudaMemcpyHostToDevice, st));
-	if (!s.d_hist12) { CU(cudaMalloc(reinterpret_cast<void**>(&s.d_hist12), 4096 * 8)); CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), 8)); }
-	// ---- pass 0: where do the k-mers fall (top 12 bits)?  Also checks the packs and n_rec.
+}
+
+int plan_chunks(kmcb200_ctx* ctx, uint64_t size, const uint64_t* pack_bytes, uint32_t n_packs, std::vector<BinChunk>& chunks, uint64_t* dev_bytes)
+{
+	if (!pack_bytes || n_packs == 0) return fail(ctx, KMCB200_ERR_INVALID, "an oversized bin (%llu bytes) needs its expander packs", (unsigned long long)size);
+	BinChunk c{0, 0, 0, 0, 0};
+	uint64_t pos = 0, dev = 0;
+	for (uint32_t i = 0; i < n_packs; ++i) {
+		if (pack_bytes[i] >= ctx->max_chunk_bytes) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander pack %u has %llu bytes", i, (unsigned long long)pack_bytes[i]);
+		if (c.npacks && c.bytes + pack_bytes[i] > ctx->max_chunk_bytes) { c.dev_off = dev; dev += (c.bytes + 64 + 15) & ~15ull; chunks.push_back(c); c = BinChunk{i, 0, pos, 0, 0}; }
+		c.npacks++; c.bytes += pack_bytes[i]; pos += pack_bytes[i];
+	}
+	if (c.npacks) { c.dev_off = dev; dev += (c.bytes + 64 + 15) & ~15ull; chunks.push_back(c); }
+	if (pos != size) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander packs cover %llu bytes but the bin has %llu", (unsigned long long)pos, (unsigned long long)size);
+	*dev_bytes = dev;
+	return 0;
+}
+
+// counting expansion of the device-resident chunks: where do the k-mers fall (top 12 bits)?  Also checks the packs.  Synchronises.
+int count_top12(kmcb200_ctx* ctx, Slot& s, const std::vector<BinChunk>& chunks, const uint64_t* pack_bytes, std::vector<uint64_t>& hist, cudaStream_t st)
+{
+	const uint32_t k = ctx->prm.kmer_len;
+	if (!s.d_hist12) { CU(cudaMalloc(reinterpret_cast<void**>(&s.d_hist12), 4096 * 8)); }
 	if (int rc = zero_async(ctx, s.d_hist12, 4096 * 8, st)) return rc;
 	ExpandMode em;
 	em.mode = kExpandCount12; em.fshift = 2 * k - 12; em.hist12 = s.d_hist12;
-	for (const Chunk& c : chunks) {
+	for (const BinChunk& c : chunks) {
 		if (int rc = stage_expand(ctx, s, s.d_bin + c.dev_off, c.bytes, kExpandUnknownRecs, pack_bytes + c.pack0, c.npacks, nullptr, st, em)) return rc;
 		uint32_t status = 0;
 		CU(cudaMemcpyAsync(&status, s.zero->status, 4, cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
 		if (status & kErrPackWalk) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: an expander pack does not end on a record boundary");
 	}
-	std::vector<uint64_t> hist(4096);
+	hist.assign(4096, 0);
 	CU(cudaMemcpyAsync(hist.data(), s.d_hist12, 4096 * 8, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
-	uint64_t total = 0;
-	for (uint64_t v : hist) total += v;
-	if (total != n_rec) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: the bin holds %llu k-mers, not n_rec = %llu", (unsigned long long)total, (unsigned long long)n_rec);
-	// ---- key blocks: aligned prefixes of <= 12 bits with at most max_block_records k-mers (bisection of the histogram)
-	struct Block { uint32_t prefix, bits; uint64_t n; };
-	std::vector<Block> blocks;
+	return 0;
+}
+
+// aligned prefixes of <= 12 bits inside [lo, hi) of the 4096-entry histogram, each with at most max_records k-mers (bisection; ascending)
+int bisect_blocks(kmcb200_ctx* ctx, const std::vector<uint64_t>& hist, uint32_t lo, uint32_t hi, uint64_t max_records, std::vector<KeyBlock>& blocks)
+{
 	struct Range { uint32_t lo, len; };
-	std::vector<Range> todo{{0, 4096}};
+	std::vector<Range> todo;
+	// cover [lo, hi) with maximal aligned ranges, largest first from the right so that the stack pops them in ascending order
+	std::vector<Range> cover;
+	for (uint32_t p = lo; p < hi;) {
+		uint32_t len = 1;
+		while (len < 4096 && (p % (2 * len)) == 0 && p + 2 * len <= hi) len *= 2;
+		cover.push_back(Range{p, len});
+		p += len;
+	}
+	for (size_t q = cover.size(); q-- > 0;) todo.push_back(cover[q]);
 	while (!todo.empty()) {
 		const Range r = todo.back(); todo.pop_back();
 		uint64_t cnt = 0;
-		for (uint32_t i = r.lo; i < r.lo + r.len; ++i) cnt += hist[i];
+		for (uint32_t q = r.lo; q < r.lo + r.len; ++q) cnt += hist[q];
 		if (cnt == 0) continue;
-		if (cnt <= ctx->max_block_records || r.len == 1) {
+		if (cnt <= max_records || r.len == 1) {
 			if (cnt >= (1ull << 32)) return fail(ctx, KMCB200_ERR_INVALID, "bin too skewed: %llu k-mers share their first 6 symbols", (unsigned long long)cnt);
 			uint32_t lg = 0; while ((1u << lg) < r.len) ++lg;
-			blocks.push_back(Block{r.lo >> lg, 12 - lg, cnt});
+			blocks.push_back(KeyBlock{r.lo >> lg, 12 - lg, cnt});
 		} else { todo.push_back(Range{r.lo + r.len / 2, r.len / 2}); todo.push_back(Range{r.lo, r.len / 2}); }      // (the lower half is popped first)
 	}
-	// ---- every block: expand with the filter (all chunks), sort, count; outputs follow each other
-	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
+	return 0;
+}
+
+// Expands (filtered), sorts and counts the given key blocks of the device-resident chunks, one after the other, WITHOUT synchronising:
+// records go to d_out behind tot_res[4] records, LUT / statistics are added to tot_lut / tot_res.  The caller zeroes the totals.
+int run_key_blocks(kmcb200_ctx* ctx, Slot& s, const std::vector<BinChunk>& chunks, const uint64_t* pack_bytes, const std::vector<KeyBlock>& blocks,
+	uint8_t* d_out, uint64_t out_capacity, uint64_t* tot_lut, uint64_t* tot_res, cudaStream_t st)
+{
+	const uint32_t k = ctx->prm.kmer_len;
 	const size_t rec_bytes = (size_t)ctx->words * 8;
-	std::vector<uint64_t> lut_blk(ctx->lut_entries);
-	for (uint64_t i = 0; i < ctx->lut_entries; ++i) h_lut[i] = 0;
-	uint64_t out_pos = 0, acc[3] = {0, 0, 0};
-	for (const Block& b : blocks) {
-		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, b.n * rec_bytes)) return rc;
-		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, b.n * rec_bytes)) return rc;
+	if (!s.d_out_counter) CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), 8));
+	uint64_t max_n = 0;
+	for (const KeyBlock& b : blocks) max_n = std::max(max_n, b.n);
+	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, max_n * rec_bytes)) return rc;          // (sized once: no reallocation, no device synchronisation inside the loop)
+	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, max_n * rec_bytes)) return rc;
+	for (const KeyBlock& b : blocks) {
 		if (int rc = zero_async(ctx, s.d_out_counter, 8, st)) return rc;
 		ExpandMode ef;
 		ef.mode = kExpandFilter; ef.fshift = 2 * k - b.bits; ef.fprefix = b.prefix; ef.out_counter = s.d_out_counter;
-		if (b.bits == 0) { ef.fshift = 0; ef.fprefix = 0; ef.fmask = 0; }          // one block = the whole bin (oversized only by its bytes): keep everything
-		for (const Chunk& c : chunks)
+		ef.fmask = b.bits ? ((1u << b.bits) - 1u) : 0u;
+		if (b.bits == 0) { ef.fshift = 0; ef.fprefix = 0; }          // one block = the whole bin (oversized only by its bytes): keep everything
+		for (const BinChunk& c : chunks)
 			if (int rc = stage_expand(ctx, s, s.d_bin + c.dev_off, c.bytes, kExpandUnknownRecs, pack_bytes + c.pack0, c.npacks, s.recs_a, st, ef)) return rc;
-		const uint64_t cap_b = ((b.n + 1) / std::max(ctx->prm.cutoff_min, 1u)) * (uint64_t)ob;
-		if (int rc = ensure(ctx, s.d_out, s.out_cap, cap_b + 64)) return rc;
 		s.ran_expand = false;
 		CU(cudaEventRecord(s.ev_expand, st));
 		if (ctx->use_leaf) {
-			if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, b.n, 1u, s.d_out, cap_b, s.d_lut, s.d_result, st, true, b.bits, b.prefix)) return rc;
+			if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, b.n, 1u, d_out, out_capacity, s.d_lut, s.d_result, st, true, b.bits, b.prefix, false, tot_res + 4)) return rc;
 		} else {
 			bool in_b = false;
 			if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, s.recs_a, s.recs_b, b.n, ctx->key_bytes, 2u * k - b.bits, (int)kHistNone, 1u, st, &in_b)) return rc;
 			CU(cudaEventRecord(s.ev_sort, st));
-			if (int rc = stage_count(ctx, s, in_b ? s.recs_b : s.recs_a, b.n, s.d_out, cap_b, s.d_lut, s.d_result, st)) return rc;
+			if (int rc = stage_count(ctx, s, in_b ? s.recs_b : s.recs_a, b.n, d_out, out_capacity, s.d_lut, s.d_result, st, false, false, tot_res + 4)) return rc;
 		}
-		uint64_t r[8];
-		unsigned long long appended = 0;
-		CU(cudaMemcpyAsync(r, s.d_result, 64, cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(&appended, s.d_out_counter, 8, cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(lut_blk.data(), s.d_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-		if (appended != b.n) return fail(ctx, KMCB200_ERR_CUDA, "internal error: key block %u/%u took %llu k-mers, expected %llu", b.prefix, b.bits, appended, (unsigned long long)b.n);
-		const uint64_t bytes = r[4] * (uint64_t)ob;
-		if (r[5] || out_pos + bytes > out_capacity) return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small", (unsigned long long)out_capacity);
-		if (bytes) CU(cudaMemcpyAsync(h_out + out_pos, s.d_out, bytes, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-		out_pos += bytes;
-		for (int i = 0; i < 3; ++i) acc[i] += r[i];
-		for (uint64_t i = 0; i < ctx->lut_entries; ++i) h_lut[i] += lut_blk[i];
+		accumulate_block_kernel<<<64, 256, 0, st>>>(tot_lut, s.d_lut, ctx->lut_entries, tot_res, s.d_result, s.d_out_counter, b.n);
+		ctx->launches++;
+		CU(cudaGetLastError());
 	}
-	if (out_bytes) *out_bytes = out_pos;
-	if (stats) { stats[0] = acc[0]; stats[1] = acc[1]; stats[2] = acc[2]; stats[3] = n_rec; }      // n_total = n_rec (kb_sorter.h:1166)
+	return 0;
+}
+
+int ensure_totals(kmcb200_ctx* ctx, Slot& s, cudaStream_t st)
+{
+	if (!s.tot_lut) {
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.tot_lut), ctx->lut_entries * 8));
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.tot_res), 64));
+	}
+	if (int rc = zero_async(ctx, s.tot_lut, ctx->lut_entries * 8, st)) return rc;
+	return zero_async(ctx, s.tot_res, 64, st);
+}
+
+int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
+	uint8_t* h_out, uint64_t out_capacity, uint64_t* h_lut, uint64_t* out_bytes, uint64_t stats[4])
+{
+	cudaStream_t st = ctx->compute;
+	const uint32_t k = ctx->prm.kmer_len;
+	std::vector<BinChunk> chunks;
+	uint64_t dev_bytes = 0;
+	if (int rc = plan_chunks(ctx, size, pack_bytes, n_packs, chunks, &dev_bytes)) return rc;
+	if (int rc = ensure(ctx, s.d_bin, s.bin_cap, dev_bytes + 64)) return rc;
+	for (const BinChunk& c : chunks) CU(cudaMemcpyAsync(s.d_bin + c.dev_off, h_bin + c.byte0, c.bytes, cudaMemcpyHostToDevice, st));
+	std::vector<KeyBlock> blocks;
+	if (n_rec <= ctx->max_block_records) blocks.push_back(KeyBlock{0, 0, n_rec});          // only too long: one block, the appended count checks n_rec
+	else {
+		if (2 * k < 24) return fail(ctx, KMCB200_ERR_INVALID, "a bin of %llu k-mers with k = %u: key blocks need k >= 12", (unsigned long long)n_rec, k);
+		std::vector<uint64_t> hist;
+		if (int rc = count_top12(ctx, s, chunks, pack_bytes, hist, st)) return rc;
+		uint64_t total = 0;
+		for (uint64_t v : hist) total += v;
+		if (total != n_rec) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: the bin holds %llu k-mers, not n_rec = %llu", (unsigned long long)total, (unsigned long long)n_rec);
+		if (int rc = bisect_blocks(ctx, hist, 0, 4096, ctx->max_block_records, blocks)) return rc;
+	}
+	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
+	if (int rc = ensure(ctx, s.d_out, s.out_cap, out_capacity + 64)) return rc;
+	if (int rc = ensure_totals(ctx, s, st)) return rc;
+	if (int rc = run_key_blocks(ctx, s, chunks, pack_bytes, blocks, s.d_out, out_capacity, s.tot_lut, s.tot_res, st)) return rc;
+	uint64_t r[8];
+	CU(cudaMemcpyAsync(r, s.tot_res, 64, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));          // the only synchronisation of the block loop
+	if (r[6]) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: the bin does not hold n_rec = %llu k-mers / a pack does not end on a record boundary", (unsigned long long)n_rec);
+	const uint64_t bytes = r[4] * (uint64_t)ob;
+	if (r[5] || bytes > out_capacity) return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small", (unsigned long long)out_capacity);
+	if (bytes) CU(cudaMemcpyAsync(h_out, s.d_out, bytes, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(h_lut, s.tot_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	s.last_blocks = (uint32_t)blocks.size();
+	if (out_bytes) *out_bytes = bytes;
+	if (stats) { stats[0] = r[0]; stats[1] = r[1]; stats[2] = r[2]; stats[3] = n_rec; }      // n_total = n_rec (kb_sorter.h:1166)
 	return 0;
 }
 
@@ -933,6 +1002,15 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
 	if (const char* e = getenv("KMCB200_OVERLAP_WALK")) ctx->overlap_walk = atoi(e) != 0;
 	if (const char* e = getenv("KMCB200_EXPAND")) ctx->use_fused = std::string(e) == "fused";
+	{	// one sort needs two record buffers + the leaves' temporary records (8-byte padded) + ~2 bytes per record of tables: what 60 % of the
+		// free HBM (shared by the context's slots) can hold, below 2^32 records (32-bit record indices inside the kernels)
+		size_t free_b = 0, total_b = 0;
+		if (cudaSetDevice(prm->device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b) {
+			const uint64_t per_rec = 2ull * 8 * ctx->words + ((ctx->suffix_bytes + ctx->counter_bytes + 7) / 8) * 8 + 2;
+			const uint64_t fit = (uint64_t)(0.6 * (double)free_b) / per_rec / std::max<uint64_t>(prm->n_slots, 1);
+			ctx->max_block_records = std::max<uint64_t>(1ull << 24, std::min<uint64_t>(fit, (1ull << 32) - (1ull << 24)));
+		}
+	}
 	if (const char* e = getenv("KMCB200_MAX_BLOCK_RECORDS")) { const long long v = atoll(e); if (v >= 1024) ctx->max_block_records = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_MAX_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= (1 << 17) && v < (1ll << 31)) ctx->max_chunk_bytes = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_L2_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 10) ctx->force_b2 = (uint32_t)v; }
@@ -982,7 +1060,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.pdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
-				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter})
+				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter, (void*)s.tot_lut, (void*)s.tot_res})
 			if (p) cudaFree(p);
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);

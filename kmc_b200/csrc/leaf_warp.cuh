@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 // exclusive scan of the per-leaf record counts: one CTA per group of 1024 leaves; the groups' sums were accumulated by the leaf kernel
 // (one atomicAdd per leaf), so a CTA's base is a sum over <= 64 numbers.  total -> result[4], capacity check -> result[5]
 __global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_emit, const uint32_t* group_sum, uint32_t n_leaves, uint64_t* leaf_off,
-	uint64_t* result, uint64_t out_capacity, uint32_t ob, const uint32_t* flags)
+	uint64_t* result, uint64_t out_capacity, uint32_t ob, const uint32_t* flags, const uint64_t* out_base)
 {
 	__shared__ uint32_t s_w[32];
 	__shared__ unsigned long long s_base;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(1024) leaf_scan_kernel(const uint32_t* leaf_em
 
 // one warp per leaf: its padded temporary records -> packed records at their final place
 __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, const uint64_t* start, const uint32_t* leaf_emit, const uint64_t* leaf_off,
-	uint32_t n_leaves, uint32_t ob, uint8_t* out, const uint64_t* result, const uint32_t* flags)
+	uint32_t n_leaves, uint32_t ob, uint8_t* out, const uint64_t* result, const uint32_t* flags, const uint64_t* out_base)
 {
 	if (*flags & kMsdFlagStop) return;
 	if (result[5]) return;                        // capacity error: nothing is written
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, co
 	const uint32_t pad = ((ob + 7) >> 3) << 3;
 	const uint32_t nbytes = leaf_emit[leaf] * ob;
 	const uint8_t* src = tmp + start[leaf] * pad;
-	uint8_t* dst = out + leaf_off[leaf] * ob;
+	uint8_t* dst = out + ((out_base ? *out_base : 0ull) + leaf_off[leaf]) * ob;      // out_base: records of earlier key blocks (oversized bins)
 	const uint32_t magic = 0xFFFFFFFFu / ob + 1;          // p / ob == umulhi(p, magic) for p < 2^16 ... checked: larger leaves take the division
 	const bool use_magic = nbytes < 65536u && ob > 1;     // (ob == 1: magic wraps to 0, and p / 1 needs no trick)
 	// (4 independent byte loads in flight per lane: the loop is bound by the latency of its loads)
