@@ -24,7 +24,9 @@
  *   KMCB200_LEAF_SLOT_BITS=8|9|10  slots of a warp's leaf table (default 10)
  *   KMCB200_LEAF_ROUND_PCT=n       records per table round in percent of the slots (default 100)
  *   KMCB200_L2_BITS=1..10          bits of the second partition level (default: from the bin size, <= 10)
- *   KMCB200_MAX_BLOCK_RECORDS=n    a bin with more k-mers is counted key block by key block (default 2^28)
+ *   KMCB200_MAX_BLOCK_RECORDS=n    a bin with more k-mers is counted key block by key block (default: what 60 % of the free HBM holds, < 2^32)
+ *   KMCB200_EXPAND=fused           single-pass expansion (expand_fused.cuh) instead of the index-based kernels (measured slower; option)
+ *   KMCB200_OVERLAP_WALK=0         index kernels of a submitted bin on the compute stream instead of its copy stream
  *   KMCB200_MAX_CHUNK_BYTES=n      ... and expanded in chunks of at most n bytes (default 2^30)
  */
 #ifndef KMC_B200_H
@@ -106,6 +108,16 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	const uint64_t* pack_bytes, const uint64_t* pack_recs, uint32_t n_packs,
 	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut);
 int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint64_t stats[4]);
+
+/* One bin over several GPUs (the reference's analogue is RADULS' team sort of a big bucket, raduls_impl.h:672-745): for a bin
+ * that is too large for a fair share of one GPU's time.  ctxs[0..n_ctx) are contexts with identical parameters on different (or, for
+ * tests, the same) devices, none with a bin in flight; one host thread per GPU is started inside the call.  GPU 0 receives the bin from
+ * the host and counts the top 12 bits; the key space is cut into one contiguous range per GPU; the other GPUs fetch the BIN BYTES
+ * (~1.1 B per k-mer, not the records) from GPU 0 by peer copies over NVLink and each expands / sorts / counts its own range.  Outputs
+ * are concatenated in key order: byte-identical to kmcb200_process_bin on one GPU. */
+int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* out_bytes, uint64_t* lut, uint64_t stats[4]);
 
 /* ---- seam #1: sort host records ------------------------------------------------------------------
  * Contract of SortFunction (raduls.h:19-20, kb_sorter.h:775-779): n records of rec_bytes (multiple of 8,

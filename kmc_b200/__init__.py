@@ -32,7 +32,7 @@ class _Params(C.Structure):
 
 EXPORTS = [
     "kmcb200_create", "kmcb200_destroy", "kmcb200_last_error", "kmcb200_out_rec_bytes", "kmcb200_out_capacity", "kmcb200_lut_entries",
-    "kmcb200_host_alloc", "kmcb200_host_free", "kmcb200_process_bin", "kmcb200_submit_bin", "kmcb200_wait_bin", "kmcb200_sort_records",
+    "kmcb200_host_alloc", "kmcb200_host_free", "kmcb200_process_bin", "kmcb200_process_bin_multi", "kmcb200_submit_bin", "kmcb200_wait_bin", "kmcb200_sort_records",
     "kmcb200_dev_process_bin", "kmcb200_dev_expand", "kmcb200_dev_sort", "kmcb200_dev_count", "kmcb200_kernel_launches",
     "kmcb200_stage_times", "kmcb200_stage_names",
 ]
@@ -65,6 +65,7 @@ def load_library(build_if_needed=True):
     L.kmcb200_host_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     L.kmcb200_host_free.argtypes = [vp, vp]
     L.kmcb200_process_bin.argtypes = [vp, i32, vp, u64, u64, u64, vp, vp, u32, vp, u64, C.POINTER(u64), vp, vp]
+    L.kmcb200_process_bin_multi.argtypes = [vp, u32, i32, vp, u64, u64, vp, u32, vp, u64, C.POINTER(u64), vp, vp]
     L.kmcb200_submit_bin.argtypes = [vp, u32, i32, vp, u64, u64, u64, vp, vp, u32, vp, u64, vp]
     L.kmcb200_wait_bin.argtypes = [vp, u32, C.POINTER(u64), vp]
     L.kmcb200_sort_records.argtypes = [vp, vp, vp, u64, u32, u32]
@@ -192,6 +193,22 @@ class Stage2Context:
         nbytes = C.c_uint64(0)
         self._check(self.lib.kmcb200_wait_bin(self._h, slot, C.byref(nbytes), stats))
         return int(nbytes.value), tuple(int(x) for x in stats)
+
+    @staticmethod
+    def process_bin_multi(ctxs, b: "SuperKmerBin", out=None, lut=None) -> "BinResult":
+        """One bin split over several contexts / GPUs by key range (kmcb200_process_bin_multi)."""
+        c0 = ctxs[0]
+        cap = c0.out_capacity(b.n_rec) + 64
+        out = np.empty(cap, dtype=np.uint8) if out is None else out
+        lut = np.empty(c0.lut_entries, dtype=np.uint64) if lut is None else lut
+        stats = (C.c_uint64 * 4)()
+        nbytes = C.c_uint64(0)
+        data = np.ascontiguousarray(b.data)
+        packs = np.ascontiguousarray(b.pack_bytes, dtype=np.uint64)
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        c0._check(c0.lib.kmcb200_process_bin_multi(arr, len(ctxs), 0, data.ctypes.data, data.size, b.n_rec, packs.ctypes.data, packs.size,
+                                                   out.ctypes.data, out.size, C.byref(nbytes), lut.ctypes.data, stats))
+        return BinResult(out[:nbytes.value], lut, *[int(x) for x in stats])
 
     # -- seam #1
     def sort_records(self, recs: np.ndarray, key_bytes=None):

@@ -11,6 +11,7 @@
 #include "leaf_warp.cuh"
 
 #include <cmath>
+#include <cstddef>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 using namespace kmcb;
 
@@ -1171,6 +1173,120 @@ int kmcb200_process_bin(kmcb200_ctx* ctx, int32_t bin_id,
 {
 	if (int rc = kmcb200_submit_bin(ctx, 0, bin_id, superkmers, size, n_rec, n_plus_x_recs, pack_bytes, pack_recs, n_packs, out_suffix, out_capacity, lut)) return rc;
 	return kmcb200_wait_bin(ctx, 0, out_bytes, stats);
+}
+
+// ---- one bin over several GPUs (the reference's analogue is the big-bucket team sort, raduls_impl.h:672-745)
+// The k-mer space is cut into one contiguous range per GPU (balanced on the 12-bit histogram of a counting expansion); what travels
+// between the GPUs is the BIN BYTES (~1.1 B per k-mer, 8-30x less than the records): GPU 0 gets them from the host, the others by
+// peer copies over NVLink; every GPU then expands with a filter, sorts and counts its own range (key blocks if the range itself is
+// too large), and the per-GPU outputs follow each other in key order - the same bytes as one GPU would produce.
+int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* out_bytes, uint64_t* lut, uint64_t stats[4])
+{
+	(void)bin_id;
+	if (!ctxs || n_ctx == 0 || !ctxs[0]) return KMCB200_ERR_INVALID;
+	kmcb200_ctx* ctx = ctxs[0];
+	if (n_ctx > 64) return fail(ctx, KMCB200_ERR_INVALID, "at most 64 contexts");
+	for (uint32_t g = 0; g < n_ctx; ++g) {
+		if (!ctxs[g] || ctxs[g]->slots.empty() || ctxs[g]->slots[0].busy) return fail(ctx, KMCB200_ERR_INVALID, "context %u is null or busy", g);
+		if (ctxs[g]->words != ctx->words || memcmp(&ctxs[g]->prm, &ctx->prm, offsetof(kmcb200_params, device)) != 0) return fail(ctx, KMCB200_ERR_INVALID, "context %u has other parameters", g);
+	}
+	if ((size && !superkmers) || !lut || (!out_suffix && out_capacity)) return fail(ctx, KMCB200_ERR_INVALID, "null buffer");
+	const uint32_t k = ctx->prm.kmer_len;
+	if (n_rec == 0 || size == 0 || n_ctx == 1 || 2 * k < 24 || n_rec < 4096ull * n_ctx)          // nothing to split
+		return kmcb200_process_bin(ctx, bin_id, superkmers, size, n_rec, n_rec, pack_bytes, nullptr, n_packs, out_suffix, out_capacity, out_bytes, lut, stats);
+	if (int rc = set_device(ctx)) return rc;
+	Slot& s0 = ctx->slots[0];
+	std::vector<BinChunk> chunks;
+	uint64_t dev_bytes = 0;
+	std::vector<uint64_t> one_pack{size};
+	if (!pack_bytes || n_packs == 0) { pack_bytes = one_pack.data(); n_packs = 1; }
+	if (int rc = plan_chunks(ctx, size, pack_bytes, n_packs, chunks, &dev_bytes)) return rc;
+	if (int rc = ensure(ctx, s0.d_bin, s0.bin_cap, dev_bytes + 64)) return rc;
+	for (const BinChunk& c : chunks) CU(cudaMemcpyAsync(s0.d_bin + c.dev_off, superkmers + c.byte0, c.bytes, cudaMemcpyHostToDevice, ctx->compute));
+	std::vector<uint64_t> hist;
+	if (int rc = count_top12(ctx, s0, chunks, pack_bytes, hist, ctx->compute)) return rc;          // (synchronises: the bytes are on GPU 0 now)
+	uint64_t total = 0;
+	for (uint64_t v : hist) total += v;
+	if (total != n_rec) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: the bin holds %llu k-mers, not n_rec = %llu", (unsigned long long)total, (unsigned long long)n_rec);
+	// ---- contiguous ranges of the 4096 prefixes, ~n_rec / n_ctx k-mers each
+	std::vector<uint32_t> cut(n_ctx + 1, 4096);
+	cut[0] = 0;
+	{
+		uint64_t acc = 0;
+		uint32_t g = 1;
+		for (uint32_t q = 0; q < 4096 && g < n_ctx; ++q) {
+			acc += hist[q];
+			while (g < n_ctx && acc * n_ctx >= (uint64_t)g * n_rec) cut[g++] = q + 1;
+		}
+	}
+	struct Part { std::vector<KeyBlock> blocks; uint64_t n = 0, cap = 0, bytes = 0; uint64_t r[8] = {}; int rc = 0; std::vector<uint64_t> lut; };
+	std::vector<Part> parts(n_ctx);
+	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
+	for (uint32_t g = 0; g < n_ctx; ++g) {
+		if (int rc = bisect_blocks(ctxs[g], hist, cut[g], cut[g + 1], ctxs[g]->max_block_records, parts[g].blocks)) { ctx->err = ctxs[g]->err; return rc; }
+		for (const KeyBlock& b : parts[g].blocks) parts[g].n += b.n;
+		parts[g].cap = ((parts[g].n + 1) / std::max(ctx->prm.cutoff_min, 1u)) * (uint64_t)ob;
+		parts[g].lut.resize(ctx->lut_entries);
+	}
+	// ---- every GPU on its own host thread: bytes from GPU 0 (peer copy), its key blocks, its totals
+	auto worker = [&](uint32_t g) {
+		kmcb200_ctx* c = ctxs[g];
+		Slot& s = c->slots[0];
+		Part& P = parts[g];
+		auto run = [&]() -> int {
+			kmcb200_ctx* ctx = c;          // (CU reports into this context)
+			if (int rc = set_device(c)) return rc;
+			cudaStream_t st = c->compute;
+			if (P.n == 0) return 0;
+			if (g > 0) {
+				if (int rc = ensure(c, s.d_bin, s.bin_cap, dev_bytes + 64)) return rc;
+				if (c->prm.device != ctxs[0]->prm.device) {
+					int can = 0;
+					cudaDeviceCanAccessPeer(&can, c->prm.device, ctxs[0]->prm.device);
+					if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[0]->prm.device, 0); if (e != cudaSuccess) cudaGetLastError(); }      // (already enabled is fine)
+				}
+				CU(cudaMemcpyPeerAsync(s.d_bin, c->prm.device, ctxs[0]->slots[0].d_bin, ctxs[0]->prm.device, dev_bytes, st));
+			}
+			if (int rc = ensure(c, s.d_out, s.out_cap, P.cap + 64)) return rc;
+			if (int rc = ensure_totals(c, s, st)) return rc;
+			if (int rc = run_key_blocks(c, s, chunks, pack_bytes, P.blocks, s.d_out, P.cap, s.tot_lut, s.tot_res, st)) return rc;
+			CU(cudaMemcpyAsync(P.r, s.tot_res, 64, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(P.lut.data(), s.tot_lut, c->lut_entries * 8, cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			return 0;
+		};
+		P.rc = run();
+	};
+	std::vector<std::thread> threads;
+	for (uint32_t g = 1; g < n_ctx; ++g) threads.emplace_back(worker, g);
+	worker(0);
+	for (auto& t : threads) t.join();
+	uint64_t pos = 0, acc[3] = {0, 0, 0};
+	for (uint32_t g = 0; g < n_ctx; ++g) {
+		if (parts[g].rc) { if (g) ctx->err = ctxs[g]->err; return parts[g].rc; }
+		if (parts[g].r[6]) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error on GPU %u's key range", g);
+		parts[g].bytes = parts[g].r[4] * (uint64_t)ob;
+		if (parts[g].r[5] || pos + parts[g].bytes > out_capacity) return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small", (unsigned long long)out_capacity);
+		pos += parts[g].bytes;
+	}
+	// ---- outputs in key order, LUTs and statistics added up
+	pos = 0;
+	for (uint64_t i = 0; i < ctx->lut_entries; ++i) lut[i] = 0;
+	for (uint32_t g = 0; g < n_ctx; ++g) {
+		kmcb200_ctx* c = ctxs[g];
+		cudaSetDevice(c->prm.device);
+		if (parts[g].bytes) { cudaError_t e = cudaMemcpyAsync(out_suffix + pos, c->slots[0].d_out, parts[g].bytes, cudaMemcpyDeviceToHost, c->compute); if (e != cudaSuccess) return fail(ctx, KMCB200_ERR_CUDA, "D2H of GPU %u's records failed: %s", g, cudaGetErrorString(e)); }
+		pos += parts[g].bytes;
+		for (int i = 0; i < 3; ++i) acc[i] += parts[g].r[i];
+		if (parts[g].n) for (uint64_t i = 0; i < ctx->lut_entries; ++i) lut[i] += parts[g].lut[i];
+	}
+	for (uint32_t g = 0; g < n_ctx; ++g) { cudaSetDevice(ctxs[g]->prm.device); cudaStreamSynchronize(ctxs[g]->compute); }
+	cudaSetDevice(ctx->prm.device);
+	if (out_bytes) *out_bytes = pos;
+	if (stats) { stats[0] = acc[0]; stats[1] = acc[1]; stats[2] = acc[2]; stats[3] = n_rec; }
+	return 0;
 }
 
 int kmcb200_sort_records(kmcb200_ctx* ctx, void* recs, void* tmp, uint64_t n, uint32_t rec_bytes, uint32_t key_bytes)

@@ -116,3 +116,19 @@ def test_reference_cli_known_answers_through_the_patched_binary(tmp_path):
         if "dump" in kat:
             got = [tuple(l.split()) for l in dump_sorted(tmp, db, "kat%d" % i).splitlines()]
             assert got == [(s, str(c)) for s, c in kat["dump"]]
+
+
+def test_kmc_runner_on_several_gpus(tmp_path):
+    """KMC_B200_DEVICES lists one sorter object per GPU, all pulling from the reference's CBinQueue (kmc.h:1564-1600): needs >= 2 GPUs."""
+    import torch
+    _need_binaries()
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("one GPU visible")
+    tmp = str(tmp_path)
+    fq = os.path.join(tmp, "reads.fq")
+    write_fastq(fq, 77, 60000)
+    ref_db, _ = count(KMC_REF, tmp, "ref", fq, 31, ("-ci2", "-sr1"))
+    devs = ",".join(str(i) for i in range(min(n_dev, 8)))
+    gpu_db, _ = count(KMC_B200, tmp, "gpus", fq, 31, ("-ci2",), env={"KMC_B200_DEVICES": devs, "KMC_B200_SORTERS_PER_GPU": "2"})
+    assert dump_sorted(tmp, gpu_db, "gpus") == dump_sorted(tmp, ref_db, "ref")

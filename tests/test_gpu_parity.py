@@ -482,3 +482,28 @@ def test_fused_expansion_option(oracle, monkeypatch, k, both, cmin, p_len, n):
     assert ei.value.code == kmc_b200.ERR_BIN_FORMAT
     _check_bin(oracle, synth_bin(5, k, 5000, genome_len=20000), p, ctx)
     ctx.close()
+
+
+@pytest.mark.parametrize("k,p_len,n,n_ctx", [(31, 7, 3_000_000, 2), (31, 7, 1_500_000, 3), (55, 7, 1_200_000, 2), (17, 5, 900_000, 4)])
+def test_one_bin_split_over_several_gpus(oracle, monkeypatch, k, p_len, n, n_ctx):
+    """kmcb200_process_bin_multi: contiguous key ranges per GPU, the bin bytes travel by peer copies, outputs concatenated in
+    key order - byte-identical to one GPU.  Distinct devices when the box has them, otherwise several contexts on device 0; the block limit
+    is lowered so that every GPU's range itself needs several key blocks."""
+    import torch
+    import kmc_b200
+    monkeypatch.setenv("KMCB200_MAX_BLOCK_RECORDS", str(max(n // 7, 1024)))
+    p = Params(k=k, cutoff_min=2, lut_prefix_len=p_len)
+    n_dev = torch.cuda.device_count()
+    sp = kmc_b200.Stage2Params(p.k, p.both_strands, p.cutoff_min, p.cutoff_max, p.counter_max, p.lut_prefix_len)
+    ctxs = [kmc_b200.Stage2Context(sp, device=(g % n_dev), n_slots=1) for g in range(n_ctx)]
+    b = fast_bin(600 + k, k, n)
+    r = kmc_b200.Stage2Context.process_bin_multi(ctxs, b)
+    e = oracle.process_bin(b, p)
+    assert r.stats == e.stats and np.array_equal(r.lut, e.lut) and r.payload.tobytes() == e.payload
+    # a malformed bin is reported, and the contexts stay usable
+    with pytest.raises(kmc_b200.KmcB200Error):
+        kmc_b200.Stage2Context.process_bin_multi(ctxs, kmc_b200.SuperKmerBin(data=b.data, n_rec=b.n_rec - 5, pack_bytes=b.pack_bytes, kmer_len=k))
+    r2 = ctxs[-1].process_bin(b)
+    assert r2.payload.tobytes() == e.payload
+    for c in ctxs:
+        c.close()
