@@ -119,6 +119,26 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
 	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* out_bytes, uint64_t* lut, uint64_t stats[4]);
 
+/* ---- database assembly without the reference's completer loop (kmc_core/kb_completer.cpp:59-326) ------------------------
+ * kmcb200_wait_bin_scanned = kmcb200_wait_bin, but the LUT arrives as the completer writes it to .kmc_pre: the exclusive prefix sum of the
+ * bin's raw counts offset by lut_base (records preceding the bin in the file, kb_completer.cpp:191-201), computed on the GPU before the copy.
+ * The writer owns a PINNED staging ring: kmcb200_db_reserve gives the region the next bin's records are copied into by the GPU (pass it as
+ * out_suffix of kmcb200_submit_bin), kmcb200_db_commit_bin queues it for the writer thread (fwrite to .kmc_suf / .kmc_pre in commit order,
+ * overlapping the GPU), kmcb200_db_close writes the footer of ProcessBinsSecondStage (:284-320).  For the same bins in the same order the
+ * two files are byte-identical to the reference's. */
+typedef struct kmcb200_db_writer kmcb200_db_writer;
+typedef struct {
+	uint32_t kmer_len, counter_size /* bytes */, lut_prefix_len, signature_len, cutoff_min, cutoff_max, both_strands;
+} kmcb200_db_params;
+int kmcb200_wait_bin_scanned(kmcb200_ctx* ctx, uint32_t slot, uint64_t lut_base, uint64_t* out_bytes, uint64_t stats[4]);
+int kmcb200_db_open(const kmcb200_db_params* params, const char* path_prefix, uint64_t staging_bytes, kmcb200_db_writer** out_writer);
+const char* kmcb200_db_last_error(const kmcb200_db_writer* w);
+uint64_t kmcb200_db_records(const kmcb200_db_writer* w);           /* records committed so far = lut_base of the next bin */
+int kmcb200_db_reserve(kmcb200_db_writer* w, uint64_t bytes, uint8_t** out_ptr);
+int kmcb200_db_commit_bin(kmcb200_db_writer* w, uint64_t payload_bytes, const uint64_t* lut, int raw_lut, const uint64_t stats[4],
+	const uint32_t* signatures, uint32_t n_signatures);
+int kmcb200_db_close(kmcb200_db_writer* w, uint64_t totals[4]);
+
 /* ---- seam #1: sort host records ------------------------------------------------------------------
  * Contract of SortFunction (raduls.h:19-20, kb_sorter.h:775-779): n records of rec_bytes (multiple of 8,
  * CKmer<SIZE> images) sorted ascending on bytes key_bytes-1..0; the result is left in `tmp` when key_bytes

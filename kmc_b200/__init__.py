@@ -30,11 +30,17 @@ class _Params(C.Structure):
                 ("counter_max", C.c_uint32), ("lut_prefix_len", C.c_uint32), ("device", C.c_int32), ("n_slots", C.c_uint32)]
 
 
+class _DbParams(C.Structure):
+    _fields_ = [("kmer_len", C.c_uint32), ("counter_size", C.c_uint32), ("lut_prefix_len", C.c_uint32), ("signature_len", C.c_uint32),
+                ("cutoff_min", C.c_uint32), ("cutoff_max", C.c_uint32), ("both_strands", C.c_uint32)]
+
+
 EXPORTS = [
     "kmcb200_create", "kmcb200_destroy", "kmcb200_last_error", "kmcb200_out_rec_bytes", "kmcb200_out_capacity", "kmcb200_lut_entries",
     "kmcb200_host_alloc", "kmcb200_host_free", "kmcb200_process_bin", "kmcb200_process_bin_multi", "kmcb200_submit_bin", "kmcb200_wait_bin", "kmcb200_sort_records",
     "kmcb200_dev_process_bin", "kmcb200_dev_expand", "kmcb200_dev_sort", "kmcb200_dev_count", "kmcb200_kernel_launches",
     "kmcb200_stage_times", "kmcb200_stage_names",
+    "kmcb200_wait_bin_scanned", "kmcb200_db_open", "kmcb200_db_last_error", "kmcb200_db_records", "kmcb200_db_reserve", "kmcb200_db_commit_bin", "kmcb200_db_close",
 ]
 
 _lib = None
@@ -77,6 +83,15 @@ def load_library(build_if_needed=True):
     L.kmcb200_kernel_launches.restype = u64
     L.kmcb200_stage_times.argtypes = [vp, u32, C.POINTER(C.c_float), u32]
     L.kmcb200_stage_names.argtypes = [vp, u32, C.c_char_p, u32]
+    L.kmcb200_wait_bin_scanned.argtypes = [vp, u32, u64, C.POINTER(u64), vp]
+    L.kmcb200_db_open.argtypes = [C.POINTER(_DbParams), C.c_char_p, u64, C.POINTER(vp)]
+    L.kmcb200_db_last_error.argtypes = [vp]
+    L.kmcb200_db_last_error.restype = C.c_char_p
+    L.kmcb200_db_records.argtypes = [vp]
+    L.kmcb200_db_records.restype = u64
+    L.kmcb200_db_reserve.argtypes = [vp, u64, C.POINTER(vp)]
+    L.kmcb200_db_commit_bin.argtypes = [vp, u64, vp, C.c_int, vp, vp, u32]
+    L.kmcb200_db_close.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -188,6 +203,13 @@ class Stage2Context:
         self._check(self.lib.kmcb200_submit_bin(self._h, slot, bin_id, data_ptr, size, n_rec, n_rec, packs.ctypes.data, None, packs.size,
                                                 out_ptr, out_capacity, lut_ptr))
 
+    def wait_bin_scanned(self, slot, lut_base):
+        """wait_bin with the LUT already prefix-summed on the GPU and offset by lut_base (what goes into .kmc_pre)."""
+        stats = (C.c_uint64 * 4)()
+        nbytes = C.c_uint64(0)
+        self._check(self.lib.kmcb200_wait_bin_scanned(self._h, slot, lut_base, C.byref(nbytes), stats))
+        return int(nbytes.value), tuple(int(x) for x in stats)
+
     def wait_bin(self, slot):
         stats = (C.c_uint64 * 4)()
         nbytes = C.c_uint64(0)
@@ -234,3 +256,44 @@ class Stage2Context:
 
     def dev_count(self, slot, d_sorted, n, d_out, out_capacity, d_lut, d_result, stream=None):
         self._check(self.lib.kmcb200_dev_count(self._h, slot, d_sorted, n, d_out, out_capacity, d_lut, d_result, stream))
+
+
+class DbWriter:
+    """KMC database files from per-bin results (kmcb200_db_*): pinned staging ring + writer thread; format of kb_completer.cpp:59-326."""
+
+    def __init__(self, path_prefix, kmer_len, counter_size, lut_prefix_len, signature_len, cutoff_min, cutoff_max, both_strands, staging_bytes=1 << 28):
+        self.lib = load_library()
+        self._h = C.c_void_p(None)
+        p = _DbParams(kmer_len, counter_size, lut_prefix_len, signature_len, cutoff_min, min(cutoff_max, 0xFFFFFFFF), int(both_strands))
+        rc = self.lib.kmcb200_db_open(C.byref(p), path_prefix.encode(), staging_bytes, C.byref(self._h))
+        if rc != 0:
+            raise KmcB200Error(rc, (self.lib.kmcb200_db_last_error(None) or b"").decode())
+        self.lut_entries = 1 << (2 * lut_prefix_len)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise KmcB200Error(rc, (self.lib.kmcb200_db_last_error(self._h) or b"").decode())
+
+    @property
+    def records(self):
+        return int(self.lib.kmcb200_db_records(self._h))
+
+    def reserve(self, nbytes):
+        ptr = C.c_void_p(None)
+        self._check(self.lib.kmcb200_db_reserve(self._h, nbytes, C.byref(ptr)))
+        return ptr.value
+
+    def commit_bin(self, payload_bytes, lut: np.ndarray, stats, signatures=(), raw_lut=False):
+        lut = np.ascontiguousarray(lut, dtype=np.uint64)
+        assert lut.size == self.lut_entries
+        st = (C.c_uint64 * 4)(*[int(x) for x in stats])
+        sig = np.ascontiguousarray(np.asarray(signatures, dtype=np.uint32))
+        self._check(self.lib.kmcb200_db_commit_bin(self._h, payload_bytes, lut.ctypes.data, int(raw_lut), st, sig.ctypes.data if sig.size else None, sig.size))
+
+    def close(self):
+        tot = (C.c_uint64 * 4)()
+        h, self._h = self._h, C.c_void_p(None)
+        rc = self.lib.kmcb200_db_close(h, tot)
+        if rc != 0:
+            raise KmcB200Error(rc, "kmcb200_db_close")
+        return tuple(int(x) for x in tot)

@@ -99,6 +99,7 @@ struct Slot {
 	// oversized bins
 	uint64_t* d_hist12 = nullptr; unsigned long long* d_out_counter = nullptr;
 	uint64_t* tot_lut = nullptr; uint64_t* tot_res = nullptr; uint32_t last_blocks = 0;      // totals over the key blocks
+	bool scan_lut = false; uint64_t scan_base = 0;                                            // kmcb200_wait_bin_scanned
 	bool sync_done = false; uint64_t sync_out_bytes = 0; uint64_t sync_stats[4] = {};
 	// pending host-buffer bin
 	bool busy = false;
@@ -971,6 +972,8 @@ int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t 
 
 }  // namespace
 
+namespace { __global__ void lut_scan_kernel(uint64_t* lut, uint64_t n, uint64_t base); }
+
 // ================================================================================================= C ABI
 extern "C" {
 
@@ -1113,7 +1116,7 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	if (n_rec > ctx->max_block_records || size >= 4 * ctx->max_chunk_bytes) {        // oversized: counted key block by key block, synchronously
 		CU(cudaStreamSynchronize(ctx->compute));
 		if (int rc = run_oversized_bin(ctx, s, superkmers, size, n_rec, pack_bytes, n_packs, out_suffix, out_capacity, lut, &s.sync_out_bytes, s.sync_stats)) return rc;
-		s.busy = true; s.sync_done = true;
+		s.busy = true; s.sync_done = true; s.host_lut = lut;
 		return 0;
 	}
 	cudaStream_t st = s.stream;       // copies
@@ -1140,8 +1143,11 @@ int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint6
 	if (!s.busy) return fail(ctx, KMCB200_ERR_INVALID, "slot %u has no submitted bin", slot);
 	if (int rc = set_device(ctx)) return rc;
 	s.busy = false;
+	const bool scan = s.scan_lut;
+	s.scan_lut = false;
 	if (s.sync_done) {          // an oversized bin: everything happened inside submit
 		s.sync_done = false;
+		if (scan) { uint64_t acc = s.scan_base; for (uint64_t i = 0; i < ctx->lut_entries; ++i) { const uint64_t x = s.host_lut[i]; s.host_lut[i] = acc; acc += x; } }
 		if (out_bytes) *out_bytes = s.sync_out_bytes;
 		if (stats) for (int i = 0; i < 4; ++i) stats[i] = s.sync_stats[i];
 		return 0;
@@ -1157,6 +1163,10 @@ int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint6
 	if (r[5] || bytes > s.host_out_cap) {
 		cudaStreamSynchronize(s.stream);
 		return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small for %llu bytes", (unsigned long long)s.host_out_cap, (unsigned long long)bytes);
+	}
+	if (scan) {          // the completer's prefix sum (kb_completer.cpp:191-201) on the GPU: the LUT arrives as it goes into .kmc_pre
+		lut_scan_kernel<<<1, 1024, 0, s.stream>>>(s.d_lut, ctx->lut_entries, s.scan_base);
+		ctx->launches++;
 	}
 	CU(cudaMemcpyAsync(s.host_lut, s.d_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, s.stream));
 	if (bytes) CU(cudaMemcpyAsync(s.host_out, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -1405,3 +1415,5 @@ int kmcb200_stage_names(kmcb200_ctx* ctx, uint32_t slot, char* buf, uint32_t cap
 }
 
 }  // extern "C"
+
+#include "db_writer.inl"
