@@ -109,6 +109,16 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut);
 int kmcb200_wait_bin(kmcb200_ctx* ctx, uint32_t slot, uint64_t* out_bytes, uint64_t stats[4]);
 
+/* SURVEY 8f N4 - a device-friendly stage-1 output: kmcb200_submit_bin for a stage 1 that also hands over, per bin, the length byte `a` of
+ * every record as a separate array (extras[n_super_kmers], stream order: the value CKmerBinCollector::PutExtendedKmer stores in front of the
+ * record, kb_collector.cpp:60-66) and the number of records of every expander pack (pack_superkmers[n_packs]).  The record index is then two
+ * parallel prefix sums per pack instead of the serial record walk; it is verified against the stream, a wrong array is KMCB200_ERR_BIN_FORMAT.
+ * INTEGRATION.md shows the few lines a KMC collector needs for it. */
+int kmcb200_submit_bin_indexed(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
+	const uint8_t* extras, uint64_t n_super_kmers, const uint32_t* pack_superkmers,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut);
+
 /* One bin over several GPUs (the reference's analogue is RADULS' team sort of a big bucket, raduls_impl.h:672-745): for a bin
  * that is too large for a fair share of one GPU's time.  ctxs[0..n_ctx) are contexts with identical parameters on different (or, for
  * tests, the same) devices, none with a bin in flight; one host thread per GPU is started inside the call.  GPU 0 receives the bin from

@@ -37,7 +37,7 @@ class _DbParams(C.Structure):
 
 EXPORTS = [
     "kmcb200_create", "kmcb200_destroy", "kmcb200_last_error", "kmcb200_out_rec_bytes", "kmcb200_out_capacity", "kmcb200_lut_entries",
-    "kmcb200_host_alloc", "kmcb200_host_free", "kmcb200_process_bin", "kmcb200_process_bin_multi", "kmcb200_submit_bin", "kmcb200_wait_bin", "kmcb200_sort_records",
+    "kmcb200_host_alloc", "kmcb200_host_free", "kmcb200_process_bin", "kmcb200_process_bin_multi", "kmcb200_submit_bin", "kmcb200_submit_bin_indexed", "kmcb200_wait_bin", "kmcb200_sort_records",
     "kmcb200_dev_process_bin", "kmcb200_dev_expand", "kmcb200_dev_sort", "kmcb200_dev_count", "kmcb200_kernel_launches",
     "kmcb200_stage_times", "kmcb200_stage_names",
     "kmcb200_wait_bin_scanned", "kmcb200_db_open", "kmcb200_db_last_error", "kmcb200_db_records", "kmcb200_db_reserve", "kmcb200_db_commit_bin", "kmcb200_db_close",
@@ -73,6 +73,7 @@ def load_library(build_if_needed=True):
     L.kmcb200_process_bin.argtypes = [vp, i32, vp, u64, u64, u64, vp, vp, u32, vp, u64, C.POINTER(u64), vp, vp]
     L.kmcb200_process_bin_multi.argtypes = [vp, u32, i32, vp, u64, u64, vp, u32, vp, u64, C.POINTER(u64), vp, vp]
     L.kmcb200_submit_bin.argtypes = [vp, u32, i32, vp, u64, u64, u64, vp, vp, u32, vp, u64, vp]
+    L.kmcb200_submit_bin_indexed.argtypes = [vp, u32, i32, vp, u64, u64, vp, u32, vp, u64, vp, vp, u64, vp]
     L.kmcb200_wait_bin.argtypes = [vp, u32, C.POINTER(u64), vp]
     L.kmcb200_sort_records.argtypes = [vp, vp, vp, u64, u32, u32]
     L.kmcb200_dev_process_bin.argtypes = [vp, u32, vp, u64, u64, vp, u32, vp, u64, vp, vp, vp]
@@ -202,6 +203,14 @@ class Stage2Context:
     def submit_bin(self, slot, data_ptr, size, n_rec, packs: np.ndarray, out_ptr, out_capacity, lut_ptr, bin_id=0):
         self._check(self.lib.kmcb200_submit_bin(self._h, slot, bin_id, data_ptr, size, n_rec, n_rec, packs.ctypes.data, None, packs.size,
                                                 out_ptr, out_capacity, lut_ptr))
+
+    def submit_bin_indexed(self, slot, data_ptr, size, n_rec, packs: np.ndarray, extras: np.ndarray, pack_superkmers: np.ndarray, out_ptr, out_capacity, lut_ptr, bin_id=0):
+        """submit_bin with stage 1's length bytes as a separate array (N4: no record walk on the GPU)."""
+        extras = np.ascontiguousarray(extras, dtype=np.uint8)
+        psk = np.ascontiguousarray(pack_superkmers, dtype=np.uint32)
+        self._keep = (extras, psk)
+        self._check(self.lib.kmcb200_submit_bin_indexed(self._h, slot, bin_id, data_ptr, size, n_rec, packs.ctypes.data, packs.size,
+                                                        extras.ctypes.data, extras.size, psk.ctypes.data, out_ptr, out_capacity, lut_ptr))
 
     def wait_bin_scanned(self, slot, lut_base):
         """wait_bin with the LUT already prefix-summed on the GPU and offset by lut_base (what goes into .kmc_pre)."""

@@ -259,6 +259,64 @@ __global__ void __launch_bounds__(32 * kWalkWarpsPerBlock) walk_packs_kernel(con
 	}
 }
 
+// SURVEY section 8f N4 - a device-friendly stage-1 output.  The walk above exists only because the stream is self-delimiting.  If stage 1
+// also hands over the length bytes as a SEPARATE array (`extras[i]` = the byte `a` of record i, 1 byte per super-k-mer; the collector has
+// it in a register when it writes the record, kb_collector.cpp:60-66) plus the number of records of every pack, the index is two block-wide
+// prefix sums per pack instead of a serial chain: one CTA per pack, one thread per record.  The result is checked against the stream (the
+// byte at every computed offset must be that record's `a`, the last record must end with the pack), so a wrong array is a reported bin
+// format error, never a wrong result.
+__global__ void __launch_bounds__(1024) index_from_extras_kernel(const ExpandArgs a, const uint8_t* __restrict__ extras, const uint64_t* __restrict__ pack_rec_start)
+{
+	__shared__ uint32_t s_b[32], s_k[32];
+	__shared__ uint32_t carry_b, carry_k;
+	__shared__ uint32_t s_bad;
+	const uint32_t p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint64_t pstart = a.pack_start[p];
+	const uint32_t len = (uint32_t)min(a.pack_start[p + 1] - pstart, (uint64_t)0xffffffffu);
+	const uint64_t r0 = pack_rec_start[p];
+	const uint32_t nrec = (uint32_t)min(pack_rec_start[p + 1] - r0, (uint64_t)0xffffffffu);
+	const uint64_t slot = pstart / a.min_rec_bytes;
+	const uint64_t tfb = tile_first_base(pstart, p, a.tile);
+	if (tid == 0) { carry_b = 0; carry_k = 0; s_bad = 0; }
+	__syncthreads();
+	// (more records than the pack's bytes can hold: the array is wrong; also keeps the index writes inside the pack's own slots)
+	const bool too_many = (uint64_t)nrec * a.min_rec_bytes > (uint64_t)len;
+	for (uint32_t j0 = 0; j0 < nrec && !too_many; j0 += 1024) {
+		const uint32_t j = j0 + tid;
+		const uint32_t x = j < nrec ? extras[r0 + j] : 0u;
+		const uint32_t nb = j < nrec ? 1u + ((x + a.k + 3u) >> 2) : 0u, nk = j < nrec ? x + 1u : 0u;
+		uint32_t ib = nb, ik = nk;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t tb = __shfl_up_sync(0xffffffffu, ib, o), tk = __shfl_up_sync(0xffffffffu, ik, o);
+			if (lane >= (uint32_t)o) { ib += tb; ik += tk; }
+		}
+		if (lane == 31) { s_b[warp] = ib; s_k[warp] = ik; }
+		__syncthreads();
+		uint32_t bb = carry_b, bk = carry_k;
+		for (uint32_t w = 0; w < warp; ++w) { bb += s_b[w]; bk += s_k[w]; }
+		const uint32_t off = bb + ib - nb, kk = bk + ik - nk;          // byte offset inside the pack / k-mers before this record
+		if (j < nrec) {
+			if (off + nb > len || a.bin[pstart + off] != (uint8_t)x) atomicOr(&s_bad, 1u);          // the stream disagrees with the array
+			else {
+				a.sk_off[slot + j] = (uint32_t)(pstart + off);
+				a.sk_kpre[slot + j] = kk;
+				const uint32_t tb = (kk + a.tile - 1) / a.tile;
+				if (tb * a.tile < kk + x + 1) a.tile_first[tfb + tb] = j;
+			}
+		}
+		__syncthreads();
+		if (tid == 1023) { carry_b = bb + ib; carry_k = bk + ik; }
+		__syncthreads();
+	}
+	if (tid == 0) {
+		const bool bad = too_many || s_bad || carry_b != len;
+		if (bad) atomicOr(a.status, kErrPackWalk);
+		a.pack_nsk[p] = bad ? 0u : nrec;
+		a.pack_nk[p] = bad ? 0u : carry_k;
+	}
+}
+
 // single CTA: exclusive scans over packs
 __global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
 {

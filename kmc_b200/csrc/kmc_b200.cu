@@ -100,6 +100,8 @@ struct Slot {
 	uint64_t* d_hist12 = nullptr; unsigned long long* d_out_counter = nullptr;
 	uint64_t* tot_lut = nullptr; uint64_t* tot_res = nullptr; uint32_t last_blocks = 0;      // totals over the key blocks
 	bool scan_lut = false; uint64_t scan_base = 0;                                            // kmcb200_wait_bin_scanned
+	uint8_t* d_extras = nullptr; size_t extras_cap = 0; uint64_t* d_pack_rec = nullptr; size_t pack_rec_cap = 0;      // kmcb200_submit_bin_indexed (N4)
+	uint64_t* h_pack_rec = nullptr; size_t h_pack_rec_cap = 0; bool have_extras = false;
 	bool sync_done = false; uint64_t sync_out_bytes = 0; uint64_t sync_stats[4] = {};
 	// pending host-buffer bin
 	bool busy = false;
@@ -571,7 +573,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	// (no per-super-k-mer index in HBM, two launches fewer), not the default.
 	bool big_pack = !(n_packs && pack_bytes) && size > (uint64_t)kWalkChunk;
 	if (n_packs && pack_bytes) for (uint32_t i = 0; i < n_packs && !big_pack; ++i) big_pack = pack_bytes[i] > (uint64_t)kWalkChunk;
-	const bool fused = ctx->use_fused && em.mode == kExpandAll && !big_pack && n_rec != kExpandUnknownRecs && n_rec < (1ull << 32) && n_rec > 0;
+	const bool fused = ctx->use_fused && !s.have_extras && em.mode == kExpandAll && !big_pack && n_rec != kExpandUnknownRecs && n_rec < (1ull << 32) && n_rec > 0;
 	s.last_n_packs = np;
 	if (fused) {
 		st = st_expand;
@@ -631,8 +633,14 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 
 	bin_init_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint32_t*>(s.zero), (uint32_t)(sizeof(ZeroBlock) / 4), reinterpret_cast<uint32_t*>(zero_lut),
 		(size_t)ctx->lut_entries * 2, reinterpret_cast<uint32_t*>(zero_result), InitExtra());
-	walk_packs_parallel_kernel<<<np, kWalkSegs, kWalkChunk + 32, st>>>(a, s.pack_done);
-	ctx->launches += 2;
+	if (s.have_extras && em.mode == kExpandAll) {          // N4: stage 1 handed over the length bytes: two prefix sums per pack instead of the walk
+		index_from_extras_kernel<<<np, 1024, 0, st>>>(a, s.d_extras, s.d_pack_rec);
+		ctx->launches += 2;
+		big_pack = false;
+	} else {
+		walk_packs_parallel_kernel<<<np, kWalkSegs, kWalkChunk + 32, st>>>(a, s.pack_done);
+		ctx->launches += 2;
+	}
 	// a pack of more than 64 KiB (not a collector flush: a caller-made pack, or the whole bin as one pack) is left to the exact warp-per-pack walker
 	if (big_pack) {
 		walk_packs_kernel<<<(np + kWalkWarpsPerBlock - 1) / kWalkWarpsPerBlock, 32 * kWalkWarpsPerBlock, 0, st>>>(a, s.pack_done);
@@ -1065,11 +1073,12 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.pdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
-				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter, (void*)s.tot_lut, (void*)s.tot_res})
+				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter, (void*)s.tot_lut, (void*)s.tot_res, (void*)s.d_extras, (void*)s.d_pack_rec})
 			if (p) cudaFree(p);
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
 		if (s.h_result) cudaFreeHost(s.h_result);
+		if (s.h_pack_rec) cudaFreeHost(s.h_pack_rec);
 		for (cudaEvent_t e : {s.ev_begin, s.ev_expand, s.ev_sort, s.ev_count, s.ev_result, s.ev_h2d, s.ev_done, s.ev_walk}) if (e) cudaEventDestroy(e);
 		for (auto e : s.ev_pass) if (e) cudaEventDestroy(e);
 		if (s.stream) cudaStreamDestroy(s.stream);
@@ -1102,12 +1111,34 @@ int kmcb200_host_free(kmcb200_ctx* ctx, void* ptr)
 	return 0;
 }
 
+static int submit_bin_impl(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* superkmers, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs, uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut,
+	const uint8_t* extras, uint64_t n_super_kmers, const uint32_t* pack_superkmers);
+
 int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, uint64_t n_plus_x_recs,
 	const uint64_t* pack_bytes, const uint64_t* pack_recs, uint32_t n_packs,
 	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut)
 {
 	(void)bin_id; (void)n_plus_x_recs; (void)pack_recs;
+	return submit_bin_impl(ctx, slot, superkmers, size, n_rec, pack_bytes, n_packs, out_suffix, out_capacity, lut, nullptr, 0, nullptr);
+}
+
+int kmcb200_submit_bin_indexed(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
+	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
+	const uint8_t* extras, uint64_t n_super_kmers, const uint32_t* pack_superkmers,
+	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut)
+{
+	(void)bin_id;
+	if (!ctx) return KMCB200_ERR_INVALID;
+	if (size && (!extras || !pack_superkmers || !pack_bytes || n_packs == 0)) return fail(ctx, KMCB200_ERR_INVALID, "the indexed form needs extras, pack_bytes and pack_superkmers");
+	return submit_bin_impl(ctx, slot, superkmers, size, n_rec, pack_bytes, n_packs, out_suffix, out_capacity, lut, extras, n_super_kmers, pack_superkmers);
+}
+
+static int submit_bin_impl(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* superkmers, uint64_t size, uint64_t n_rec,
+	const uint64_t* pack_bytes, uint32_t n_packs, uint8_t* out_suffix, uint64_t out_capacity, uint64_t* lut,
+	const uint8_t* extras, uint64_t n_super_kmers, const uint32_t* pack_superkmers)
+{
 	if (int rc = check_slot(ctx, slot)) return rc;
 	Slot& s = ctx->slots[slot];
 	if (s.busy) return fail(ctx, KMCB200_ERR_BUSY, "slot %u already holds a submitted bin", slot);
@@ -1123,6 +1154,25 @@ int kmcb200_submit_bin(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 	if (int rc = ensure(ctx, s.d_bin, s.bin_cap, size + 64)) return rc;
 	if (int rc = ensure(ctx, s.d_out, s.out_cap, out_capacity + 64)) return rc;
 	if (size) CU(cudaMemcpyAsync(s.d_bin, superkmers, size, cudaMemcpyHostToDevice, st));
+	s.have_extras = false;
+	if (extras && size && n_rec) {          // N4: the length bytes + the first record of every pack travel next to the bin
+		if (int rc = ensure(ctx, s.d_extras, s.extras_cap, n_super_kmers + 64)) return rc;
+		if (int rc = ensure(ctx, s.d_pack_rec, s.pack_rec_cap, (size_t)n_packs + 2)) return rc;
+		if (s.h_pack_rec_cap < (size_t)n_packs + 2) {
+			CU(cudaStreamSynchronize(st));
+			if (s.h_pack_rec) CU(cudaFreeHost(s.h_pack_rec));
+			s.h_pack_rec = nullptr; s.h_pack_rec_cap = 0;
+			CU(cudaHostAlloc(reinterpret_cast<void**>(&s.h_pack_rec), ((size_t)n_packs + 2 + n_packs / 4) * 8, cudaHostAllocDefault));
+			s.h_pack_rec_cap = (size_t)n_packs + 2 + n_packs / 4;
+		} else CU(cudaEventSynchronize(s.ev_h2d));          // (the previous bin's copy out of this staging buffer is done)
+		uint64_t acc = 0;
+		for (uint32_t i = 0; i < n_packs; ++i) { s.h_pack_rec[i] = acc; acc += pack_superkmers[i]; }
+		s.h_pack_rec[n_packs] = acc;
+		if (acc != n_super_kmers) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "pack_superkmers add up to %llu records, n_super_kmers is %llu", (unsigned long long)acc, (unsigned long long)n_super_kmers);
+		CU(cudaMemcpyAsync(s.d_extras, extras, n_super_kmers, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(s.d_pack_rec, s.h_pack_rec, ((size_t)n_packs + 1) * 8, cudaMemcpyHostToDevice, st));
+		s.have_extras = true;
+	}
 	const bool with_packs = size != 0 && n_rec != 0;
 	if (with_packs) if (int rc = upload_packs(ctx, s, size, pack_bytes, n_packs, st)) return rc;      // on the copy stream, next to the bin
 	CU(cudaEventRecord(s.ev_h2d, st));

@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 					}
 				}
 				emit_base += n_main;
+				__syncwarp();          // (racecheck, round 2: a lane that leaves the emission early must not clear the table / bitmaps under the lanes still reading them)
 				// ---- next round: back up from finished halves of a split, then one step to the right
 				while (e > e0 && (r & 1u)) { r >>= 1; --e; }
 				++r;

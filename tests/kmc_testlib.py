@@ -227,6 +227,23 @@ def fast_bin(seed, k, n_rec, genome_len=None, mean_extra=11.0, err_ppm=10000) ->
     return Bin(data=data[:size.value], n_rec=n_rec, n_super_kmers=int(n_sk.value), pack_bytes=packs[:n_packs.value], pack_recs=precs[:n_packs.value], k=k)
 
 
+def bin_extras(b: "Bin"):
+    """(extras u8 [n_super_kmers], pack_superkmers u32 [n_packs]): what a stage 1 with the N4 patch would hand over (kmcb200_submit_bin_indexed)."""
+    d, k = b.data, b.k
+    ex, per_pack = [], []
+    pos = 0
+    for pb in [int(x) for x in b.pack_bytes]:
+        end, n = pos + pb, 0
+        while pos < end:
+            a = int(d[pos])
+            ex.append(a)
+            pos += 1 + (a + k + 3) // 4
+            n += 1
+        assert pos == end
+        per_pack.append(n)
+    return np.array(ex, dtype=np.uint8), np.array(per_pack, dtype=np.uint32)
+
+
 def to_skb(b: "Bin"):
     """Bin -> the package's SuperKmerBin (what Stage2Context.process_bin takes)."""
     import kmc_b200

@@ -507,3 +507,34 @@ def test_one_bin_split_over_several_gpus(oracle, monkeypatch, k, p_len, n, n_ctx
     assert r2.payload.tobytes() == e.payload
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("k,both,cmin,p_len,n", [(31, True, 2, 7, 400000), (55, True, 1, 7, 150000), (17, False, 1, 5, 200000), (128, True, 1, 8, 50000)])
+def test_indexed_submit_needs_no_walk(oracle, k, both, cmin, p_len, n):
+    """kmcb200_submit_bin_indexed: stage 1 hands over the length bytes as a separate array; the index is two prefix sums per
+    pack.  Same bytes as the walk; an array that disagrees with the stream is a bin-format error."""
+    import kmc_b200
+    from kmc_testlib import bin_extras
+    p = Params(k=k, both_strands=both, cutoff_min=cmin, lut_prefix_len=p_len)
+    b = fast_bin(700 + k, k, n)
+    extras, psk = bin_extras(b)
+    ctx = _ctx(p, n_slots=2)
+    e = oracle.process_bin(b, p)
+    cap = ctx.out_capacity(b.n_rec) + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    lut = np.zeros(ctx.lut_entries, dtype=np.uint64)
+    data = np.ascontiguousarray(b.data)
+    l0 = ctx.kernel_launches()
+    ctx.submit_bin_indexed(0, data.ctypes.data, data.size, b.n_rec, np.ascontiguousarray(b.pack_bytes), extras, psk, out.ctypes.data, cap, lut.ctypes.data)
+    nbytes, stats = ctx.wait_bin(0)
+    assert stats == e.stats and out[:nbytes].tobytes() == e.payload and np.array_equal(lut, e.lut)
+    # wrong arrays: a length byte off by one / a record moved to the neighbouring pack
+    bad = extras.copy()
+    bad[len(bad) // 2] ^= 1
+    for ex, ps in [(bad, psk)] + ([(extras, psk + np.array([1, -1] + [0] * (psk.size - 2)).astype(np.uint32))] if psk.size >= 2 else []):
+        ctx.submit_bin_indexed(1, data.ctypes.data, data.size, b.n_rec, np.ascontiguousarray(b.pack_bytes), ex, ps, out.ctypes.data, cap, lut.ctypes.data)
+        with pytest.raises(kmc_b200.KmcB200Error) as ei:
+            ctx.wait_bin(1)
+        assert ei.value.code == kmc_b200.ERR_BIN_FORMAT
+    _check_bin(oracle, b, p, ctx)                  # and the walk path on the same context still works
+    ctx.close()
