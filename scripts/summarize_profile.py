@@ -15,7 +15,7 @@ if os.path.exists(lp):
         name = r[4].split("(")[0].replace("void ", "")
         agg.setdefault(name, []).append(float(r[-1]) / 1e3)
     tot = sum(sum(v) for v in agg.values())
-    out.append("## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, %d launches of `bench.py --steps 2 --warmup 3`; cold-cache, serialised: compare SHARES)\n" % len(rows))
+    out.append("## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, %d launches of `bench.py --steps 2 --warmup 3 --no-cpu --no-secondary`, taken inside the timed region; cold-cache, serialised: compare SHARES)\n" % len(rows))
     out.append("| kernel | launches | avg µs | min µs | max µs | share of listed time |\n|---|---|---|---|---|---|")
     for k, v in agg.items():
         out.append("| `%s` | %d | %.1f | %.1f | %.1f | %.1f %% |" % (k, len(v), sum(v) / len(v), min(v), max(v), 100 * sum(v) / tot))
@@ -44,15 +44,16 @@ if os.path.exists(rp):
             except ValueError: pass
             vals.append(v + (" " + u if u and u not in ("%",) else ""))
         out.append("| %s | `%s` | " % (r[0], name) + " | ".join(vals) + " |")
-        if "msd_partition" in name and traffic is None:          # the kernel bench.py's roofline names (radix_pass launches are no-op fallbacks)
+        if "leaf_warp" in name and traffic is None:          # the dominant stage of the step (bench.py: roofline.stage = leaf_count)
             def tobytes(x, unit):
                 return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
             traffic = tobytes(r[idx["dram__bytes_read.sum"]], rows[1][idx["dram__bytes_read.sum"]]) + tobytes(r[idx["dram__bytes_write.sum"]], rows[1][idx["dram__bytes_write.sum"]])
     out.append("")
     if traffic:
-        json.dump({"dram_bytes_per_launch": traffic, "source": "ncu --set full, %s, first msd_partition_kernel instance" % os.path.basename(rp)},
-                  open(os.path.join(P, "radix_pass_traffic.json"), "w"))
-        out.append("dominant-kernel DRAM traffic per launch: %.4g bytes (algorithmic 2*N*W = %.4g)\n" % (traffic, 2.0 * (1 << 26) * 8))
+        json.dump({"stage": "leaf_count", "dram_bytes_per_launch": traffic,
+                   "source": "ncu --set full --clock-control none, %s: leaf_warp_kernel<1,10> on one bin of 117440512 k-mers (scripts/probe_bin.py), the workload's mean bin" % os.path.basename(rp)},
+                  open(os.path.join(P, "dominant_kernel_traffic.json"), "w"))
+        out.append("dominant-kernel (leaf_warp_kernel) DRAM traffic per launch: %.4g bytes (algorithmic N*W + U*7 = %.4g for N = 117440512)\n" % (traffic, 117440512 * 8.0 + 4858316 * 7.0))
 
 for suffix in ("", "_reference"):
     bp = os.path.join(G, "bench_%s%s.json" % (tag, suffix))
