@@ -69,9 +69,14 @@ struct ExpandArgs {
 	uint32_t mode;               // 0: everything (above); 1: only count the top 12 bits into hist12; 2: only k-mers of one key block, appended to recs
 	uint32_t fshift, fprefix, fmask;    // mode 2: keep the k-mers with ((kmer >> fshift) & fmask) == fprefix
 	uint64_t* hist12;            // mode 1: [4096]
-	unsigned long long* out_counter;     // mode 2: records appended so far
+	unsigned long long* out_counter;     // mode 2: records appended so far; mode 3: [n_blocks] records appended to every key block's region
+	// mode 3 (oversized bins whose records fit in HBM once): ONE expansion scatters every k-mer into the region of its key block
+	const uint16_t* blk_of_prefix;       // [4096] key block of a 12-bit prefix
+	const uint64_t* region_start;        // [n_blocks] first record of every block's region inside recs
+	uint32_t n_blocks;                   // <= kExpandMaxBlocks
 };
-enum : uint32_t { kExpandAll = 0, kExpandCount12 = 1, kExpandFilter = 2 };
+enum : uint32_t { kExpandAll = 0, kExpandCount12 = 1, kExpandFilter = 2, kExpandScatter = 3 };
+constexpr uint32_t kExpandMaxBlocks = 512;
 constexpr uint64_t kExpandUnknownRecs = ~0ull;      // n_rec of a chunk: not checked
 
 enum : uint32_t { kErrPackWalk = 1, kErrRecCount = 2 };
@@ -617,6 +622,35 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 					const Rec<WORDS> r = kmer_of(slot);
 					atomicAdd(reinterpret_cast<unsigned long long*>(a.hist12) + msd_free_bits<WORDS>(r, a.fshift, 0xFFFu), 1ull);
 				}
+			}
+		} else if (a.mode == kExpandScatter) {
+			// oversized bin, all key blocks at once: rank inside (tile, block) from a shared-memory counter, one global atomicAdd per
+			// (tile, block) reserves the run inside the block's region, the k-mers are extracted a second time and written there
+			// (holding 8 wide records per thread across the barriers would cost the registers)
+			__shared__ uint32_t s_bcnt[kExpandMaxBlocks];
+			__shared__ unsigned long long s_bbase[kExpandMaxBlocks];
+			for (uint32_t b = tid; b < a.n_blocks; b += kExpandThreads) s_bcnt[b] = 0;
+			__syncthreads();
+			uint16_t blk[IPT], rnk[IPT];
+#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				const uint32_t slot = i * kExpandThreads + tid;
+				if (slot < cnt) {
+					const Rec<WORDS> r = kmer_of(slot);
+					blk[i] = a.blk_of_prefix[msd_free_bits<WORDS>(r, a.fshift, 0xFFFu)];
+					rnk[i] = (uint16_t)atomicAdd(&s_bcnt[blk[i]], 1u);
+				}
+			}
+			__syncthreads();
+			for (uint32_t b = tid; b < a.n_blocks; b += kExpandThreads) {
+				const uint32_t c = s_bcnt[b];
+				if (c) s_bbase[b] = a.region_start[b] + atomicAdd(a.out_counter + b, (unsigned long long)c);
+			}
+			__syncthreads();
+#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				const uint32_t slot = i * kExpandThreads + tid;
+				if (slot < cnt) out[s_bbase[blk[i]] + rnk[i]] = kmer_of(slot);
 			}
 		} else {
 			// oversized bin, one key block: the k-mers of the block are appended densely (their order does not matter, they get sorted)

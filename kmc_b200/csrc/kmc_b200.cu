@@ -97,7 +97,8 @@ struct Slot {
 	int n_passes_run = 0;                                   // number of timed sort intervals (ev_pass[i] .. ev_pass[i+1])
 	bool ran_expand = false, ran_sort = false, ran_count = false;
 	// oversized bins
-	uint64_t* d_hist12 = nullptr; unsigned long long* d_out_counter = nullptr;
+	uint64_t* d_hist12 = nullptr; unsigned long long* d_out_counter = nullptr; size_t out_counter_cap = 0;
+	uint16_t* d_blk_of_prefix = nullptr; uint64_t* d_region_start = nullptr; size_t region_cap = 0; bool last_scatter = false;      // key blocks, scatter flow
 	uint64_t* tot_lut = nullptr; uint64_t* tot_res = nullptr; uint32_t last_blocks = 0;      // totals over the key blocks
 	bool scan_lut = false; uint64_t scan_base = 0;                                            // kmcb200_wait_bin_scanned
 	uint8_t* d_extras = nullptr; size_t extras_cap = 0; uint64_t* d_pack_rec = nullptr; size_t pack_rec_cap = 0;      // kmcb200_submit_bin_indexed (N4)
@@ -120,6 +121,8 @@ struct kmcb200_ctx {
 	uint32_t force_b2 = 0;                                  // KMCB200_L2_BITS: bits of the second partition level (0: chosen from the bin size)
 	bool use_msd = true;                                    // KMCB200_SORT=lsd forces the plain 8-bit LSD passes
 	bool use_fused = false;                                 // KMCB200_EXPAND=fused: the single-pass expansion (expand_fused.cuh) - measured slower than the index-based kernels, kept as an option
+	bool scatter_blocks = true;                             // KMCB200_KEY_BLOCKS=filter: key blocks always re-expand the bin with a filter (what happens anyway when the records do not fit in HBM once)
+	uint64_t key_block_records = 1ull << 28;                // KMCB200_KEY_BLOCK_RECORDS: preferred size of a key block when the bin is scattered once (leaves of ~1-2 K records)
 	bool overlap_walk = true;                               // KMCB200_OVERLAP_WALK=0: the index kernels of a submitted bin on the compute stream instead of its copy stream
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
@@ -282,8 +285,10 @@ uint32_t choose_b2(const kmcb200_ctx* ctx, uint64_t n, bool counted_leaves)
 	auto bits_for = [&](uint64_t target) { uint32_t lg = 0; while ((1ull << lg) < (n + target - 1) / target) ++lg; return lg > 8 ? lg - 8 : 0u; };
 	uint32_t b2;
 	if (counted_leaves) {
-		b2 = bits_for(1024);
-		if (b2 > 8) b2 = std::max(8u, std::min(bits_for(2048), 10u));
+		b2 = std::min(bits_for(1024), 10u);
+		// (one-word records only: the leaves of wider records verify every hit against a record in HBM and lose more from a second
+		// table round than the wide scatter costs - k = 55, 2^28 k-mers: 17.1 ms with 10 bits, 21.0 ms with 9)
+		if (WORDS == 1 && b2 > 8) b2 = std::max(8u, std::min(bits_for(2048), 10u));
 		if (ctx->force_b2) b2 = ctx->force_b2;          // (tests: the wide second level on small bins)
 	} else
 		b2 = std::min(bits_for(std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64)), 8u);
@@ -508,6 +513,7 @@ struct ExpandMode {            // oversized bins: count the top 12 bits / keep o
 	uint32_t mode = kExpandAll, fshift = 0, fprefix = 0, fmask = 0xFFFu;
 	uint64_t* hist12 = nullptr;
 	unsigned long long* out_counter = nullptr;
+	const uint16_t* blk_of_prefix = nullptr; const uint64_t* region_start = nullptr; uint32_t n_blocks = 0;      // kExpandScatter
 };
 
 // Host prefix sum of the expander-pack sizes -> pinned staging -> device, on `st`.  The host-buffer path enqueues this on the slot's
@@ -625,6 +631,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.status = s.zero->status; a.flags = s.zero->msd_flags;
 	a.recs = d_recs;
 	a.mode = em.mode; a.fshift = em.fshift; a.fprefix = em.fprefix; a.fmask = em.fmask; a.hist12 = em.hist12; a.out_counter = em.out_counter;
+	a.blk_of_prefix = em.blk_of_prefix; a.region_start = em.region_start; a.n_blocks = em.n_blocks;
 	if (em.mode == kExpandAll) {
 		if (int rc = DISPATCH_WORDS(ctx, ensure_msd, ctx, s, n_rec, np, DISPATCH_WORDS(ctx, choose_nd2, ctx, n_rec, ctx->use_leaf))) return rc;
 		a.cells1 = s.msd_cells; a.item_lo1 = s.msd_item_lo1; a.item_cnt1 = s.msd_item_cnt1;
@@ -716,17 +723,20 @@ template <int WORDS> int setup_leaves_w(kmcb200_ctx* ctx) { return DISPATCH_SLOT
 // stand behind as the device-flagged fallback (they return at once unless a leaf could not be counted).
 template <int WORDS>
 int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np_eff, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st,
-	bool from_blocks = false, uint32_t block_bits = 0, uint32_t block_prefix = 0, bool outputs_zeroed = false, const uint64_t* out_base = nullptr)
+	bool from_blocks = false, uint32_t block_bits = 0, uint32_t block_prefix = 0, bool outputs_zeroed = false, const uint64_t* out_base = nullptr,
+	void* ra = nullptr, void* rb = nullptr)
 {
+	if (!ra) ra = s.recs_a;          // (a key block of a scattered bin sorts its own region of the bin-wide record buffer in place, with rb as scratch)
+	if (!rb) rb = s.recs_b;
 	// block_bits > 0: the records are one key block of an oversized bin (all share their top block_bits bits = block_prefix):
 	// the sort starts below those bits, and nobody has counted the first digit yet
 	bool in_b = false;
 	LeafPlan plan;
-	if (int rc = launch_sort<WORDS>(ctx, s, s.recs_a, s.recs_b, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len - block_bits, from_blocks ? (int)kHistNone : s.hist_mode, np_eff, st, &in_b, &plan)) return rc;
+	if (int rc = launch_sort<WORDS>(ctx, s, ra, rb, n_rec, ctx->key_bytes, 2u * ctx->prm.kmer_len - block_bits, from_blocks ? (int)kHistNone : s.hist_mode, np_eff, st, &in_b, &plan)) return rc;
 	if (!plan.active) {          // small bin: plain LSD passes, classic count
 		CU(cudaEventRecord(s.ev_sort, st));
 		s.ran_sort = true;
-		const void* sorted = in_b ? s.recs_b : s.recs_a;
+		const void* sorted = in_b ? rb : ra;
 		return stage_count(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, st, outputs_zeroed, true, out_base);
 	}
 	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
@@ -752,12 +762,12 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	s.pass_names[iv] = "leaf_count"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 	// fallback (two launches that return at once unless a leaf could not be counted): all LSD passes from the level-1 output in one
 	// cooperative kernel (which first forgets what the leaves added to the LUT / statistics), then the classic count
-	if (int rc = launch_lsd_sort<WORDS>(ctx, s, s.recs_b, s.recs_a, n_rec, ctx->key_bytes, flags, kMsdFlagFallback, d_lut, d_result, st)) return rc;
+	if (int rc = launch_lsd_sort<WORDS>(ctx, s, rb, ra, n_rec, ctx->key_bytes, flags, kMsdFlagFallback, d_lut, d_result, st)) return rc;
 	s.pass_names[iv] = "lsd_fallback(all passes)"; CU(cudaEventRecord(s.ev_pass[++iv], st));
 	s.n_passes_run = iv;
 	CU(cudaEventRecord(s.ev_sort, st));
 	s.ran_sort = true;
-	const void* sorted = (ctx->key_bytes % 2 == 0) ? s.recs_b : s.recs_a;
+	const void* sorted = (ctx->key_bytes % 2 == 0) ? rb : ra;
 	return launch_count<WORDS>(ctx, s, sorted, n_rec, d_out, out_capacity, d_lut, d_result, flags, kMsdFlagFallback, st, out_base);
 }
 
@@ -891,16 +901,80 @@ int bisect_blocks(kmcb200_ctx* ctx, const std::vector<uint64_t>& hist, uint32_t 
 	return 0;
 }
 
-// Expands (filtered), sorts and counts the given key blocks of the device-resident chunks, one after the other, WITHOUT synchronising:
-// records go to d_out behind tot_res[4] records, LUT / statistics are added to tot_lut / tot_res.  The caller zeroes the totals.
+// Expands, sorts and counts the given key blocks of the device-resident chunks, one after the other, WITHOUT synchronising: records go to
+// d_out behind tot_res[4] records, LUT / statistics are added to tot_lut / tot_res.  The caller zeroes the totals.
+//   scatter (the records of all the blocks fit in HBM once, next to one block's scratch): ONE expansion writes every k-mer into the region
+//           of its block inside a bin-wide record buffer, and every block is sorted in place there;
+//   filter  (the records do not fit, or KMCB200_KEY_BLOCKS=filter): every block expands the whole bin again and keeps its own k-mers.
 int run_key_blocks(kmcb200_ctx* ctx, Slot& s, const std::vector<BinChunk>& chunks, const uint64_t* pack_bytes, const std::vector<KeyBlock>& blocks,
 	uint8_t* d_out, uint64_t out_capacity, uint64_t* tot_lut, uint64_t* tot_res, cudaStream_t st)
 {
 	const uint32_t k = ctx->prm.kmer_len;
 	const size_t rec_bytes = (size_t)ctx->words * 8;
-	if (!s.d_out_counter) CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), 8));
-	uint64_t max_n = 0;
-	for (const KeyBlock& b : blocks) max_n = std::max(max_n, b.n);
+	uint64_t max_n = 0, sum_n = 0;
+	for (const KeyBlock& b : blocks) { max_n = std::max(max_n, b.n); sum_n += b.n; }
+	bool scatter = ctx->scatter_blocks && blocks.size() > 1 && blocks.size() <= kExpandMaxBlocks && 2 * k >= 24;
+	if (scatter) {          // does the bin-wide buffer fit next to what a block needs (scratch records, padded leaf output, tables)?
+		size_t free_b = 0, total_b = 0;
+		CU(cudaMemGetInfo(&free_b, &total_b));
+		const uint64_t have = (uint64_t)free_b + s.recs_a_cap + s.recs_b_cap + s.leaf_tmp_cap;          // (the slot's own buffers are re-sized below)
+		const uint64_t need = sum_n * rec_bytes + max_n * (rec_bytes + 8 * ((ctx->suffix_bytes + ctx->counter_bytes + 7) / 8) + 4) + (256ull << 20);
+		scatter = need <= (uint64_t)(0.9 * (double)have);
+	}
+	if (!s.d_out_counter || s.out_counter_cap < blocks.size() + 1) {
+		if (s.d_out_counter) CU(cudaFree(s.d_out_counter));
+		s.d_out_counter = nullptr;
+		s.out_counter_cap = std::max<size_t>(blocks.size() + 1, 64);
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), s.out_counter_cap * 8));
+	}
+	s.last_scatter = scatter;
+	if (scatter) {
+		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, sum_n * rec_bytes)) return rc;          // the bin-wide record buffer
+		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, max_n * rec_bytes)) return rc;          // one block's scratch
+		// block of every 12-bit prefix, first record of every block's region
+		std::vector<uint16_t> h_blk(4096, 0);
+		std::vector<uint64_t> h_reg(blocks.size());
+		uint64_t acc = 0;
+		for (size_t i = 0; i < blocks.size(); ++i) {
+			h_reg[i] = acc; acc += blocks[i].n;
+			const uint32_t lo = blocks[i].prefix << (12 - blocks[i].bits), len = 1u << (12 - blocks[i].bits);
+			for (uint32_t q = lo; q < lo + len; ++q) h_blk[q] = (uint16_t)i;
+		}
+		if (!s.d_blk_of_prefix) CU(cudaMalloc(reinterpret_cast<void**>(&s.d_blk_of_prefix), 4096 * 2));
+		if (!s.d_region_start || s.region_cap < blocks.size()) {
+			if (s.d_region_start) CU(cudaFree(s.d_region_start));
+			s.d_region_start = nullptr;
+			s.region_cap = std::max<size_t>(blocks.size(), 64);
+			CU(cudaMalloc(reinterpret_cast<void**>(&s.d_region_start), s.region_cap * 8));
+		}
+		CU(cudaMemcpyAsync(s.d_blk_of_prefix, h_blk.data(), 4096 * 2, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(s.d_region_start, h_reg.data(), blocks.size() * 8, cudaMemcpyHostToDevice, st));
+		CU(cudaStreamSynchronize(st));          // (the two small host vectors go out of scope)
+		if (int rc = zero_async(ctx, s.d_out_counter, blocks.size() * 8, st)) return rc;
+		ExpandMode es;
+		es.mode = kExpandScatter; es.fshift = 2 * k - 12; es.out_counter = s.d_out_counter;
+		es.blk_of_prefix = s.d_blk_of_prefix; es.region_start = s.d_region_start; es.n_blocks = (uint32_t)blocks.size();
+		for (const BinChunk& c : chunks)
+			if (int rc = stage_expand(ctx, s, s.d_bin + c.dev_off, c.bytes, kExpandUnknownRecs, pack_bytes + c.pack0, c.npacks, s.recs_a, st, es)) return rc;
+		s.ran_expand = false;
+		CU(cudaEventRecord(s.ev_expand, st));
+		for (size_t i = 0; i < blocks.size(); ++i) {
+			const KeyBlock& b = blocks[i];
+			void* region = s.recs_a + h_reg[i] * rec_bytes;
+			if (ctx->use_leaf) {
+				if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, b.n, 1u, d_out, out_capacity, s.d_lut, s.d_result, st, true, b.bits, b.prefix, false, tot_res + 4, region, (void*)s.recs_b)) return rc;
+			} else {
+				bool in_b = false;
+				if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, region, s.recs_b, b.n, ctx->key_bytes, 2u * k - b.bits, (int)kHistNone, 1u, st, &in_b)) return rc;
+				CU(cudaEventRecord(s.ev_sort, st));
+				if (int rc = stage_count(ctx, s, in_b ? (void*)s.recs_b : region, b.n, d_out, out_capacity, s.d_lut, s.d_result, st, false, false, tot_res + 4)) return rc;
+			}
+			accumulate_block_kernel<<<64, 256, 0, st>>>(tot_lut, s.d_lut, ctx->lut_entries, tot_res, s.d_result, s.d_out_counter + i, b.n);
+			ctx->launches++;
+			CU(cudaGetLastError());
+		}
+		return 0;
+	}
 	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, max_n * rec_bytes)) return rc;          // (sized once: no reallocation, no device synchronisation inside the loop)
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, max_n * rec_bytes)) return rc;
 	for (const KeyBlock& b : blocks) {
@@ -957,7 +1031,15 @@ int run_oversized_bin(kmcb200_ctx* ctx, Slot& s, const uint8_t* h_bin, uint64_t 
 		uint64_t total = 0;
 		for (uint64_t v : hist) total += v;
 		if (total != n_rec) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: the bin holds %llu k-mers, not n_rec = %llu", (unsigned long long)total, (unsigned long long)n_rec);
-		if (int rc = bisect_blocks(ctx, hist, 0, 4096, ctx->max_block_records, blocks)) return rc;
+		// key blocks of the preferred size (leaves of 1-2 K records: the leaf kernel's best case) when ONE scattering expansion can serve them
+		// all - i.e. the records fit in HBM once; otherwise as large as one sort can take, because then every block costs an expansion
+		size_t free_b = 0, total_b = 0;
+		CU(cudaMemGetInfo(&free_b, &total_b));
+		const uint64_t rec_b = (uint64_t)ctx->words * 8;
+		const bool fits_once = ctx->scatter_blocks && (double)n_rec * rec_b + (double)ctx->key_block_records * (rec_b + 12) * 1.5 < 0.85 * (double)(free_b + s.recs_a_cap + s.recs_b_cap + s.leaf_tmp_cap);
+		const uint64_t limit = fits_once ? std::min(ctx->max_block_records, ctx->key_block_records) : ctx->max_block_records;
+		if (int rc = bisect_blocks(ctx, hist, 0, 4096, limit, blocks)) return rc;
+		if (blocks.size() > kExpandMaxBlocks) { blocks.clear(); if (int rc = bisect_blocks(ctx, hist, 0, 4096, ctx->max_block_records, blocks)) return rc; }
 	}
 	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
 	if (int rc = ensure(ctx, s.d_out, s.out_cap, out_capacity + 64)) return rc;
@@ -1013,6 +1095,8 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	ctx->sm_count = dp.multiProcessorCount;
 	if (const char* e = getenv("KMCB200_SORT")) ctx->use_msd = std::string(e) != "lsd";
 	if (const char* e = getenv("KMCB200_LEAF")) ctx->use_leaf = std::string(e) != "sort";
+	if (const char* e = getenv("KMCB200_KEY_BLOCKS")) ctx->scatter_blocks = std::string(e) != "filter";
+	if (const char* e = getenv("KMCB200_KEY_BLOCK_RECORDS")) { const long long v = atoll(e); if (v >= 1024) ctx->key_block_records = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_OVERLAP_WALK")) ctx->overlap_walk = atoi(e) != 0;
 	if (const char* e = getenv("KMCB200_EXPAND")) ctx->use_fused = std::string(e) == "fused";
 	{	// one sort needs two record buffers + the leaves' temporary records (8-byte padded) + ~2 bytes per record of tables: what 60 % of the
@@ -1073,7 +1157,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.pdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
-				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter, (void*)s.tot_lut, (void*)s.tot_res, (void*)s.d_extras, (void*)s.d_pack_rec})
+				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter, (void*)s.tot_lut, (void*)s.tot_res, (void*)s.d_extras, (void*)s.d_pack_rec, (void*)s.d_blk_of_prefix, (void*)s.d_region_start})
 			if (p) cudaFree(p);
 		for (auto p : s.h_pack_start) if (p) cudaFreeHost(p);
 		for (auto e : s.ev_pack) if (e) cudaEventDestroy(e);
@@ -1285,7 +1369,13 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 	std::vector<Part> parts(n_ctx);
 	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
 	for (uint32_t g = 0; g < n_ctx; ++g) {
-		if (int rc = bisect_blocks(ctxs[g], hist, cut[g], cut[g + 1], ctxs[g]->max_block_records, parts[g].blocks)) { ctx->err = ctxs[g]->err; return rc; }
+		uint64_t range_n = 0;
+		for (uint32_t q = cut[g]; q < cut[g + 1]; ++q) range_n += hist[q];
+		// (as in run_oversized_bin: small key blocks when one scattering expansion serves them all, i.e. the range's records fit in HBM once)
+		const bool small = ctxs[g]->scatter_blocks && (double)range_n * ctx->words * 8 < 0.5 * 0.6 * 180e9;
+		const uint64_t limit = small ? std::min(ctxs[g]->max_block_records, ctxs[g]->key_block_records) : ctxs[g]->max_block_records;
+		if (int rc = bisect_blocks(ctxs[g], hist, cut[g], cut[g + 1], limit, parts[g].blocks)) { ctx->err = ctxs[g]->err; return rc; }
+		if (parts[g].blocks.size() > kExpandMaxBlocks) { parts[g].blocks.clear(); if (int rc = bisect_blocks(ctxs[g], hist, cut[g], cut[g + 1], ctxs[g]->max_block_records, parts[g].blocks)) { ctx->err = ctxs[g]->err; return rc; } }
 		for (const KeyBlock& b : parts[g].blocks) parts[g].n += b.n;
 		parts[g].cap = ((parts[g].n + 1) / std::max(ctx->prm.cutoff_min, 1u)) * (uint64_t)ob;
 		parts[g].lut.resize(ctx->lut_entries);

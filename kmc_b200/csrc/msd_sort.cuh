@@ -592,11 +592,14 @@ __global__ void __launch_bounds__(MsdLocalCfg<WORDS>::kThreads) msd_local_sort_k
 		const uint64_t lo = p.start[b];
 		const uint32_t m = (uint32_t)(p.start[b + 1] - lo);
 		if (m == 0) continue;
-		// records to registers: warp w owns [w*32*KPT, ...), round r = 32 consecutive records (stable order = index order)
+		// records to registers: warp w owns [w*32*kpt, ...), round r = 32 consecutive records (stable order = index order).  kpt = the rounds
+		// this leaf needs (a leaf of ~1 K records fills 4 of the 16 rounds the capacity allows: the others are skipped, not padded)
+		const uint32_t kpt = (m + THREADS - 1) / THREADS;
 		R key[KPT];
 #pragma unroll
 		for (int r = 0; r < KPT; ++r) {
-			const uint32_t idx = warp * (32 * KPT) + r * 32 + lane;
+			if ((uint32_t)r >= kpt) break;
+			const uint32_t idx = warp * (32 * kpt) + r * 32 + lane;
 			if (idx < m) key[r] = gin[lo + idx];
 			else {
 #pragma unroll
@@ -613,7 +616,8 @@ __global__ void __launch_bounds__(MsdLocalCfg<WORDS>::kThreads) msd_local_sort_k
 				uint32_t dg[KPT];
 #pragma unroll
 				for (int r = 0; r < KPT; ++r) {
-					const uint32_t idx = warp * (32 * KPT) + r * 32 + lane;
+					if ((uint32_t)r >= kpt) break;
+					const uint32_t idx = warp * (32 * kpt) + r * 32 + lane;
 					dg[r] = idx < m ? rec_bits<WORDS>(key[r], shift, mask) : mask;
 					atomicAdd(&wh[dg[r]], 1u);
 				}
@@ -630,9 +634,10 @@ __global__ void __launch_bounds__(MsdLocalCfg<WORDS>::kThreads) msd_local_sort_k
 				__syncthreads();
 				uint32_t peers[KPT];
 #pragma unroll
-				for (int r = 0; r < KPT; ++r) peers[r] = match_digit8(dg[r]);
+				for (int r = 0; r < KPT; ++r) { if ((uint32_t)r >= kpt) break; peers[r] = match_digit8(dg[r]); }
 #pragma unroll
 				for (int r = 0; r < KPT; ++r) {
+					if ((uint32_t)r >= kpt) break;
 					const uint32_t d = dg[r];
 					const uint32_t mm = peers[r];
 					const uint32_t below = __popc(mm & lanemask_lt());
@@ -648,13 +653,14 @@ __global__ void __launch_bounds__(MsdLocalCfg<WORDS>::kThreads) msd_local_sort_k
 				}
 				__syncthreads();
 #pragma unroll
-				for (int r = 0; r < KPT; ++r) key[r] = buf[warp * (32 * KPT) + r * 32 + lane];
+				for (int r = 0; r < KPT; ++r) { if ((uint32_t)r >= kpt) break; key[r] = buf[warp * (32 * kpt) + r * 32 + lane]; }
 				// (the next pass synchronises before it writes to buf again)
 			}
 		}
 #pragma unroll
 		for (int r = 0; r < KPT; ++r) {
-			const uint32_t idx = warp * (32 * KPT) + r * 32 + lane;
+			if ((uint32_t)r >= kpt) break;
+			const uint32_t idx = warp * (32 * kpt) + r * 32 + lane;
 			if (idx < m) gout[lo + idx] = key[r];
 		}
 	}

@@ -56,7 +56,8 @@ with ThreadPoolExecutor(32) as ex:
 print("bin: 2^%d k-mers, %.2f GB of super-k-mer bytes, %d packs" % (lg, sk.size / 1e9, sk.pack_bytes.size), flush=True)
 a, na, ta = run(sk, {})
 print("one shot   : %.1f ms host-to-host (pageable buffers) = %.3g k-mers/s, %d records" % (ta * 1e3, sk.n_rec / ta, na), flush=True)
-b, nb, tb = run(sk, {"KMCB200_MAX_BLOCK_RECORDS": 1 << (lg - 2)})
-same = na == nb and a.stats == b.stats and np.array_equal(a.lut, b.lut) and a.payload.tobytes() == b.payload.tobytes()
-print("key blocks : %.1f ms (<= 2^%d k-mers per block) = %.3g k-mers/s, byte-identical to one shot: %s" % (tb * 1e3, lg - 2, sk.n_rec / tb, same), flush=True)
-assert same
+for flow, blk in (("scatter", lg - 3), ("filter", lg - 2)):
+    b, nb, tb = run(sk, {"KMCB200_MAX_BLOCK_RECORDS": 1 << blk, "KMCB200_KEY_BLOCKS": flow})
+    same = na == nb and a.stats == b.stats and np.array_equal(a.lut, b.lut) and a.payload.tobytes() == b.payload.tobytes()
+    print("key blocks, %-7s: %.1f ms (<= 2^%d k-mers per block) = %.3g k-mers/s, byte-identical to one shot: %s" % (flow, tb * 1e3, blk, sk.n_rec / tb, same), flush=True)
+    assert same

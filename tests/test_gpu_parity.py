@@ -93,12 +93,14 @@ def test_leaf_path_without_duplicates(oracle, k, p_len):
     ctx.close()
 
 
-@pytest.mark.parametrize("k,both,p_len,max_block,max_chunk", [(31, True, 7, 150000, 1 << 18), (55, True, 7, 400000, 1 << 17), (31, False, 3, 1 << 30, 1 << 17), (70, True, 6, 90000, 1 << 18)])
-def test_oversized_bin_in_key_blocks(oracle, monkeypatch, k, both, p_len, max_block, max_chunk):
+@pytest.mark.parametrize("flow", ["scatter", "filter"])
+@pytest.mark.parametrize("k,both,p_len,max_block,max_chunk", [(31, True, 7, 150000, 1 << 18), (55, True, 7, 400000, 1 << 17), (31, False, 3, 1 << 30, 1 << 17), (70, True, 6, 90000, 1 << 18), (31, True, 7, 3000, 1 << 18)])
+def test_oversized_bin_in_key_blocks(oracle, monkeypatch, flow, k, both, p_len, max_block, max_chunk):
     """A bin with more k-mers than one sort may take (or too many bytes): expanded chunk by chunk, counted key block by key block
     (limits lowered through the environment so that ~1.3 M k-mers already need ~10-30 blocks and ~6-12 chunks); the result must not change."""
     monkeypatch.setenv("KMCB200_MAX_BLOCK_RECORDS", str(max_block))
     monkeypatch.setenv("KMCB200_MAX_CHUNK_BYTES", str(max_chunk))
+    monkeypatch.setenv("KMCB200_KEY_BLOCKS", flow)          # scatter: one expansion into per-block regions; filter: one filtered expansion per block
     p = Params(k=k, both_strands=both, cutoff_min=2, lut_prefix_len=p_len)
     _check_bin(oracle, synth_bin(77 + k, k, 110000, genome_len=60000, err=0.01), p)
 
@@ -407,10 +409,12 @@ def test_key_blocks_equal_one_shot_2_27(monkeypatch):
     ctx.close()
     monkeypatch.setenv("KMCB200_MAX_BLOCK_RECORDS", str(1 << 24))
     monkeypatch.setenv("KMCB200_MAX_CHUNK_BYTES", str(1 << 24))
-    ctx = _ctx(p)
-    c = ctx.process_bin(b)
-    ctx.close()
-    assert a.n_total == 1 << 27 and a.stats == c.stats and np.array_equal(a.lut, c.lut) and a.payload.tobytes() == c.payload.tobytes()
+    for flow in ("scatter", "filter"):
+        monkeypatch.setenv("KMCB200_KEY_BLOCKS", flow)
+        ctx = _ctx(p)
+        c = ctx.process_bin(b)
+        ctx.close()
+        assert a.n_total == 1 << 27 and a.stats == c.stats and np.array_equal(a.lut, c.lut) and a.payload.tobytes() == c.payload.tobytes(), flow
 
 
 def test_wrong_n_rec_is_fatal_on_the_device(oracle):
