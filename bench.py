@@ -376,10 +376,12 @@ def secondary_block(kmc_b200, torch, dev, tstream, args, peak):
         out["k31_all_distinct_2^26"] = one(31, 7, distinct, "k=31, one bin of %d k-mers, every k-mer (nearly) distinct: coverage 1, nothing survives ci=2" % n26, 8)
         del distinct
         out["config3_k55_2^28"] = one(55, 7, [gen_bin(3000, 55, n28, ex)], "BASELINE configs[3]: k=55 (two-word records, expanded to plain k-mers), one bin of %d k-mers" % n28, 16, reps=3)
-    # seam #1: the sort alone on 2^26 uniform 62-bit keys (configs[1] literally) - device-resident and through the host-buffer call - vs RADULS alone
-    ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(31, True, CUTOFF_MIN, CUTOFF_MAX, COUNTER_MAX, 7), device=dev.index, n_slots=1)
+    # seam #1: the sort alone on 2^26 uniform 64-bit keys (configs[1] literally: "2^26 packed 64-bit k-mers" = k = 32) - device-resident and
+    # through the host-buffer call - vs RADULS alone.  (Keys that leave the top bits of their key bytes unused make the first MSD level
+    # coarser: seam #1 takes the significant bits from key_bytes, not from k.)
+    ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(32, True, CUTOFF_MIN, CUTOFF_MAX, COUNTER_MAX, 8), device=dev.index, n_slots=1)
     rng = np.random.default_rng(12345)
-    keys = (rng.integers(0, 1 << 62, size=n26, dtype=np.uint64)).reshape(-1, 1)
+    keys = (rng.integers(0, 1 << 63, size=n26, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n26, dtype=np.uint64)).reshape(-1, 1)
     d_a = torch.from_numpy(keys.view(np.int64)).to(dev)
     d_in = torch.empty_like(d_a); d_tmp = torch.empty_like(d_a)
     ms_l = []
@@ -396,7 +398,7 @@ def secondary_block(kmc_b200, torch, dev, tstream, args, peak):
     t0 = time.perf_counter()
     ctx.sort_records(keys, 8)
     t_host = time.perf_counter() - t0
-    sort = {"workload": "kmcb200_dev_sort / kmcb200_sort_records, %d uniform 62-bit keys (8-byte records, 8 key bytes)" % n26,
+    sort = {"workload": "kmcb200_dev_sort / kmcb200_sort_records, %d uniform 64-bit keys (k = 32: 8-byte records, 8 key bytes)" % n26,
             "dev_ms": min(ms_l[1:]), "dev_keys_per_s": n26 / (min(ms_l[1:]) * 1e-3), "host_call_s": t_host, "host_call_keys_per_s": n26 / t_host}
     R = reference_lib()
     if R is not None and not args.no_cpu:

@@ -929,13 +929,14 @@ int run_key_blocks(kmcb200_ctx* ctx, Slot& s, const std::vector<BinChunk>& chunk
 	}
 	s.last_scatter = scatter;
 	if (scatter) {
-		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, sum_n * rec_bytes)) return rc;          // the bin-wide record buffer
+		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, (sum_n + blocks.size() + 2) * rec_bytes)) return rc;          // the bin-wide record buffer (+ the regions' alignment gaps)
 		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, max_n * rec_bytes)) return rc;          // one block's scratch
 		// block of every 12-bit prefix, first record of every block's region
 		std::vector<uint16_t> h_blk(4096, 0);
 		std::vector<uint64_t> h_reg(blocks.size());
 		uint64_t acc = 0;
 		for (size_t i = 0; i < blocks.size(); ++i) {
+			acc = (acc + 1) & ~1ull;          // regions start on even records = 16 bytes: the partition kernel's TMA tile loads need it
 			h_reg[i] = acc; acc += blocks[i].n;
 			const uint32_t lo = blocks[i].prefix << (12 - blocks[i].bits), len = 1u << (12 - blocks[i].bits);
 			for (uint32_t q = lo; q < lo + len; ++q) h_blk[q] = (uint16_t)i;

@@ -182,11 +182,21 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 	for (uint32_t d = tid; d < (uint32_t)NDMAX; d += blockDim.x) hist[d] = 0;
 	__syncthreads();
 
+#ifndef KMCB200_PART_BLOCKED
+#define KMCB200_PART_BLOCKED 0
+#endif
+	// items of a CTA: round robin (0) or one contiguous block of items per CTA (1: the bases of consecutive items of a digit share sectors of the cell scan)
+#if KMCB200_PART_BLOCKED
+	const uint32_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
+	const uint32_t item_begin = min(blockIdx.x * per_cta, n_items), item_end = min(item_begin + per_cta, n_items), item_step = 1;
+#else
+	const uint32_t item_begin = blockIdx.x, item_end = n_items, item_step = gridDim.x;
+#endif
 	if (tid >= (uint32_t)THREADS) {
 		// ---------------------------------------------------------------- producer warp
 		const uint32_t lane = tid & 31u;
 		uint32_t it = 0;
-		for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+		for (uint32_t item = item_begin; item < item_end; item += item_step, ++it) {
 			const uint32_t st = it % STAGES;
 			if (it >= (uint32_t)STAGES) mbar_wait(&empty[st], ((it / STAGES) - 1u) & 1u);      // the consumers are done with this buffer
 			const MsdItemGeom g = msd_item_geom<WORDS>(p.items, item, p.nd);
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 	// -------------------------------------------------------------------- consumers (named barrier 1: the producer is not part of it)
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
 	uint32_t it = 0;
-	for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+	for (uint32_t item = item_begin; item < item_end; item += item_step, ++it) {
 		const uint32_t st = it % STAGES;
 		mbar_wait(&full[st], (it / STAGES) & 1u);
 		const uint32_t head = s_geom[st * 4 + 0], valid = s_geom[st * 4 + 1];
