@@ -500,7 +500,9 @@ __device__ __forceinline__ uint32_t msd_free_bits(const Rec<WORDS>& r, uint32_t 
 	return (uint32_t)v & mask;
 }
 
-template <int WORDS>
+// MODE is a template parameter: the bin path (kExpandAll) must not pay registers / shared memory for the oversized-bin modes
+// (measured: with the scatter code in the same instance the kernel went from 32 to more registers and the expansion from 0.75 to 0.90 ms)
+template <int WORDS, uint32_t MODE = kExpandAll>
 __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(const ExpandArgs a)
 {
 	constexpr int kExpandTile = ExpandCfg<WORDS>::kTile, kExpandThreads = ExpandCfg<WORDS>::kThreads;
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 			return extract_kmer<WORDS>(a.bin + off[j] + 1, s, a.k, a.both_strands != 0,
 				[](uintptr_t wa) { return __ldg(reinterpret_cast<const unsigned long long*>(wa)); });
 		};
-		if (a.mode == kExpandAll) {
+		if constexpr (MODE == kExpandAll) {
 #pragma unroll kExpandUnroll
 			for (int i = 0; i < IPT; ++i) {
 				const uint32_t slot = i * kExpandThreads + tid;
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				htop[tid] = 0;
 			}
 			if (tid == 0) { a.item_lo1[g] = obase; a.item_cnt1[g] = (uint16_t)cnt; }
-		} else if (a.mode == kExpandCount12) {
+		} else if constexpr (MODE == kExpandCount12) {
 			// oversized bin, first pass: where do the k-mers fall?  (top 12 bits; nothing is written)
 			for (int i = 0; i < IPT; ++i) {
 				const uint32_t slot = i * kExpandThreads + tid;
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 					atomicAdd(reinterpret_cast<unsigned long long*>(a.hist12) + msd_free_bits<WORDS>(r, a.fshift, 0xFFFu), 1ull);
 				}
 			}
-		} else if (a.mode == kExpandScatter) {
+		} else if constexpr (MODE == kExpandScatter) {
 			// oversized bin, all key blocks at once: rank inside (tile, block) from a shared-memory counter, one global atomicAdd per
 			// (tile, block) reserves the run inside the block's region, the k-mers are extracted a second time and written there
 			// (holding 8 wide records per thread across the barriers would cost the registers)
@@ -637,8 +639,8 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				const uint32_t slot = i * kExpandThreads + tid;
 				if (slot < cnt) {
 					const Rec<WORDS> r = kmer_of(slot);
-					blk[i] = a.blk_of_prefix[msd_free_bits<WORDS>(r, a.fshift, 0xFFFu)];
-					rnk[i] = (uint16_t)atomicAdd(&s_bcnt[blk[i]], 1u);
+					blk[i] = a.blk_of_prefix[msd_free_bits<WORDS>(r, a.fshift, 0xFFFu)];          // 0xFFFF: not a k-mer of these blocks (another GPU's key range)
+					if (blk[i] != 0xFFFFu) rnk[i] = (uint16_t)atomicAdd(&s_bcnt[blk[i]], 1u);
 				}
 			}
 			__syncthreads();
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 #pragma unroll
 			for (int i = 0; i < IPT; ++i) {
 				const uint32_t slot = i * kExpandThreads + tid;
-				if (slot < cnt) out[s_bbase[blk[i]] + rnk[i]] = kmer_of(slot);
+				if (slot < cnt && blk[i] != 0xFFFFu) out[s_bbase[blk[i]] + rnk[i]] = kmer_of(slot);
 			}
 		} else {
 			// oversized bin, one key block: the k-mers of the block are appended densely (their order does not matter, they get sorted)

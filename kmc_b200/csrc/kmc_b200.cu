@@ -259,7 +259,12 @@ int launch_expand(kmcb200_ctx* ctx, const ExpandArgs& a, cudaStream_t st)
 	const uint64_t n_bound = a.n_rec == kExpandUnknownRecs ? a.size * 4 : a.n_rec;
 	const uint32_t max_tiles = (uint32_t)(n_bound / ExpandCfg<WORDS>::kTile) + a.n_packs + 1;
 	const uint32_t grid = std::min<uint32_t>(max_tiles, (uint32_t)(ctx->sm_count * ctx->occ_expand));
-	expand_kernel<WORDS><<<grid, ExpandCfg<WORDS>::kThreads, 0, st>>>(a);
+	switch (a.mode) {
+	case kExpandAll: expand_kernel<WORDS, kExpandAll><<<grid, ExpandCfg<WORDS>::kThreads, 0, st>>>(a); break;
+	case kExpandCount12: expand_kernel<WORDS, kExpandCount12><<<grid, ExpandCfg<WORDS>::kThreads, 0, st>>>(a); break;
+	case kExpandScatter: expand_kernel<WORDS, kExpandScatter><<<grid, ExpandCfg<WORDS>::kThreads, 0, st>>>(a); break;
+	default: expand_kernel<WORDS, kExpandFilter><<<grid, ExpandCfg<WORDS>::kThreads, 0, st>>>(a); break;
+	}
 	ctx->launches++;
 	CU(cudaGetLastError());
 	return 0;
@@ -932,7 +937,7 @@ int run_key_blocks(kmcb200_ctx* ctx, Slot& s, const std::vector<BinChunk>& chunk
 		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, (sum_n + blocks.size() + 2) * rec_bytes)) return rc;          // the bin-wide record buffer (+ the regions' alignment gaps)
 		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, max_n * rec_bytes)) return rc;          // one block's scratch
 		// block of every 12-bit prefix, first record of every block's region
-		std::vector<uint16_t> h_blk(4096, 0);
+		std::vector<uint16_t> h_blk(4096, (uint16_t)0xFFFF);          // prefixes outside these blocks (another GPU's range): skipped
 		std::vector<uint64_t> h_reg(blocks.size());
 		uint64_t acc = 0;
 		for (size_t i = 0; i < blocks.size(); ++i) {

@@ -182,16 +182,9 @@ __global__ void __launch_bounds__(MsdCfg<WORDS>::kThreads + 32, MsdCfg<WORDS>::k
 	for (uint32_t d = tid; d < (uint32_t)NDMAX; d += blockDim.x) hist[d] = 0;
 	__syncthreads();
 
-#ifndef KMCB200_PART_BLOCKED
-#define KMCB200_PART_BLOCKED 0
-#endif
-	// items of a CTA: round robin (0) or one contiguous block of items per CTA (1: the bases of consecutive items of a digit share sectors of the cell scan)
-#if KMCB200_PART_BLOCKED
-	const uint32_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
-	const uint32_t item_begin = min(blockIdx.x * per_cta, n_items), item_end = min(item_begin + per_cta, n_items), item_step = 1;
-#else
+	// items of a CTA: round robin.  (One contiguous block of items per CTA - so that the bases of consecutive items of a digit share sectors
+	// of the cell scan - measured slower on the B200: 0.53 / 0.55 ms against 0.475 / 0.454 for the two passes of a 1.2e8-record bin.)
 	const uint32_t item_begin = blockIdx.x, item_end = n_items, item_step = gridDim.x;
-#endif
 	if (tid >= (uint32_t)THREADS) {
 		// ---------------------------------------------------------------- producer warp
 		const uint32_t lane = tid & 31u;
