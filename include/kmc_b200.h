@@ -121,10 +121,11 @@ int kmcb200_submit_bin_indexed(kmcb200_ctx* ctx, uint32_t slot, int32_t bin_id,
 
 /* One bin over several GPUs (the reference's analogue is RADULS' team sort of a big bucket, raduls_impl.h:672-745): for a bin
  * that is too large for a fair share of one GPU's time.  ctxs[0..n_ctx) are contexts with identical parameters on different (or, for
- * tests, the same) devices, none with a bin in flight; one host thread per GPU is started inside the call.  GPU 0 receives the bin from
- * the host and counts the top 12 bits; the key space is cut into one contiguous range per GPU; the other GPUs fetch the BIN BYTES
- * (~1.1 B per k-mer, not the records) from GPU 0 by peer copies over NVLink and each expands / sorts / counts its own range.  Outputs
- * are concatenated in key order: byte-identical to kmcb200_process_bin on one GPU. */
+ * tests, the same) devices, none with a bin in flight; one host thread per GPU is started inside the call.  Every GPU gets a contiguous
+ * share of the bin's packs from the host and counts its top 12 bits; the host cuts the key space into one range per GPU and the ranges into
+ * key blocks; every GPU expands its share once, scattering the k-mers by key block; the records are exchanged with peer copies (NVLink:
+ * an all-to-all of 8 B x n_rec x (N-1)/N); every GPU sorts and counts its own blocks.  Outputs are concatenated in key order:
+ * byte-identical to kmcb200_process_bin on one GPU. */
 int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t bin_id,
 	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
 	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* out_bytes, uint64_t* lut, uint64_t stats[4]);

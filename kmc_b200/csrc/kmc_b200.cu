@@ -54,6 +54,7 @@ struct Slot {
 	// records
 	uint8_t* recs_a = nullptr; size_t recs_a_cap = 0;
 	uint8_t* recs_b = nullptr; size_t recs_b_cap = 0;
+	uint8_t* recs_x = nullptr; size_t recs_x_cap = 0;        // kmcb200_process_bin_multi: this GPU's key range, gathered from all GPUs
 	// bin + index
 	uint8_t* d_bin = nullptr; size_t bin_cap = 0;
 	uint64_t* d_pack_start = nullptr; size_t packs_cap = 0;
@@ -836,7 +837,7 @@ __global__ void accumulate_block_kernel(uint64_t* tot_lut, const uint64_t* blk_l
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		tot_res[0] += blk_res[0]; tot_res[1] += blk_res[1]; tot_res[2] += blk_res[2];
 		tot_res[5] |= blk_res[5]; tot_res[7] |= blk_res[7];
-		if (*appended != expected) tot_res[6] |= kErrRecCount;          // the filter took another number of k-mers than the counting pass (or n_rec) said
+		if (appended && *appended != expected) tot_res[6] |= kErrRecCount;          // the filter took another number of k-mers than the counting pass (or n_rec) said
 		tot_res[4] += blk_res[4];                                         // = out_base of the next block
 	}
 }
@@ -906,6 +907,64 @@ int bisect_blocks(kmcb200_ctx* ctx, const std::vector<uint64_t>& hist, uint32_t 
 	return 0;
 }
 
+// one key block whose records already lie in `region` (n records, 16-byte aligned): sort in place with rb as scratch, count, accumulate
+int sort_count_block(kmcb200_ctx* ctx, Slot& s, void* region, void* rb, const KeyBlock& b, uint8_t* d_out, uint64_t out_capacity,
+	uint64_t* tot_lut, uint64_t* tot_res, const unsigned long long* appended, cudaStream_t st)
+{
+	const uint32_t k = ctx->prm.kmer_len;
+	if (ctx->use_leaf) {
+		if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, b.n, 1u, d_out, out_capacity, s.d_lut, s.d_result, st, true, b.bits, b.prefix, false, tot_res + 4, region, rb)) return rc;
+	} else {
+		bool in_b = false;
+		if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, region, rb, b.n, ctx->key_bytes, 2u * k - b.bits, (int)kHistNone, 1u, st, &in_b)) return rc;
+		CU(cudaEventRecord(s.ev_sort, st));
+		if (int rc = stage_count(ctx, s, in_b ? rb : region, b.n, d_out, out_capacity, s.d_lut, s.d_result, st, false, false, tot_res + 4)) return rc;
+	}
+	accumulate_block_kernel<<<64, 256, 0, st>>>(tot_lut, s.d_lut, ctx->lut_entries, tot_res, s.d_result, appended, b.n);
+	ctx->launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+// uploads the tables of a scattering expansion (block of every 12-bit prefix, first record of every block's region) and zeroes the counters
+int setup_scatter(kmcb200_ctx* ctx, Slot& s, const std::vector<KeyBlock>& blocks, const std::vector<uint64_t>& region_start, cudaStream_t st)
+{
+	if (!s.d_out_counter || s.out_counter_cap < blocks.size() + 1) {
+		if (s.d_out_counter) CU(cudaFree(s.d_out_counter));
+		s.d_out_counter = nullptr;
+		s.out_counter_cap = std::max<size_t>(blocks.size() + 1, 64);
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), s.out_counter_cap * 8));
+	}
+	std::vector<uint16_t> h_blk(4096, (uint16_t)0xFFFF);          // prefixes outside these blocks: skipped
+	for (size_t i = 0; i < blocks.size(); ++i) {
+		const uint32_t lo = blocks[i].prefix << (12 - blocks[i].bits), len = 1u << (12 - blocks[i].bits);
+		for (uint32_t q = lo; q < lo + len; ++q) h_blk[q] = (uint16_t)i;
+	}
+	if (!s.d_blk_of_prefix) CU(cudaMalloc(reinterpret_cast<void**>(&s.d_blk_of_prefix), 4096 * 2));
+	if (!s.d_region_start || s.region_cap < blocks.size()) {
+		if (s.d_region_start) CU(cudaFree(s.d_region_start));
+		s.d_region_start = nullptr;
+		s.region_cap = std::max<size_t>(blocks.size(), 64);
+		CU(cudaMalloc(reinterpret_cast<void**>(&s.d_region_start), s.region_cap * 8));
+	}
+	CU(cudaMemcpyAsync(s.d_blk_of_prefix, h_blk.data(), 4096 * 2, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(s.d_region_start, region_start.data(), blocks.size() * 8, cudaMemcpyHostToDevice, st));
+	CU(cudaStreamSynchronize(st));          // (h_blk goes out of scope)
+	return zero_async(ctx, s.d_out_counter, blocks.size() * 8, st);
+}
+
+int scatter_chunks(kmcb200_ctx* ctx, Slot& s, const std::vector<BinChunk>& chunks, const uint64_t* pack_bytes, uint32_t n_blocks, void* dst, cudaStream_t st)
+{
+	ExpandMode es;
+	es.mode = kExpandScatter; es.fshift = 2 * ctx->prm.kmer_len - 12; es.out_counter = s.d_out_counter;
+	es.blk_of_prefix = s.d_blk_of_prefix; es.region_start = s.d_region_start; es.n_blocks = n_blocks;
+	for (const BinChunk& c : chunks)
+		if (int rc = stage_expand(ctx, s, s.d_bin + c.dev_off, c.bytes, kExpandUnknownRecs, pack_bytes + c.pack0, c.npacks, dst, st, es)) return rc;
+	s.ran_expand = false;
+	CU(cudaEventRecord(s.ev_expand, st));
+	return 0;
+}
+
 // Expands, sorts and counts the given key blocks of the device-resident chunks, one after the other, WITHOUT synchronising: records go to
 // d_out behind tot_res[4] records, LUT / statistics are added to tot_lut / tot_res.  The caller zeroes the totals.
 //   scatter (the records of all the blocks fit in HBM once, next to one block's scratch): ONE expansion writes every k-mer into the region
@@ -926,61 +985,23 @@ int run_key_blocks(kmcb200_ctx* ctx, Slot& s, const std::vector<BinChunk>& chunk
 		const uint64_t need = sum_n * rec_bytes + max_n * (rec_bytes + 8 * ((ctx->suffix_bytes + ctx->counter_bytes + 7) / 8) + 4) + (256ull << 20);
 		scatter = need <= (uint64_t)(0.9 * (double)have);
 	}
-	if (!s.d_out_counter || s.out_counter_cap < blocks.size() + 1) {
-		if (s.d_out_counter) CU(cudaFree(s.d_out_counter));
-		s.d_out_counter = nullptr;
-		s.out_counter_cap = std::max<size_t>(blocks.size() + 1, 64);
-		CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), s.out_counter_cap * 8));
-	}
 	s.last_scatter = scatter;
 	if (scatter) {
 		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, (sum_n + blocks.size() + 2) * rec_bytes)) return rc;          // the bin-wide record buffer (+ the regions' alignment gaps)
 		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, max_n * rec_bytes)) return rc;          // one block's scratch
-		// block of every 12-bit prefix, first record of every block's region
-		std::vector<uint16_t> h_blk(4096, (uint16_t)0xFFFF);          // prefixes outside these blocks (another GPU's range): skipped
 		std::vector<uint64_t> h_reg(blocks.size());
 		uint64_t acc = 0;
 		for (size_t i = 0; i < blocks.size(); ++i) {
 			acc = (acc + 1) & ~1ull;          // regions start on even records = 16 bytes: the partition kernel's TMA tile loads need it
 			h_reg[i] = acc; acc += blocks[i].n;
-			const uint32_t lo = blocks[i].prefix << (12 - blocks[i].bits), len = 1u << (12 - blocks[i].bits);
-			for (uint32_t q = lo; q < lo + len; ++q) h_blk[q] = (uint16_t)i;
 		}
-		if (!s.d_blk_of_prefix) CU(cudaMalloc(reinterpret_cast<void**>(&s.d_blk_of_prefix), 4096 * 2));
-		if (!s.d_region_start || s.region_cap < blocks.size()) {
-			if (s.d_region_start) CU(cudaFree(s.d_region_start));
-			s.d_region_start = nullptr;
-			s.region_cap = std::max<size_t>(blocks.size(), 64);
-			CU(cudaMalloc(reinterpret_cast<void**>(&s.d_region_start), s.region_cap * 8));
-		}
-		CU(cudaMemcpyAsync(s.d_blk_of_prefix, h_blk.data(), 4096 * 2, cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(s.d_region_start, h_reg.data(), blocks.size() * 8, cudaMemcpyHostToDevice, st));
-		CU(cudaStreamSynchronize(st));          // (the two small host vectors go out of scope)
-		if (int rc = zero_async(ctx, s.d_out_counter, blocks.size() * 8, st)) return rc;
-		ExpandMode es;
-		es.mode = kExpandScatter; es.fshift = 2 * k - 12; es.out_counter = s.d_out_counter;
-		es.blk_of_prefix = s.d_blk_of_prefix; es.region_start = s.d_region_start; es.n_blocks = (uint32_t)blocks.size();
-		for (const BinChunk& c : chunks)
-			if (int rc = stage_expand(ctx, s, s.d_bin + c.dev_off, c.bytes, kExpandUnknownRecs, pack_bytes + c.pack0, c.npacks, s.recs_a, st, es)) return rc;
-		s.ran_expand = false;
-		CU(cudaEventRecord(s.ev_expand, st));
-		for (size_t i = 0; i < blocks.size(); ++i) {
-			const KeyBlock& b = blocks[i];
-			void* region = s.recs_a + h_reg[i] * rec_bytes;
-			if (ctx->use_leaf) {
-				if (int rc = DISPATCH_WORDS(ctx, run_sort_count_leaves, ctx, s, b.n, 1u, d_out, out_capacity, s.d_lut, s.d_result, st, true, b.bits, b.prefix, false, tot_res + 4, region, (void*)s.recs_b)) return rc;
-			} else {
-				bool in_b = false;
-				if (int rc = DISPATCH_WORDS(ctx, launch_sort, ctx, s, region, s.recs_b, b.n, ctx->key_bytes, 2u * k - b.bits, (int)kHistNone, 1u, st, &in_b)) return rc;
-				CU(cudaEventRecord(s.ev_sort, st));
-				if (int rc = stage_count(ctx, s, in_b ? (void*)s.recs_b : region, b.n, d_out, out_capacity, s.d_lut, s.d_result, st, false, false, tot_res + 4)) return rc;
-			}
-			accumulate_block_kernel<<<64, 256, 0, st>>>(tot_lut, s.d_lut, ctx->lut_entries, tot_res, s.d_result, s.d_out_counter + i, b.n);
-			ctx->launches++;
-			CU(cudaGetLastError());
-		}
+		if (int rc = setup_scatter(ctx, s, blocks, h_reg, st)) return rc;
+		if (int rc = scatter_chunks(ctx, s, chunks, pack_bytes, (uint32_t)blocks.size(), s.recs_a, st)) return rc;
+		for (size_t i = 0; i < blocks.size(); ++i)
+			if (int rc = sort_count_block(ctx, s, s.recs_a + h_reg[i] * rec_bytes, s.recs_b, blocks[i], d_out, out_capacity, tot_lut, tot_res, s.d_out_counter + i, st)) return rc;
 		return 0;
 	}
+	if (!s.d_out_counter) { s.out_counter_cap = 64; CU(cudaMalloc(reinterpret_cast<void**>(&s.d_out_counter), s.out_counter_cap * 8)); }
 	if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, max_n * rec_bytes)) return rc;          // (sized once: no reallocation, no device synchronisation inside the loop)
 	if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, max_n * rec_bytes)) return rc;
 	for (const KeyBlock& b : blocks) {
@@ -1159,7 +1180,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 	cudaSetDevice(ctx->prm.device);
 	cudaDeviceSynchronize();
 	for (auto& s : ctx->slots) {
-		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
+		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.recs_x, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
 				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.pdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
@@ -1326,15 +1347,16 @@ int kmcb200_process_bin(kmcb200_ctx* ctx, int32_t bin_id,
 }
 
 // ---- one bin over several GPUs (the reference's analogue is the big-bucket team sort, raduls_impl.h:672-745)
-// The k-mer space is cut into one contiguous range per GPU (balanced on the 12-bit histogram of a counting expansion); what travels
-// between the GPUs is the BIN BYTES (~1.1 B per k-mer, 8-30x less than the records): GPU 0 gets them from the host, the others by
-// peer copies over NVLink; every GPU then expands with a filter, sorts and counts its own range (key blocks if the range itself is
-// too large), and the per-GPU outputs follow each other in key order - the same bytes as one GPU would produce.
+// Every GPU gets a contiguous SHARE of the bin's packs straight from the host (its own PCIe link), counts the top 12 bits of its share,
+// and - once the host has added the histograms up, cut the key space into one contiguous range per GPU and the ranges into key blocks -
+// expands its share ONCE, scattering every k-mer into the region of its key block.  Then the records are exchanged: every GPU pulls, for
+// each of its own blocks, that block's region from every GPU with peer copies over NVLink (an all-to-all of 8 B x n_rec x (N-1)/N in
+// total, the only inter-GPU traffic of this path), sorts and counts its blocks in place, and the per-GPU outputs follow each other in key
+// order - the same bytes as one GPU would produce.  Expansion, H2D and sort all shrink with the number of GPUs.
 int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t bin_id,
 	const uint8_t* superkmers, uint64_t size, uint64_t n_rec, const uint64_t* pack_bytes, uint32_t n_packs,
 	uint8_t* out_suffix, uint64_t out_capacity, uint64_t* out_bytes, uint64_t* lut, uint64_t stats[4])
 {
-	(void)bin_id;
 	if (!ctxs || n_ctx == 0 || !ctxs[0]) return KMCB200_ERR_INVALID;
 	kmcb200_ctx* ctx = ctxs[0];
 	if (n_ctx > 64) return fail(ctx, KMCB200_ERR_INVALID, "at most 64 contexts");
@@ -1344,23 +1366,62 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 	}
 	if ((size && !superkmers) || !lut || (!out_suffix && out_capacity)) return fail(ctx, KMCB200_ERR_INVALID, "null buffer");
 	const uint32_t k = ctx->prm.kmer_len;
-	if (n_rec == 0 || size == 0 || n_ctx == 1 || 2 * k < 24 || n_rec < 4096ull * n_ctx)          // nothing to split
+	if (n_rec == 0 || size == 0 || n_ctx == 1 || 2 * k < 24 || n_rec < 4096ull * n_ctx || !pack_bytes || n_packs < n_ctx)          // nothing to split
 		return kmcb200_process_bin(ctx, bin_id, superkmers, size, n_rec, n_rec, pack_bytes, nullptr, n_packs, out_suffix, out_capacity, out_bytes, lut, stats);
-	if (int rc = set_device(ctx)) return rc;
-	Slot& s0 = ctx->slots[0];
-	std::vector<BinChunk> chunks;
-	uint64_t dev_bytes = 0;
-	std::vector<uint64_t> one_pack{size};
-	if (!pack_bytes || n_packs == 0) { pack_bytes = one_pack.data(); n_packs = 1; }
-	if (int rc = plan_chunks(ctx, size, pack_bytes, n_packs, chunks, &dev_bytes)) return rc;
-	if (int rc = ensure(ctx, s0.d_bin, s0.bin_cap, dev_bytes + 64)) return rc;
-	for (const BinChunk& c : chunks) CU(cudaMemcpyAsync(s0.d_bin + c.dev_off, superkmers + c.byte0, c.bytes, cudaMemcpyHostToDevice, ctx->compute));
-	std::vector<uint64_t> hist;
-	if (int rc = count_top12(ctx, s0, chunks, pack_bytes, hist, ctx->compute)) return rc;          // (synchronises: the bytes are on GPU 0 now)
+	const size_t rec_bytes = (size_t)ctx->words * 8;
+	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
+
+	struct Part {
+		uint32_t pack0 = 0, npacks = 0; uint64_t byte0 = 0, bytes = 0;          // the share of the bin this GPU expands
+		std::vector<BinChunk> chunks;
+		std::vector<uint64_t> hist;                                               // top 12 bits of the share's k-mers
+		std::vector<uint64_t> src_off;                                            // [blocks] first record of every block's region in the share's scatter buffer
+		std::vector<uint32_t> own;                                                // blocks (global indices) of this GPU's key range, ascending
+		std::vector<uint64_t> dst_off;                                            // [own] first record of the block in the GPU's range buffer
+		uint64_t n_share = 0, n_range = 0, cap = 0, bytes_out = 0;
+		uint64_t r[8] = {};
+		std::vector<uint64_t> lut;
+		int rc = 0;
+		cudaEvent_t ev_scatter = nullptr;
+	};
+	std::vector<Part> parts(n_ctx);
+	{	// contiguous shares of ~size / n_ctx bytes, cut at pack boundaries
+		uint64_t pos = 0;
+		uint32_t g = 0;
+		parts[0].pack0 = 0; parts[0].byte0 = 0;
+		for (uint32_t i = 0; i < n_packs; ++i) {
+			if (g + 1 < n_ctx && parts[g].npacks > 0 && pos >= (uint64_t)(g + 1) * size / n_ctx && n_packs - i >= n_ctx - g - 1) { ++g; parts[g].pack0 = i; parts[g].byte0 = pos; }
+			parts[g].npacks++; parts[g].bytes += pack_bytes[i]; pos += pack_bytes[i];
+		}
+		if (pos != size) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "expander packs cover %llu bytes but the bin has %llu", (unsigned long long)pos, (unsigned long long)size);
+	}
+	auto run_all = [&](auto&& fn) {          // one host thread per GPU
+		std::vector<std::thread> threads;
+		for (uint32_t g = 1; g < n_ctx; ++g) threads.emplace_back([&, g] { parts[g].rc = fn(g); });
+		parts[0].rc = fn(0);
+		for (auto& t : threads) t.join();
+		for (uint32_t g = 0; g < n_ctx; ++g) if (parts[g].rc) { if (g) ctx->err = ctxs[g]->err; return parts[g].rc; }
+		return 0;
+	};
+	// ---- phase A: own share host -> device, counting expansion
+	if (int rc = run_all([&](uint32_t g) -> int {
+		kmcb200_ctx* ctx = ctxs[g];
+		Slot& s = ctx->slots[0];
+		Part& P = parts[g];
+		if (int rc = set_device(ctx)) return rc;
+		if (P.npacks == 0) { P.hist.assign(4096, 0); return 0; }
+		uint64_t dev_bytes = 0;
+		if (int rc = plan_chunks(ctx, P.bytes, pack_bytes + P.pack0, P.npacks, P.chunks, &dev_bytes)) return rc;
+		if (int rc = ensure(ctx, s.d_bin, s.bin_cap, dev_bytes + 64)) return rc;
+		for (const BinChunk& c : P.chunks) CU(cudaMemcpyAsync(s.d_bin + c.dev_off, superkmers + P.byte0 + c.byte0, c.bytes, cudaMemcpyHostToDevice, ctx->compute));
+		return count_top12(ctx, s, P.chunks, pack_bytes + P.pack0, P.hist, ctx->compute);
+	})) return rc;
+	std::vector<uint64_t> hist(4096, 0);
 	uint64_t total = 0;
+	for (uint32_t g = 0; g < n_ctx; ++g) for (uint32_t q = 0; q < 4096; ++q) { hist[q] += parts[g].hist[q]; parts[g].n_share += parts[g].hist[q]; }
 	for (uint64_t v : hist) total += v;
 	if (total != n_rec) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error: the bin holds %llu k-mers, not n_rec = %llu", (unsigned long long)total, (unsigned long long)n_rec);
-	// ---- contiguous ranges of the 4096 prefixes, ~n_rec / n_ctx k-mers each
+	// ---- key ranges (~n_rec / n_ctx k-mers each) and their key blocks
 	std::vector<uint32_t> cut(n_ctx + 1, 4096);
 	cut[0] = 0;
 	{
@@ -1371,61 +1432,107 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 			while (g < n_ctx && acc * n_ctx >= (uint64_t)g * n_rec) cut[g++] = q + 1;
 		}
 	}
-	struct Part { std::vector<KeyBlock> blocks; uint64_t n = 0, cap = 0, bytes = 0; uint64_t r[8] = {}; int rc = 0; std::vector<uint64_t> lut; };
-	std::vector<Part> parts(n_ctx);
-	const uint32_t ob = ctx->suffix_bytes + ctx->counter_bytes;
-	for (uint32_t g = 0; g < n_ctx; ++g) {
-		uint64_t range_n = 0;
-		for (uint32_t q = cut[g]; q < cut[g + 1]; ++q) range_n += hist[q];
-		// (as in run_oversized_bin: small key blocks when one scattering expansion serves them all, i.e. the range's records fit in HBM once)
-		const bool small = ctxs[g]->scatter_blocks && (double)range_n * ctx->words * 8 < 0.5 * 0.6 * 180e9;
-		const uint64_t limit = small ? std::min(ctxs[g]->max_block_records, ctxs[g]->key_block_records) : ctxs[g]->max_block_records;
-		if (int rc = bisect_blocks(ctxs[g], hist, cut[g], cut[g + 1], limit, parts[g].blocks)) { ctx->err = ctxs[g]->err; return rc; }
-		if (parts[g].blocks.size() > kExpandMaxBlocks) { parts[g].blocks.clear(); if (int rc = bisect_blocks(ctxs[g], hist, cut[g], cut[g + 1], ctxs[g]->max_block_records, parts[g].blocks)) { ctx->err = ctxs[g]->err; return rc; } }
-		for (const KeyBlock& b : parts[g].blocks) parts[g].n += b.n;
-		parts[g].cap = ((parts[g].n + 1) / std::max(ctx->prm.cutoff_min, 1u)) * (uint64_t)ob;
-		parts[g].lut.resize(ctx->lut_entries);
+	std::vector<KeyBlock> blocks;          // all GPUs' blocks, ascending
+	std::vector<uint32_t> owner;
+	uint64_t limit = std::min(ctx->max_block_records, ctx->key_block_records);
+	for (int attempt = 0; attempt < 8; ++attempt) {
+		blocks.clear(); owner.clear();
+		for (uint32_t g = 0; g < n_ctx; ++g) {
+			const size_t before = blocks.size();
+			if (int rc = bisect_blocks(ctx, hist, cut[g], cut[g + 1], limit, blocks)) return rc;
+			owner.resize(blocks.size(), g);
+			(void)before;
+		}
+		if (blocks.size() <= kExpandMaxBlocks) break;
+		limit *= 2;                          // too many blocks for one scattering expansion: larger ones
 	}
-	// ---- every GPU on its own host thread: bytes from GPU 0 (peer copy), its key blocks, its totals
-	auto worker = [&](uint32_t g) {
-		kmcb200_ctx* c = ctxs[g];
-		Slot& s = c->slots[0];
+	if (blocks.size() > kExpandMaxBlocks) return fail(ctx, KMCB200_ERR_INVALID, "bin too skewed for %u GPUs: %zu key blocks", n_ctx, blocks.size());
+	for (uint32_t g = 0; g < n_ctx; ++g) {
 		Part& P = parts[g];
-		auto run = [&]() -> int {
-			kmcb200_ctx* ctx = c;          // (CU reports into this context)
-			if (int rc = set_device(c)) return rc;
-			cudaStream_t st = c->compute;
-			if (P.n == 0) return 0;
-			if (g > 0) {
-				if (int rc = ensure(c, s.d_bin, s.bin_cap, dev_bytes + 64)) return rc;
-				if (c->prm.device != ctxs[0]->prm.device) {
-					int can = 0;
-					cudaDeviceCanAccessPeer(&can, c->prm.device, ctxs[0]->prm.device);
-					if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[0]->prm.device, 0); if (e != cudaSuccess) cudaGetLastError(); }      // (already enabled is fine)
-				}
-				CU(cudaMemcpyPeerAsync(s.d_bin, c->prm.device, ctxs[0]->slots[0].d_bin, ctxs[0]->prm.device, dev_bytes, st));
-			}
-			if (int rc = ensure(c, s.d_out, s.out_cap, P.cap + 64)) return rc;
-			if (int rc = ensure_totals(c, s, st)) return rc;
-			if (int rc = run_key_blocks(c, s, chunks, pack_bytes, P.blocks, s.d_out, P.cap, s.tot_lut, s.tot_res, st)) return rc;
-			CU(cudaMemcpyAsync(P.r, s.tot_res, 64, cudaMemcpyDeviceToHost, st));
-			CU(cudaMemcpyAsync(P.lut.data(), s.tot_lut, c->lut_entries * 8, cudaMemcpyDeviceToHost, st));
+		P.src_off.resize(blocks.size());
+		uint64_t acc = 0;
+		for (size_t b = 0; b < blocks.size(); ++b) {
+			uint64_t c = 0;
+			const uint32_t lo = blocks[b].prefix << (12 - blocks[b].bits), len = 1u << (12 - blocks[b].bits);
+			for (uint32_t q = lo; q < lo + len; ++q) c += P.hist[q];
+			P.src_off[b] = acc; acc += c;          // (source regions need no alignment: they are only ever copied from)
+		}
+		acc = 0;
+		for (size_t b = 0; b < blocks.size(); ++b) if (owner[b] == g) {
+			acc = (acc + 1) & ~1ull;
+			P.own.push_back((uint32_t)b); P.dst_off.push_back(acc);
+			acc += blocks[b].n; P.n_range += blocks[b].n;
+		}
+		P.cap = ((P.n_range + 1) / std::max(ctx->prm.cutoff_min, 1u)) * (uint64_t)ob;
+		P.lut.resize(ctx->lut_entries);
+	}
+	auto share_count = [&](uint32_t g, size_t b) { return (b + 1 < blocks.size() ? parts[g].src_off[b + 1] : parts[g].n_share) - parts[g].src_off[b]; };
+	// ---- phase B: every GPU scatters its share into per-block regions (one expansion); buffers of the exchange are sized
+	if (int rc = run_all([&](uint32_t g) -> int {
+		kmcb200_ctx* ctx = ctxs[g];
+		Slot& s = ctx->slots[0];
+		Part& P = parts[g];
+		if (int rc = set_device(ctx)) return rc;
+		cudaStream_t st = ctx->compute;
+		if (!P.ev_scatter) CU(cudaEventCreateWithFlags(&P.ev_scatter, cudaEventDisableTiming));
+		uint64_t max_n = 0;
+		for (uint32_t b : P.own) max_n = std::max(max_n, blocks[b].n);
+		if (int rc = ensure(ctx, s.recs_a, s.recs_a_cap, (P.n_share + 2) * rec_bytes)) return rc;                       // the share, scattered by block
+		if (int rc = ensure(ctx, s.recs_x, s.recs_x_cap, (P.n_range + P.own.size() + 2) * rec_bytes)) return rc;       // the range, block after block
+		if (int rc = ensure(ctx, s.recs_b, s.recs_b_cap, (max_n + 2) * rec_bytes)) return rc;                         // one block's scratch
+		if (int rc = ensure(ctx, s.d_out, s.out_cap, P.cap + 64)) return rc;
+		if (int rc = ensure_totals(ctx, s, st)) return rc;
+		if (P.npacks) {
+			if (int rc = setup_scatter(ctx, s, blocks, P.src_off, st)) return rc;
+			if (int rc = scatter_chunks(ctx, s, P.chunks, pack_bytes + P.pack0, (uint32_t)blocks.size(), s.recs_a, st)) return rc;
+			// (the share must have delivered what its counting pass announced - otherwise the exchange below would copy garbage)
+			std::vector<unsigned long long> got(blocks.size());
+			CU(cudaMemcpyAsync(got.data(), s.d_out_counter, blocks.size() * 8, cudaMemcpyDeviceToHost, st));
 			CU(cudaStreamSynchronize(st));
-			return 0;
-		};
-		P.rc = run();
-	};
-	std::vector<std::thread> threads;
-	for (uint32_t g = 1; g < n_ctx; ++g) threads.emplace_back(worker, g);
-	worker(0);
-	for (auto& t : threads) t.join();
+			for (size_t b = 0; b < blocks.size(); ++b) if (got[b] != share_count(g, b)) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error on GPU %u's share", g);
+		}
+		CU(cudaEventRecord(P.ev_scatter, st));
+		return 0;
+	})) return rc;
+	// ---- phase C: the exchange (every GPU pulls its blocks' regions from every GPU), then sort + count block after block, in place
+	int rc_c = run_all([&](uint32_t h) -> int {
+		kmcb200_ctx* ctx = ctxs[h];
+		Slot& s = ctx->slots[0];
+		Part& P = parts[h];
+		if (int rc = set_device(ctx)) return rc;
+		cudaStream_t st = ctx->compute;
+		for (uint32_t g = 0; g < n_ctx; ++g) if (g != h && ctxs[g]->prm.device != ctx->prm.device) {
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, ctx->prm.device, ctxs[g]->prm.device);
+			if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[g]->prm.device, 0); if (e != cudaSuccess) cudaGetLastError(); }      // (already enabled is fine)
+		}
+		for (uint32_t g = 0; g < n_ctx; ++g) CU(cudaStreamWaitEvent(st, parts[g].ev_scatter, 0));
+		for (size_t i = 0; i < P.own.size(); ++i) {
+			const uint32_t b = P.own[i];
+			uint64_t sub = 0;
+			for (uint32_t g = 0; g < n_ctx; ++g) {
+				const uint64_t c = share_count(g, b);
+				if (c) CU(cudaMemcpyPeerAsync(s.recs_x + (P.dst_off[i] + sub) * rec_bytes, ctx->prm.device,
+					ctxs[g]->slots[0].recs_a + parts[g].src_off[b] * rec_bytes, ctxs[g]->prm.device, c * rec_bytes, st));
+				sub += c;
+			}
+			if (sub != blocks[b].n) return fail(ctx, KMCB200_ERR_CUDA, "internal error: block %u has %llu records, expected %llu", b, (unsigned long long)sub, (unsigned long long)blocks[b].n);
+			if (int rc = sort_count_block(ctx, s, s.recs_x + P.dst_off[i] * rec_bytes, s.recs_b, blocks[b], s.d_out, P.cap, s.tot_lut, s.tot_res, nullptr, st)) return rc;
+		}
+		CU(cudaMemcpyAsync(P.r, s.tot_res, 64, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(P.lut.data(), s.tot_lut, ctx->lut_entries * 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		return 0;
+	});
+	for (uint32_t g = 0; g < n_ctx; ++g) if (parts[g].ev_scatter) { cudaSetDevice(ctxs[g]->prm.device); cudaEventDestroy(parts[g].ev_scatter); }
+	cudaSetDevice(ctx->prm.device);
+	if (rc_c) return rc_c;
 	uint64_t pos = 0, acc[3] = {0, 0, 0};
 	for (uint32_t g = 0; g < n_ctx; ++g) {
-		if (parts[g].rc) { if (g) ctx->err = ctxs[g]->err; return parts[g].rc; }
 		if (parts[g].r[6]) return fail(ctx, KMCB200_ERR_BIN_FORMAT, "bin format error on GPU %u's key range", g);
-		parts[g].bytes = parts[g].r[4] * (uint64_t)ob;
-		if (parts[g].r[5] || pos + parts[g].bytes > out_capacity) return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small", (unsigned long long)out_capacity);
-		pos += parts[g].bytes;
+		parts[g].bytes_out = parts[g].r[4] * (uint64_t)ob;
+		if (parts[g].r[5] || pos + parts[g].bytes_out > out_capacity) return fail(ctx, KMCB200_ERR_CAPACITY, "out_capacity %llu too small", (unsigned long long)out_capacity);
+		pos += parts[g].bytes_out;
 	}
 	// ---- outputs in key order, LUTs and statistics added up
 	pos = 0;
@@ -1433,10 +1540,10 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 	for (uint32_t g = 0; g < n_ctx; ++g) {
 		kmcb200_ctx* c = ctxs[g];
 		cudaSetDevice(c->prm.device);
-		if (parts[g].bytes) { cudaError_t e = cudaMemcpyAsync(out_suffix + pos, c->slots[0].d_out, parts[g].bytes, cudaMemcpyDeviceToHost, c->compute); if (e != cudaSuccess) return fail(ctx, KMCB200_ERR_CUDA, "D2H of GPU %u's records failed: %s", g, cudaGetErrorString(e)); }
-		pos += parts[g].bytes;
+		if (parts[g].bytes_out) { cudaError_t e = cudaMemcpyAsync(out_suffix + pos, c->slots[0].d_out, parts[g].bytes_out, cudaMemcpyDeviceToHost, c->compute); if (e != cudaSuccess) return fail(ctx, KMCB200_ERR_CUDA, "D2H of GPU %u's records failed: %s", g, cudaGetErrorString(e)); }
+		pos += parts[g].bytes_out;
 		for (int i = 0; i < 3; ++i) acc[i] += parts[g].r[i];
-		if (parts[g].n) for (uint64_t i = 0; i < ctx->lut_entries; ++i) lut[i] += parts[g].lut[i];
+		if (parts[g].n_range) for (uint64_t i = 0; i < ctx->lut_entries; ++i) lut[i] += parts[g].lut[i];
 	}
 	for (uint32_t g = 0; g < n_ctx; ++g) { cudaSetDevice(ctxs[g]->prm.device); cudaStreamSynchronize(ctxs[g]->compute); }
 	cudaSetDevice(ctx->prm.device);
