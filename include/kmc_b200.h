@@ -25,6 +25,8 @@
  *   KMCB200_LEAF_ROUND_PCT=n       records per table round in percent of the slots (default 100)
  *   KMCB200_L2_BITS=1..10          bits of the second partition level (default: from the bin size, <= 10)
  *   KMCB200_MAX_BLOCK_RECORDS=n    a bin with more k-mers is counted key block by key block (default: what 60 % of the free HBM holds, < 2^32)
+ *   KMCB200_KEY_BLOCKS=filter     key blocks of an oversized bin re-expand it with a filter (default: one scattering expansion when the records fit in HBM once)
+ *   KMCB200_KEY_BLOCK_RECORDS=n    preferred size of a key block in the scattering flow (default 2^28)
  *   KMCB200_EXPAND=fused           single-pass expansion (expand_fused.cuh) instead of the index-based kernels (measured slower; option)
  *   KMCB200_OVERLAP_WALK=0         index kernels of a submitted bin on the compute stream instead of its copy stream
  *   KMCB200_MAX_CHUNK_BYTES=n      ... and expanded in chunks of at most n bytes (default 2^30)
