@@ -1253,6 +1253,7 @@ static int submit_bin_impl(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* super
 	if (int rc = check_slot(ctx, slot)) return rc;
 	Slot& s = ctx->slots[slot];
 	if (s.busy) return fail(ctx, KMCB200_ERR_BUSY, "slot %u already holds a submitted bin", slot);
+	s.have_extras = false;
 	if ((size && !superkmers) || !lut || (!out_suffix && out_capacity)) return fail(ctx, KMCB200_ERR_INVALID, "null buffer");
 	if (int rc = set_device(ctx)) return rc;
 	if (n_rec > ctx->max_block_records || size >= 4 * ctx->max_chunk_bytes) {        // oversized: counted key block by key block, synchronously
@@ -1467,6 +1468,10 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 		P.lut.resize(ctx->lut_entries);
 	}
 	auto share_count = [&](uint32_t g, size_t b) { return (b + 1 < blocks.size() ? parts[g].src_off[b + 1] : parts[g].n_share) - parts[g].src_off[b]; };
+	auto drop_events = [&]() {
+		for (uint32_t g = 0; g < n_ctx; ++g) if (parts[g].ev_scatter) { cudaSetDevice(ctxs[g]->prm.device); cudaStreamSynchronize(ctxs[g]->compute); cudaEventDestroy(parts[g].ev_scatter); parts[g].ev_scatter = nullptr; }
+		cudaSetDevice(ctx->prm.device);
+	};
 	// ---- phase B: every GPU scatters its share into per-block regions (one expansion); buffers of the exchange are sized
 	if (int rc = run_all([&](uint32_t g) -> int {
 		kmcb200_ctx* ctx = ctxs[g];
@@ -1493,7 +1498,7 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 		}
 		CU(cudaEventRecord(P.ev_scatter, st));
 		return 0;
-	})) return rc;
+	})) { drop_events(); return rc; }
 	// ---- phase C: the exchange (every GPU pulls its blocks' regions from every GPU), then sort + count block after block, in place
 	int rc_c = run_all([&](uint32_t h) -> int {
 		kmcb200_ctx* ctx = ctxs[h];
@@ -1524,8 +1529,7 @@ int kmcb200_process_bin_multi(kmcb200_ctx* const* ctxs, uint32_t n_ctx, int32_t 
 		CU(cudaStreamSynchronize(st));
 		return 0;
 	});
-	for (uint32_t g = 0; g < n_ctx; ++g) if (parts[g].ev_scatter) { cudaSetDevice(ctxs[g]->prm.device); cudaEventDestroy(parts[g].ev_scatter); }
-	cudaSetDevice(ctx->prm.device);
+	drop_events();          // (also waits for every GPU: nobody still copies out of a neighbour's scatter buffer)
 	if (rc_c) return rc_c;
 	uint64_t pos = 0, acc[3] = {0, 0, 0};
 	for (uint32_t g = 0; g < n_ctx; ++g) {
@@ -1580,6 +1584,7 @@ int kmcb200_dev_process_bin(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_su
 	if (int rc = check_slot(ctx, slot)) return rc;
 	if (int rc = set_device(ctx)) return rc;
 	Slot& s = ctx->slots[slot];
+	s.have_extras = false;          // (a length-byte array of an earlier kmcb200_submit_bin_indexed on this slot does not describe this bin)
 	return run_bin(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_out, out_capacity, d_lut, d_result, stream ? (cudaStream_t)stream : ctx->compute);
 }
 
@@ -1591,6 +1596,7 @@ int kmcb200_dev_expand(kmcb200_ctx* ctx, uint32_t slot, const uint8_t* d_superkm
 	Slot& s = ctx->slots[slot];
 	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
 	if (n_rec == 0) return 0;
+	s.have_extras = false;
 	CU(cudaEventRecord(s.ev_begin, st));
 	if (int rc = stage_expand(ctx, s, d_superkmers, size, n_rec, pack_bytes, n_packs, d_recs, st)) return rc;
 	if (d_result) {
