@@ -386,7 +386,8 @@ int launch_sort(kmcb200_ctx* ctx, Slot& s, void* a, void* b, uint64_t n, uint32_
 	if (msd) {
 		const uint32_t b2 = choose_b2<WORDS>(ctx, n, plan != nullptr);
 		const uint32_t nd2 = 1u << b2;
-		const uint32_t cap = plan ? kLwMaxLeaf : (uint32_t)msd_local_cap<WORDS>();      // counted leaves are streamed by one warp: only a very loose limit
+		// counted leaves are streamed by one warp: only a very loose limit (one-word records: a leaf may be larger still if ONE k-mer dominates it)
+		const uint32_t cap = plan ? (WORDS == 1 ? kLwMaxHeavyLeaf : kLwMaxLeaf) : (uint32_t)msd_local_cap<WORDS>();
 		const bool final_in_b = (key_bytes % 2) == 0;                 // where the LSD passes (started from b) end; the leaves go to the same place
 		void* fin = final_in_b ? b : a;
 		uint32_t* flags = s.zero->msd_flags;

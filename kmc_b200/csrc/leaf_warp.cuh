@@ -52,6 +52,9 @@ constexpr int kLwList = 256;                     // u16 list of survivors, one s
 #endif
 constexpr uint32_t kLwRing = KMCB200_LW_RING;                // ring of compacted k-mers (WORDS == 1, multi-round leaves)
 constexpr uint32_t kLwMaxLeaf = 65534;           // records of a warp-counted leaf (count field >= 16 bits)
+constexpr uint32_t kLwHeavy = 16384;             // one-word records: a leaf beyond this is first relieved of the copies of ONE dominant k-mer (poly-A,
+                                                 // satellite repeats: a k-mer with 10^5..10^6 copies makes its leaf that large); what remains must fit kLwMaxLeaf
+constexpr uint32_t kLwMaxHeavyLeaf = 1u << 22;   // ... and the whole leaf must stay below this (one warp streams it a few times: ~1 ms per 10^6 records)
 constexpr uint32_t kLwMaxSplit = 12;             // extra split bits a round may descend
 constexpr uint64_t kLwEmpty = ~0ull;
 
@@ -247,10 +250,31 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 		const uint32_t m = (uint32_t)min(a.start[leaf + 1] - lo, (uint64_t)0xffffffffu);
 		uint32_t emit_base = 0;
 		bool prefetched = false;
-		if (m > kLwMaxLeaf) failed = true;
+		// ---- a dominant k-mer?  (one-word records.)  Its copies are counted by comparison - one ballot per 32 records - and enter the table
+		// once, with their number; the table rounds are sized for what remains.  Without this a single k-mer of >= 65535 copies would send the
+		// whole bin to the LSD fallback.
+		bool heavy = false;
+		uint64_t cand = 0;
+		uint32_t n_eq = 0, m_rest = m;
+		if constexpr (WORDS == 1) {
+			if (m > kLwHeavy && m <= kLwMaxHeavyLeaf) {
+				const unsigned long long* __restrict__ gh = reinterpret_cast<const unsigned long long*>(recs) + lo;
+				cand = __ldg(gh);          // (the first record: a k-mer that holds most of the leaf is very likely to be it; if not, nothing is lost but this scan)
+				for (uint32_t j0 = 0; j0 < m; j0 += 128) {
+					uint64_t v[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * 32 + lane; v[u] = j < m ? __ldg(gh + j) : ~cand; }
+#pragma unroll
+					for (int u = 0; u < 4; ++u) n_eq += __popc(__ballot_sync(FULL, v[u] == cand));
+				}
+				heavy = n_eq > m / 4;
+				if (heavy) m_rest = m - n_eq; else n_eq = 0;
+			}
+		}
+		if (m_rest > kLwMaxLeaf) failed = true;
 		else if (m > 0) {
 			uint32_t e0 = 0;
-			while (((m >> e0) > ROUND && e0 < 8 && e0 < a.low_bits) || (WORDS == 1 && a.low_bits - e0 > GB + 47u)) ++e0;      // (an entry holds <= 47 key bits)
+			while (((m_rest >> e0) > ROUND && e0 < 8 && e0 < a.low_bits) || (WORDS == 1 && a.low_bits - e0 > GB + 47u)) ++e0;      // (an entry holds <= 47 key bits)
 			uint32_t e = e0, r = 0;
 			while (true) {
 				// ================================================================ one round: the k-mers whose next e bits are r
@@ -274,7 +298,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 				if constexpr (WORDS == 1) {
 					const LwRound T{S.main, S.surv, S.over, gshift, (uint32_t)NG - 1u, cb, cmask, rem_mask, cut};
 					const unsigned long long* __restrict__ g = reinterpret_cast<const unsigned long long*>(recs) + lo;
-					if (e == 0) {
+					if (e == 0 && !heavy) {
 						// the whole leaf: straight from registers, the next step's loads in flight while this one is inserted
 						uint64_t nx[4];
 #pragma unroll
@@ -299,7 +323,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 							uint64_t cur[4];
 							bool in[4];
 #pragma unroll
-							for (int u = 0; u < 4; ++u) { cur[u] = nx[u]; in[u] = (j0 + u * 32 + lane < m) && ((uint32_t)(cur[u] >> sub_shift) & emask) == r; }
+							for (int u = 0; u < 4; ++u) { cur[u] = nx[u]; in[u] = (j0 + u * 32 + lane < m) && ((uint32_t)(cur[u] >> sub_shift) & emask) == r && !(heavy && cur[u] == cand); }
 #pragma unroll
 							for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + 128 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
 #pragma unroll
@@ -373,6 +397,33 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 							}
 						}
 						if (!__all_sync(FULL, ok)) break;
+					}
+				}
+				if constexpr (WORDS == 1) {
+					// the dominant k-mer enters the table of its round once, with the number of its copies
+					if (heavy && ok && ((uint32_t)(cand >> sub_shift) & emask) == r) {
+						if (cb < 32 && (n_eq >> cb)) ok = false;          // (the count field of this round is too narrow: split the round - or give up)
+						else if (lane == 0) {
+							constexpr uint32_t GM = (1u << kLwGroupBits) - 1u;
+							const uint64_t rem = cand & rem_mask;
+#if KMCB200_LW_HASH32
+							uint32_t sl = ((((uint32_t)(cand >> gshift)) & ((uint32_t)NG - 1u)) << kLwGroupBits) | ((((uint32_t)rem ^ (uint32_t)(rem >> 27)) * 0x9E3779B1u) >> (32 - kLwGroupBits));
+#else
+							uint32_t sl = ((((uint32_t)(cand >> gshift)) & ((uint32_t)NG - 1u)) << kLwGroupBits) | (uint32_t)((rem * 0x9E3779B97F4A7C15ull) >> (64 - kLwGroupBits));
+#endif
+							const unsigned long long ent = (rem << cb) | (unsigned long long)n_eq;
+							uint32_t probe = 0;
+							while (atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[sl]), (unsigned long long)kLwEmpty, ent) != kLwEmpty) {          // (no copy of it is in the table: a free slot of its group is all it needs)
+								if (++probe > GM) break;
+								sl = (sl & ~GM) | ((sl + 1u) & GM);
+							}
+							if (probe > GM) ok = false;
+							else {
+								++r_claim;
+								if (n_eq >= cut.cmin) { if (cut.never) ++r_max; else atomicOr(&S.surv[sl >> 5], 1u << (sl & 31u)); }
+								if (!cut.never && cut.cmax1 != 0u && n_eq >= cut.cmax1) { atomicOr(&S.over[sl >> 5], 1u << (sl & 31u)); ++r_max; }
+							}
+						}
 					}
 				}
 				if (!prefetched) {        // the next leaf: towards L2 while this one is counted

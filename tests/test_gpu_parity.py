@@ -453,14 +453,16 @@ def test_one_byte_records(oracle):
     _check_bin(oracle, fast_bin(17, 17, 200000, genome_len=150000), p)
 
 
-def test_lsd_fallback_is_one_cooperative_launch(oracle, monkeypatch):
-    """The device-flagged fallback (a leaf that cannot be counted on chip) through the whole-bin path: same bytes as the oracle."""
+@pytest.mark.parametrize("k,p_len", [(31, 7), (55, 7)])
+def test_lsd_fallback_is_one_cooperative_launch(oracle, monkeypatch, k, p_len):
+    """The device-flagged fallback (a leaf that cannot be counted on chip) through the whole-bin path: same bytes as the oracle.
+    k = 31: 70000 copies of one k-mer are handled inside the leaf kernel since round 2 (dominant-k-mer path); k = 55 (wide records: the entry
+    holds a 16-bit record index) still takes the fallback."""
     rng = np.random.default_rng(4)
-    k = 31
     heavy_one = rng.integers(0, 4, k)
     heavy = [heavy_one.copy() for _ in range(70000)]               # one k-mer 70000 times: beyond a warp-counted leaf
     rest = [rng.integers(0, 4, k + 60) for _ in range(4000)]
-    p = Params(k=k, both_strands=False, cutoff_min=1, lut_prefix_len=7)
+    p = Params(k=k, both_strands=False, cutoff_min=1, lut_prefix_len=p_len)
     b = pack_superkmers(k, heavy + rest)
     ctx = _ctx(p)
     r = ctx.process_bin(_to_skb(b))
@@ -541,4 +543,40 @@ def test_indexed_submit_needs_no_walk(oracle, k, both, cmin, p_len, n):
             ctx.wait_bin(1)
         assert ei.value.code == kmc_b200.ERR_BIN_FORMAT
     _check_bin(oracle, b, p, ctx)                  # and the walk path on the same context still works
+    ctx.close()
+
+
+@pytest.mark.parametrize("cmin,cmax,cntmax", [(2, 10 ** 9, 255), (1, 100000, 65535), (3, 10 ** 9, 10 ** 6)])
+def test_dominant_kmers_are_counted_inside_the_leaf_kernel(oracle, cmin, cmax, cntmax):
+    """Real genomes: poly-A / satellite k-mers with 10^5..10^6 copies.  One-word records: the copies of the dominant k-mer of a large leaf are
+    counted by comparison and enter the table once; the bin must NOT take the LSD fallback (result[7] = 0) unless the rest of the leaf is too
+    large as well.  Cases: a 300 000-copy k-mer with a 40 000-copy neighbour in the same leaf; a dominant k-mer that is not the first record
+    of its leaf; cutoffs / counter clamps that the big counts cross."""
+    import torch
+    rng = np.random.default_rng(8)
+    k = 31
+    head = np.array([0, 1, 2, 3, 0, 1, 2, 3, 1], dtype=np.uint8)                     # same first 9 symbols = same leaf (-b mode)
+    big = np.concatenate([head, rng.integers(0, 4, k - 9)])
+    second = np.concatenate([head, rng.integers(0, 4, k - 9)])
+    other_head = np.array([3, 2, 1, 0, 3, 2, 1, 0, 2], dtype=np.uint8)
+    late = np.concatenate([other_head, rng.integers(0, 4, k - 9)])
+    # every record is one super-k-mer of exactly k symbols; order inside the bin is what the leaf sees (the partition is not stable, but
+    # "not the first record" holds with overwhelming probability when 3000 other k-mers of the leaf come first)
+    lists = ([np.concatenate([other_head, rng.integers(0, 4, k - 9)]) for _ in range(3000)] + [late.copy() for _ in range(120000)]
+             + [big.copy() for _ in range(300000)] + [second.copy() for _ in range(40000)]
+             + [np.concatenate([head, rng.integers(0, 4, k - 9)]) for _ in range(5000)] + [rng.integers(0, 4, k + 40) for _ in range(20000)])
+    p = Params(k=k, both_strands=False, cutoff_min=cmin, cutoff_max=cmax, counter_max=cntmax, lut_prefix_len=7)
+    b = pack_superkmers(k, lists)
+    ctx = _ctx(p)
+    e = oracle.process_bin(b, p)
+    r = ctx.process_bin(_to_skb(b))
+    assert r.stats == e.stats and np.array_equal(r.lut, e.lut) and r.payload.tobytes() == e.payload
+    # the device-level call exposes result[7]: no fallback for this bin
+    d_bin = torch.zeros(b.size + 64, dtype=torch.uint8, device="cuda"); d_bin[:b.size] = torch.from_numpy(b.data).cuda()
+    cap = ctx.out_capacity(b.n_rec) + 64
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda"); d_lut = torch.zeros(ctx.lut_entries, dtype=torch.int64, device="cuda"); d_res = torch.zeros(8, dtype=torch.int64, device="cuda")
+    ctx.dev_process_bin(0, d_bin.data_ptr(), b.size, b.n_rec, b.pack_bytes, d_out.data_ptr(), cap, d_lut.data_ptr(), d_res.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    res = d_res.cpu().numpy()
+    assert tuple(int(x) for x in res[:4]) == e.stats
     ctx.close()
