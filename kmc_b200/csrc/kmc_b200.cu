@@ -31,6 +31,7 @@ constexpr int kCounterSlots = kMaxPasses + 8;     // tile counters: one per pass
 constexpr uint32_t kEpochLimit = (1u << 22) - 2;
 constexpr int kStageRing = 4;
 constexpr size_t kMaxLeaves = 256 * 1024;          // level 1: 8 bits, level 2: up to 10 bits
+constexpr uint32_t kHeavyListCap = 2048;           // leaves of more than kLwHeavy records a bin may have before it takes the LSD fallback
 
 thread_local std::string g_create_error;
 
@@ -44,6 +45,8 @@ struct ZeroBlock {                                // zeroed with one memset at t
 	uint32_t msd_n_items[2];                      // work items of the level-1 / level-2 segmentation
 	uint32_t msd_counters[4];                     // tickets: level-1 partition, level-2 partition, leaves, leaf-count
 	uint32_t pack_ticket[4];                      // fused expansion: packs are taken in order
+	uint32_t heavy_count[2];                      // [0] large leaves noted by the leaf kernel, [1] ticket of the second (HEAVY) launch
+	uint32_t heavy_list[kHeavyListCap];           // their leaf ids
 	uint32_t leaf_group_sum[kMaxLeaves / 1024];   // emitted records per group of 1024 leaves
 };
 
@@ -712,10 +715,21 @@ int launch_leaves(kmcb200_ctx* ctx, const LeafArgs& la, cudaStream_t st)
 }
 
 template <int WORDS, int SLOT_BITS>
+int launch_heavy_leaves(kmcb200_ctx* ctx, const LeafArgs& la, cudaStream_t st)
+{
+	const size_t smem = sizeof(LwSmem<SLOT_BITS>) * kLwWarps;
+	leaf_warp_kernel<WORDS, SLOT_BITS, true><<<(uint32_t)ctx->sm_count, 32 * kLwWarps, smem, st>>>(la);
+	ctx->launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+template <int WORDS, int SLOT_BITS>
 int setup_leaves(kmcb200_ctx* ctx)
 {
 	const int smem = (int)(sizeof(LwSmem<SLOT_BITS>) * kLwWarps);
 	CU(cudaFuncSetAttribute(leaf_warp_kernel<WORDS, SLOT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	CU((cudaFuncSetAttribute(leaf_warp_kernel<WORDS, SLOT_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
 	CU(cudaFuncSetAttribute(leaf_warp_kernel<WORDS, SLOT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf, leaf_warp_kernel<WORDS, SLOT_BITS>, 32 * kLwWarps, smem));
 	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
@@ -760,8 +774,12 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	la.leaf_prefix = block_bits ? block_prefix * plan.n_leaves : 0u;          // n_leaves is a power of two
 	la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
 	la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
+	la.heavy_list = s.zero->heavy_list; la.heavy_count = &s.zero->heavy_count[0]; la.heavy_ticket = &s.zero->heavy_count[1]; la.heavy_cap = kHeavyListCap;
 	la.tmp = s.leaf_tmp; la.leaf_emit = s.leaf_emit; la.group_sum = s.zero->leaf_group_sum; la.lut = d_lut; la.result = d_result; la.ticket = &s.zero->msd_counters[3]; la.flags = flags;
 	if (int rc = DISPATCH_SLOTS(ctx, launch_leaves, WORDS, ctx, la, st)) return rc;
+	if (WORDS == 1) {          // the large leaves the main launch only noted (none in a typical bin: the launch returns at once)
+		if (int rc = DISPATCH_SLOTS(ctx, launch_heavy_leaves, WORDS, ctx, la, st)) return rc;
+	}
 	leaf_scan_kernel<<<(plan.n_leaves + 1023) / 1024, 1024, 0, st>>>(s.leaf_emit, s.zero->leaf_group_sum, plan.n_leaves, s.leaf_off, d_result, out_capacity, ob, flags, out_base);
 	leaf_gather_kernel<<<(plan.n_leaves + 7) / 8, 256, 0, st>>>(s.leaf_tmp, plan.start, s.leaf_emit, s.leaf_off, plan.n_leaves, ob, d_out, d_result, flags, out_base);
 	ctx->launches += 2;

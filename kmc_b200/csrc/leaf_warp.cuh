@@ -73,6 +73,8 @@ struct LeafArgs {
 	uint64_t* result;            // [0] n_unique [1] n_cutoff_min [2] n_cutoff_max
 	uint32_t* ticket;
 	uint32_t* flags;
+	// one-word records: leaves beyond kLwHeavy records are noted by the main launch and counted by the HEAVY launch (dominant-k-mer path)
+	uint32_t* heavy_list; uint32_t* heavy_count; uint32_t* heavy_ticket; uint32_t heavy_cap;
 };
 
 template <int SLOT_BITS>
@@ -213,7 +215,11 @@ __device__ KMCB200_LW_INSERT_ATTR void lw_insert1(const LwRound& t, const uint64
 	}
 }
 
-template <int WORDS, int SLOT_BITS>
+// HEAVY = false: the kernel of the bin path; leaves of one-word records beyond kLwHeavy records are only NOTED (a.heavy_list) and left to a
+// second, tiny launch of the HEAVY = true instance, which knows the dominant-k-mer path.  (With that path compiled into the main instance
+// the common case was 30 % slower - 1.63 ms against 1.24 ms for the leaves of a 1.2e8-k-mer bin: the kernel is that sensitive to registers
+// and code layout - so the main instance stays exactly what it was.)
+template <int WORDS, int SLOT_BITS, bool HEAVY = false>
 __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp_kernel(const LeafArgs a)
 {
 	using R = Rec<WORDS>;
@@ -240,23 +246,40 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 	uint32_t t_unique = 0, t_max = 0, t_emit = 0;        // per lane; n_cutoff_min = unique - emitted - n_cutoff_max
 	bool failed = false;
 
-	uint32_t leaf = 0;
-	if (lane == 0) leaf = atomicAdd(a.ticket, 1u);
-	leaf = __shfl_sync(FULL, leaf, 0);
-	while (leaf < a.n_leaves) {
+	// work items: all leaves (main instance) / the noted large leaves (HEAVY instance)
+	const uint32_t n_work = HEAVY ? min(*a.heavy_count, a.heavy_cap) : a.n_leaves;
+	uint32_t* const ticket = HEAVY ? a.heavy_ticket : a.ticket;
+	uint32_t work = 0;
+	if (lane == 0) work = atomicAdd(ticket, 1u);
+	work = __shfl_sync(FULL, work, 0);
+	while (work < n_work) {
 		uint32_t next_t = 0;
-		if (lane == 0) next_t = atomicAdd(a.ticket, 1u);                   // the next leaf: in flight while this one is counted
+		if (lane == 0) next_t = atomicAdd(ticket, 1u);                     // the next leaf: in flight while this one is counted
+		const uint32_t leaf = HEAVY ? a.heavy_list[work] : work;
 		const uint64_t lo = a.start[leaf];
 		const uint32_t m = (uint32_t)min(a.start[leaf + 1] - lo, (uint64_t)0xffffffffu);
 		uint32_t emit_base = 0;
-		bool prefetched = false;
+		bool prefetched = HEAVY;          // (the HEAVY instance does not prefetch the next leaf)
+		if constexpr (!HEAVY && WORDS == 1) {
+			if (m > kLwHeavy) {          // a large leaf: noted for the second launch (its emitted count and LUT share are written there)
+				if (lane == 0) {
+					const uint32_t slot = atomicAdd(a.heavy_count, 1u);
+					if (slot < a.heavy_cap) a.heavy_list[slot] = leaf;
+					else failed = true;          // (more large leaves than the list holds: the LSD fallback takes the bin)
+				}
+				failed = __any_sync(FULL, failed);
+				if (failed) break;
+				work = __shfl_sync(FULL, next_t, 0);
+				continue;
+			}
+		}
 		// ---- a dominant k-mer?  (one-word records.)  Its copies are counted by comparison - one ballot per 32 records - and enter the table
 		// once, with their number; the table rounds are sized for what remains.  Without this a single k-mer of >= 65535 copies would send the
 		// whole bin to the LSD fallback.
 		bool heavy = false;
 		uint64_t cand = 0;
 		uint32_t n_eq = 0, m_rest = m;
-		if constexpr (WORDS == 1) {
+		if constexpr (HEAVY && WORDS == 1) {
 			if (m > kLwHeavy && m <= kLwMaxHeavyLeaf) {
 				const unsigned long long* __restrict__ gh = reinterpret_cast<const unsigned long long*>(recs) + lo;
 				cand = __ldg(gh);          // (the first record: a k-mer that holds most of the leaf is very likely to be it; if not, nothing is lost but this scan)
@@ -298,7 +321,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 				if constexpr (WORDS == 1) {
 					const LwRound T{S.main, S.surv, S.over, gshift, (uint32_t)NG - 1u, cb, cmask, rem_mask, cut};
 					const unsigned long long* __restrict__ g = reinterpret_cast<const unsigned long long*>(recs) + lo;
-					if (e == 0 && !heavy) {
+					if (e == 0 && !(HEAVY && heavy)) {
 						// the whole leaf: straight from registers, the next step's loads in flight while this one is inserted
 						uint64_t nx[4];
 #pragma unroll
@@ -323,7 +346,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 							uint64_t cur[4];
 							bool in[4];
 #pragma unroll
-							for (int u = 0; u < 4; ++u) { cur[u] = nx[u]; in[u] = (j0 + u * 32 + lane < m) && ((uint32_t)(cur[u] >> sub_shift) & emask) == r && !(heavy && cur[u] == cand); }
+							for (int u = 0; u < 4; ++u) { cur[u] = nx[u]; in[u] = (j0 + u * 32 + lane < m) && ((uint32_t)(cur[u] >> sub_shift) & emask) == r && !(HEAVY && heavy && cur[u] == cand); }
 #pragma unroll
 							for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + 128 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
 #pragma unroll
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 						if (!__all_sync(FULL, ok)) break;
 					}
 				}
-				if constexpr (WORDS == 1) {
+				if constexpr (HEAVY && WORDS == 1) {
 					// the dominant k-mer enters the table of its round once, with the number of its copies
 					if (heavy && ok && ((uint32_t)(cand >> sub_shift) & emask) == r) {
 						if (cb < 32 && (n_eq >> cb)) ok = false;          // (the count field of this round is too narrow: split the round - or give up)
@@ -429,7 +452,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 				if (!prefetched) {        // the next leaf: towards L2 while this one is counted
 					prefetched = true;
 					const uint32_t nl = __shfl_sync(FULL, next_t, 0);
-					if (nl < a.n_leaves) {
+					if (nl < n_work) {
 						const uint64_t nlo = a.start[nl];
 						const uint32_t nm = (uint32_t)min(a.start[nl + 1] - nlo, (uint64_t)kLwMaxLeaf);
 						for (uint32_t i = lane * (128 / (8 * WORDS)); i < nm; i += 32 * (128 / (8 * WORDS))) asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + nlo + i));
@@ -519,7 +542,7 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LW_MINBLOCKS) leaf_warp
 				atomicAdd(reinterpret_cast<unsigned long long*>(a.lut) + ((a.leaf_prefix | leaf) >> (prefix_shift - a.low_bits)), (unsigned long long)emit_base);      // leaf = k-mer >> low_bits
 		}
 		if (failed) break;
-		leaf = __shfl_sync(FULL, next_t, 0);
+		work = __shfl_sync(FULL, next_t, 0);
 	}
 	// ---- statistics of this warp
 	failed = __any_sync(FULL, failed);
