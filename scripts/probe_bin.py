@@ -10,8 +10,18 @@ n_rec = int(sys.argv[1]) if len(sys.argv) > 1 else 117440512
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 31
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 ctx = kmc_b200.Stage2Context(kmc_b200.Stage2Params(k, True, 2, 10 ** 9, 255, 7), device=0, n_slots=1)
-with ThreadPoolExecutor(16) as ex:
-    hb = bench.gen_bin(4004, k, n_rec, ex)
+_cache = "/dev/shm/probe_bin_%d_%d.npz" % (n_rec, k)          # (several runs of one gpurun call share the generated bin)
+if os.path.exists(_cache):
+    from kmc_testlib import Bin
+    z = np.load(_cache)
+    hb = Bin(data=z["data"], n_rec=n_rec, n_super_kmers=int(z["nsk"]), pack_bytes=z["pack_bytes"], pack_recs=z["pack_recs"], k=k)
+else:
+    with ThreadPoolExecutor(32) as ex:
+        hb = bench.gen_bin(4004, k, n_rec, ex)
+    try:
+        np.savez(_cache, data=hb.data, nsk=hb.n_super_kmers, pack_bytes=hb.pack_bytes, pack_recs=hb.pack_recs)
+    except OSError:
+        pass
 cap = ctx.out_capacity(n_rec) + 64
 dev = torch.device("cuda", 0)
 d_bin = torch.zeros(hb.size + 64, dtype=torch.uint8, device=dev); d_bin[:hb.size] = torch.from_numpy(hb.data).to(dev)

@@ -43,6 +43,10 @@ __global__ void k(uint32_t* out, int unused)
 		if (MODE == 16) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((d * 3 + lane) & 1023); atomicAdd(p, 1ull); }      // ADD.64
 		if (MODE == 17) { acc += atomicMin(&sh[(d * 3 + lane) & 2047], d * 7919u); }                                    // MIN.32
 		if (MODE == 18) { acc += atomicExch(&sh[(d * 3 + lane) & 2047], d); }                                           // EXCH.32
+		if (MODE == 20) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((acc + d) & 1023); acc += (uint32_t)atomicCAS(p, 0xFFFFFFFFFFFFFFFFull, (unsigned long long)d); }   // CAS.64, address depends on the previous result: latency
+		if (MODE == 21) { const unsigned long long* p = reinterpret_cast<const unsigned long long*>(sh) + ((acc + d) & 1023); acc += (uint32_t)*reinterpret_cast<const volatile unsigned long long*>(p); }   // LDS.64 dependent chain
+		if (MODE == 22) { acc += atomicAdd(&sh[(acc + d) & 2047], 1u); }                                                // ADD.32 with return, dependent chain
+		if (MODE == 23) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((d * 3 + lane) & 1023); const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(p); if ((uint32_t)v != 12345u) atomicAdd(reinterpret_cast<uint32_t*>(p), 1u); }   // LDS.64 + ADD.32 (the 'copy of a known k-mer' path without CAS)
 		if (MODE == 19) { unsigned long long* p = reinterpret_cast<unsigned long long*>(sh) + ((d * 3 + lane) & 1023); acc += (uint32_t)atomicExch(p, (unsigned long long)d); }  // EXCH.64
 	}
 	long long t1 = clock64();
@@ -91,6 +95,11 @@ int main()
 		run<17>("atomicMin 32 smem random", thr, bps);
 		run<18>("atomicExch 32 smem random", thr, bps);
 		run<19>("atomicExch 64 smem random", thr, bps);
+		run<23>("LDS.64 + atomicAdd 32 (no CAS)", thr, bps);
+		run<20>("atomicCAS 64 dependent chain, 1 warp/SM", 32, 1);
+		run<21>("LDS.64 dependent chain, 1 warp/SM", 32, 1);
+		run<22>("atomicAdd 32 ret dependent chain, 1 warp/SM", 32, 1);
+		run<0>("baseline lcg, 1 warp/SM", 32, 1);
 		run<8>("match + leader LDS/STS RMW + syncwarp", thr, bps);
 		run<9>("plain smem RMW (LDS+IADD+STS)", thr, bps);
 	}
