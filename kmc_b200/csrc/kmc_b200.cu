@@ -9,6 +9,7 @@
 #include "count.cuh"
 #include "msd_sort.cuh"
 #include "leaf_warp.cuh"
+#include "leaf_hash.cuh"
 
 #include <cmath>
 #include <cstddef>
@@ -130,6 +131,10 @@ struct kmcb200_ctx {
 	bool overlap_walk = true;                               // KMCB200_OVERLAP_WALK=0: the index kernels of a submitted bin on the compute stream instead of its copy stream
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
+	int occ_leaf_hash = 1;
+	bool leaf_hash = true;                                  // KMCB200_LEAF_KERNEL = hash | warp: one-word records are counted by leaf_hash_kernel (round 2) / leaf_warp_kernel
+	uint32_t leaf_fill_pct = 62;                            // KMCB200_LEAF_FILL_PCT: leaf_hash_kernel plans a table round for this load
+	uint32_t leaf_ratio0_q8 = 90;                           // KMCB200_LEAF_RATIO0: first guess of distinct k-mers per record, x 256 (30x coverage, 1 % errors: ~0.3)
 	uint64_t max_block_records = 1ull << 28;                // a bin with more k-mers is counted key block by key block: from the free HBM at create (KMCB200_MAX_BLOCK_RECORDS overrides)
 	uint64_t max_chunk_bytes = 1ull << 30;                  // KMCB200_MAX_CHUNK_BYTES: ... and expanded chunk by chunk
 	uint32_t leaf_round_pct = 100;                          // KMCB200_LEAF_ROUND_PCT: records per table round in percent of the slots
@@ -706,6 +711,14 @@ __global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uin
 template <int WORDS, int SLOT_BITS>
 int launch_leaves(kmcb200_ctx* ctx, const LeafArgs& la, cudaStream_t st)
 {
+	if (WORDS == 1 && ctx->leaf_hash) {
+		const size_t hsmem = sizeof(LhSmem<SLOT_BITS>) * kLwWarps;
+		const uint32_t hgrid = std::min<uint32_t>((la.n_leaves + kLwWarps - 1) / kLwWarps, (uint32_t)(ctx->sm_count * ctx->occ_leaf_hash));
+		leaf_hash_kernel<SLOT_BITS><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+		ctx->launches++;
+		CU(cudaGetLastError());
+		return 0;
+	}
 	const size_t smem = sizeof(LwSmem<SLOT_BITS>) * kLwWarps;
 	const uint32_t lgrid = std::min<uint32_t>((la.n_leaves + kLwWarps - 1) / kLwWarps, (uint32_t)(ctx->sm_count * ctx->occ_leaf));
 	leaf_warp_kernel<WORDS, SLOT_BITS><<<lgrid, 32 * kLwWarps, smem, st>>>(la);
@@ -733,6 +746,13 @@ int setup_leaves(kmcb200_ctx* ctx)
 	CU(cudaFuncSetAttribute(leaf_warp_kernel<WORDS, SLOT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf, leaf_warp_kernel<WORDS, SLOT_BITS>, 32 * kLwWarps, smem));
 	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
+	if (WORDS == 1) {
+		const int hsmem = (int)(sizeof(LhSmem<SLOT_BITS>) * kLwWarps);
+		CU(cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
+		CU(cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf_hash, leaf_hash_kernel<SLOT_BITS>, 32 * kLwWarps, hsmem));
+		if (ctx->occ_leaf_hash < 1) ctx->occ_leaf_hash = 1;
+	}
 	return 0;
 }
 
@@ -771,6 +791,7 @@ int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np
 	LeafArgs la{};
 	la.recs = plan.recs; la.start = plan.start; la.n_leaves = plan.n_leaves; la.low_bits = plan.low_bits;
 	la.round_pct = ctx->leaf_round_pct;
+	la.fill_pct = ctx->leaf_fill_pct; la.ratio0_q8 = ctx->leaf_ratio0_q8;
 	la.leaf_prefix = block_bits ? block_prefix * plan.n_leaves : 0u;          // n_leaves is a power of two
 	la.k = ctx->prm.kmer_len; la.lut_prefix_len = ctx->prm.lut_prefix_len; la.cutoff_min = ctx->prm.cutoff_min; la.cutoff_max = ctx->prm.cutoff_max;
 	la.counter_max = ctx->prm.counter_max; la.counter_bytes = ctx->counter_bytes; la.suffix_bytes = ctx->suffix_bytes;
@@ -1158,6 +1179,9 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	if (const char* e = getenv("KMCB200_MAX_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= (1 << 17) && v < (1ll << 31)) ctx->max_chunk_bytes = (uint64_t)v; }
 	if (const char* e = getenv("KMCB200_L2_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 10) ctx->force_b2 = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_ROUND_PCT")) { const int v = atoi(e); if (v >= 50 && v <= 1000) ctx->leaf_round_pct = (uint32_t)v; }
+	if (const char* e = getenv("KMCB200_LEAF_KERNEL")) ctx->leaf_hash = std::string(e) != "warp";
+	if (const char* e = getenv("KMCB200_LEAF_FILL_PCT")) { const int v = atoi(e); if (v >= 10 && v <= 85) ctx->leaf_fill_pct = (uint32_t)v; }
+	if (const char* e = getenv("KMCB200_LEAF_RATIO0")) { const int v = atoi(e); if (v >= 8 && v <= 256) ctx->leaf_ratio0_q8 = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_SLOT_BITS")) { const int b = atoi(e); if (b == 8 || b == 9 || b == 10) ctx->leaf_slot_bits = b; }
 	ctx->slots.resize(prm->n_slots);
 	auto bail = [&](int rc) { std::string e = ctx->err; kmcb200_destroy(ctx); g_create_error = e; return rc; };

@@ -64,6 +64,8 @@ struct LeafArgs {
 	uint32_t n_leaves;
 	uint32_t low_bits;           // bits below the partition digits
 	uint32_t round_pct;          // records a round of the table is sized for, in percent of its slots (duplicate-rich bins: ~0.3 distinct k-mers per record)
+	uint32_t fill_pct;           // leaf_hash_kernel: distinct k-mers a round of the table is planned for, in percent of its slots
+	uint32_t ratio0_q8;          // leaf_hash_kernel: first estimate of distinct k-mers per record, x 256 (every warp then follows what it sees)
 	uint32_t leaf_prefix;        // key block of an oversized bin: (block prefix << log2(n_leaves)), so that (leaf_prefix | leaf) = k-mer >> low_bits; else 0
 	uint32_t k, lut_prefix_len, cutoff_min, cutoff_max, counter_max, counter_bytes, suffix_bytes;
 	uint8_t* tmp;                // leaf L writes its records, padded to a multiple of 8 bytes, at tmp + start[L] * pad
