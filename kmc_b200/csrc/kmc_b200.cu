@@ -133,6 +133,8 @@ struct kmcb200_ctx {
 	int occ_leaf = 1;
 	int occ_leaf_hash = 1;
 	bool leaf_hash = true;                                  // KMCB200_LEAF_KERNEL = hash | warp: one-word records are counted by leaf_hash_kernel (round 2) / leaf_warp_kernel
+	uint32_t leaf_max_b2 = 9;                               // KMCB200_LEAF_MAX_B2
+	uint32_t leaf_target = 1024;                            // KMCB200_LEAF_TARGET: mean leaf size the second partition level of a large bin aims at (leaf_hash_kernel)
 	uint32_t leaf_fill_pct = 62;                            // KMCB200_LEAF_FILL_PCT: leaf_hash_kernel plans a table round for this load
 	uint32_t leaf_ratio0_q8 = 90;                           // KMCB200_LEAF_RATIO0: first guess of distinct k-mers per record, x 256 (30x coverage, 1 % errors: ~0.3)
 	uint64_t max_block_records = 1ull << 28;                // a bin with more k-mers is counted key block by key block: from the free HBM at create (KMCB200_MAX_BLOCK_RECORDS overrides)
@@ -302,7 +304,11 @@ uint32_t choose_b2(const kmcb200_ctx* ctx, uint64_t n, bool counted_leaves)
 		b2 = std::min(bits_for(1024), 10u);
 		// (one-word records only: the leaves of wider records verify every hit against a record in HBM and lose more from a second
 		// table round than the wide scatter costs - k = 55, 2^28 k-mers: 17.1 ms with 10 bits, 21.0 ms with 9)
-		if (WORDS == 1 && b2 > 8) b2 = std::max(8u, std::min(bits_for(2048), 10u));
+		if (WORDS == 1 && b2 > 8 && !ctx->leaf_hash) b2 = std::max(8u, std::min(bits_for(2048), 10u));
+		// leaf_hash_kernel: a leaf of up to ~2100 records of a 30x bin is ONE table round, and the leaves of a bin spread over 0 .. 2x their mean
+		// (measured over the bin sizes of the target workload, profiles/README.md: 9 bits from ~10^8 k-mers on; the 1024-digit count and scatter
+		// kernels cost more than a second table round saves, even at 2^28 k-mers)
+		if (WORDS == 1 && b2 > 8 && ctx->leaf_hash) b2 = std::max(8u, std::min(bits_for(ctx->leaf_target), ctx->leaf_max_b2));
 		if (ctx->force_b2) b2 = ctx->force_b2;          // (tests: the wide second level on small bins)
 	} else
 		b2 = std::min(bits_for(std::max<uint64_t>(msd_local_cap<WORDS>() / 5, 64)), 8u);
@@ -714,7 +720,10 @@ int launch_leaves(kmcb200_ctx* ctx, const LeafArgs& la, cudaStream_t st)
 	if (WORDS == 1 && ctx->leaf_hash) {
 		const size_t hsmem = sizeof(LhSmem<SLOT_BITS>) * kLwWarps;
 		const uint32_t hgrid = std::min<uint32_t>((la.n_leaves + kLwWarps - 1) / kLwWarps, (uint32_t)(ctx->sm_count * ctx->occ_leaf_hash));
-		leaf_hash_kernel<SLOT_BITS><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+		// (the usual cutoffs - cutoff_min >= 2, a cutoff_max no count of a leaf reaches - get the instance without the rarely needed transitions)
+		const bool simple = la.cutoff_min >= 2u && la.cutoff_max >= la.cutoff_min && (la.cutoff_max + 1u == 0u || la.cutoff_max + 1u > kLwHeavy + 1u);
+		if (simple) leaf_hash_kernel<SLOT_BITS, true><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+		else leaf_hash_kernel<SLOT_BITS, false><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
 		ctx->launches++;
 		CU(cudaGetLastError());
 		return 0;
@@ -748,9 +757,14 @@ int setup_leaves(kmcb200_ctx* ctx)
 	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
 	if (WORDS == 1) {
 		const int hsmem = (int)(sizeof(LhSmem<SLOT_BITS>) * kLwWarps);
-		CU(cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
-		CU(cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-		CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf_hash, leaf_hash_kernel<SLOT_BITS>, 32 * kLwWarps, hsmem));
+		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
+		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
+		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+		int occ_f = 1;
+		CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf_hash, leaf_hash_kernel<SLOT_BITS, true>, 32 * kLwWarps, hsmem)));
+		CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, leaf_hash_kernel<SLOT_BITS, false>, 32 * kLwWarps, hsmem)));
+		ctx->occ_leaf_hash = std::min(ctx->occ_leaf_hash, occ_f);
 		if (ctx->occ_leaf_hash < 1) ctx->occ_leaf_hash = 1;
 	}
 	return 0;
@@ -1180,6 +1194,8 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	if (const char* e = getenv("KMCB200_L2_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 10) ctx->force_b2 = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_ROUND_PCT")) { const int v = atoi(e); if (v >= 50 && v <= 1000) ctx->leaf_round_pct = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_KERNEL")) ctx->leaf_hash = std::string(e) != "warp";
+	if (const char* e = getenv("KMCB200_LEAF_MAX_B2")) { const int v = atoi(e); if (v >= 8 && v <= 10) ctx->leaf_max_b2 = (uint32_t)v; }
+	if (const char* e = getenv("KMCB200_LEAF_TARGET")) { const int v = atoi(e); if (v >= 128 && v <= 8192) ctx->leaf_target = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_FILL_PCT")) { const int v = atoi(e); if (v >= 10 && v <= 85) ctx->leaf_fill_pct = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_RATIO0")) { const int v = atoi(e); if (v >= 8 && v <= 256) ctx->leaf_ratio0_q8 = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_SLOT_BITS")) { const int b = atoi(e); if (b == 8 || b == 9 || b == 10) ctx->leaf_slot_bits = b; }

@@ -40,7 +40,7 @@ namespace kmcb {
 #ifndef KMCB200_LH_VGBITS
 #define KMCB200_LH_VGBITS 6
 #endif
-constexpr uint32_t kLhQueue = KMCB200_LH_QUEUE;          // deferred probes (a step adds <= 128 to <= 31 left over)
+constexpr uint32_t kLhQueue = KMCB200_LH_QUEUE;          // deferred probes (a step adds <= 128 to <= 63 left over)
 constexpr uint32_t kLhVgBits = KMCB200_LH_VGBITS;        // virtual groups of the emission: 2^6
 constexpr uint32_t kLhVg = 1u << kLhVgBits;
 constexpr uint32_t kLhKeyBits = 48;                      // key bits of an entry / a queue item
@@ -55,55 +55,196 @@ struct LhSmem {
 	uint32_t over[kSlots / 32];      // ... whose count went past cutoff_max
 	uint32_t vbase[kLhVg + 4];       // emission: first list position of every virtual group (+ end)
 	uint32_t vcur[kLhVg];            // emission: counters / cursors of the virtual groups
+	uint64_t dummy[32];              // one word per lane, always 0: where the CAS of a lane with nothing to insert goes
 	__device__ __forceinline__ uint16_t* list() { return reinterpret_cast<uint16_t*>(queue); }       // [kSlots]
 };
 
 __device__ __forceinline__ uint32_t lh_hash(uint64_t rem) { return ((uint32_t)rem ^ (uint32_t)(rem >> 27)) * 0x9E3779B1u; }
 
-struct LhRound {
-	uint64_t* main; uint64_t* queue; uint32_t* surv; uint32_t* over;
-	uint32_t cb, cmask;
-	uint64_t rem_mask;
-	LwCut cut;
-};
-
-// what a probe found: the slot was empty and is ours now (claimed) / holds this k-mer (one more copy) / holds another k-mer (miss)
-template <int SLOT_BITS>
-__device__ __forceinline__ bool lh_settle(const LhRound& t, bool act, unsigned long long old, uint64_t rem, uint32_t slot, uint32_t& r_claim, uint32_t& r_max)
+// Shared-memory atomics on 32-bit shared addresses (inline PTX).  ptxas turns a predicated ATOMS into a branch around it (BSSY / BRA / BSYNC),
+// and those reconvergence points fence the four probe chains of a step off from each other; an UNCONDITIONAL atomic keeps the code
+// straight-line - a lane with nothing to do aims its CAS at a dummy word of its own (holds 0: the compare with EMPTY fails, nothing is written),
+// adds 0 to a count, ORs 0 into a bitmap - but occupies the shared-memory atomic unit for all 32 lanes.  Measured on the B200 (1.17e8-k-mer
+// bin, leaves): everything predicated 0.87 ms, everything unconditional 1.18 ms (the ORs of 32 lanes into a 32-word bitmap collide).
+#ifndef KMCB200_LH_UNCOND_CAS
+#define KMCB200_LH_UNCOND_CAS 0
+#endif
+#ifndef KMCB200_LH_UNCOND_ADD
+#define KMCB200_LH_UNCOND_ADD 0
+#endif
+#ifndef KMCB200_LH_UNCOND_OR
+#define KMCB200_LH_UNCOND_OR 0
+#endif
+__device__ __forceinline__ unsigned long long lh_cas64(bool p, uint32_t saddr, uint32_t sdummy, unsigned long long val)
 {
-	const bool empty = old == kLwEmpty;
-	const bool hit = empty || (uint64_t)(old >> t.cb) == rem;
-	if (act && hit) {
-		uint32_t newc = 1u;
-		if (empty) ++r_claim;
-		else newc = (atomicAdd(reinterpret_cast<uint32_t*>(&t.main[slot]), 1u) & t.cmask) + 1u;      // low word = count (never carries: count < 2^cb - 1)
-		lw_transition(t.cut, newc, t.surv, t.over, slot, r_max);
-	}
-	return act && !hit;
+#if KMCB200_LH_UNCOND_CAS
+	unsigned long long old;
+	asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(p ? saddr : sdummy), "l"((unsigned long long)kLwEmpty), "l"(val) : "memory");
+#else
+	unsigned long long old = 0ull;
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p atom.shared.cas.b64 %0, [%2], %3, %4;\n\t}"
+		: "+l"(old) : "r"((uint32_t)p), "r"(saddr), "l"((unsigned long long)kLwEmpty), "l"(val) : "memory");
+#endif
+	return old;
+}
+// KMCB200_LH_LDS_FIRST: look at the slot with a plain load first; only a lane that finds it EMPTY tries to claim it with the (5x more expensive)
+// CAS.64 - three of four records of a 30x bin are copies of a k-mer that is in the table already
+#ifndef KMCB200_LH_LDS_FIRST
+#define KMCB200_LH_LDS_FIRST 1
+#endif
+__device__ __forceinline__ unsigned long long lh_probe(bool p, uint32_t saddr, uint32_t sdummy, unsigned long long val)
+{
+#if KMCB200_LH_LDS_FIRST
+	unsigned long long cur;
+	asm volatile("ld.shared.u64 %0, [%1];" : "=l"(cur) : "r"(saddr) : "memory");
+	const bool empty = cur == kLwEmpty;
+	const unsigned long long got = lh_cas64(p && empty, saddr, sdummy, val);
+	return empty ? got : cur;          // (a slot that was EMPTY may have been taken in between: then the CAS returns its owner)
+#else
+	return lh_cas64(p, saddr, sdummy, val);
+#endif
+}
+__device__ __forceinline__ uint32_t lh_add32(bool p, uint32_t saddr)
+{
+#if KMCB200_LH_UNCOND_ADD
+	uint32_t old;
+	asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(p ? 1u : 0u) : "memory");
+#else
+	uint32_t old = 0u;
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}" : "+r"(old) : "r"((uint32_t)p), "r"(saddr) : "memory");
+#endif
+	return old;
+}
+__device__ __forceinline__ void lh_or32(bool p, uint32_t saddr, uint32_t bits)
+{
+#if KMCB200_LH_UNCOND_OR
+	asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(saddr), "r"(p ? bits : 0u) : "memory");
+#else
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.shared.or.b32 [%1], %2;\n\t}" :: "r"((uint32_t)p), "r"(saddr), "r"(bits) : "memory");
+#endif
 }
 
-// one drain step: up to 32 deferred probes, each moved on by one slot
-template <int SLOT_BITS>
+struct LhRound {
+	uint32_t s_main, s_queue, s_surv, s_over;          // shared-memory addresses of the warp's table, queue and bitmaps
+	uint32_t s_dummy;                                  // ... and of this LANE's dummy word (always 0)
+	uint64_t* queue;
+	uint32_t cb, cmask;
+	uint64_t rem_mask, key_unit;                       // key_unit = 1 << cb: two entries hold the same k-mer iff (a ^ b) < key_unit
+	uint32_t cmin, cmax1;                              // max(cutoff_min, 1); cutoff_max + 1 (0: never reached)
+	bool never, has_max;                               // never: cutoff_max < cutoff_min (whatever reaches cmin counts as n_cutoff_max); has_max: counts can reach cmax1 at all
+};
+
+// what a probe found: the slot was empty and is ours now (claimed) / holds this k-mer (one more copy, cutoffs applied on the way:
+// kb_sorter.h:1174-1191) / holds another k-mer (returns true: the probe goes on, later)
+// SIMPLE: cutoff_min >= 2 and a cutoff_max no count of a leaf can exceed (the usual -ci2 -cx1e9): one compare per copy, nothing per claim
+template <bool SIMPLE>
+__device__ __forceinline__ bool lh_settle(const LhRound& t, bool act, unsigned long long old, unsigned long long ent, uint32_t slot, uint32_t& r_claim, uint32_t& r_max)
+{
+	const bool empty = old == kLwEmpty;
+	const bool same = !empty && (old ^ ent) < t.key_unit;
+	const bool add = act && same;
+	const uint32_t newc = (lh_add32(add, t.s_main + slot * 8u) & t.cmask) + 1u;      // low word = count (never carries: count < 2^cb - 1)
+	const bool claimed = act && empty;
+	r_claim += claimed ? 1u : 0u;
+	const uint32_t bit = 1u << (slot & 31u), woff = (slot >> 5) * 4u;
+	if (SIMPLE) {
+		lh_or32(add && newc == t.cmin, t.s_surv + woff, bit);
+	} else {
+		const bool at_min = (add && newc == t.cmin) || (claimed && t.cmin == 1u);
+		if (t.never) r_max += at_min ? 1u : 0u;
+		else lh_or32(at_min, t.s_surv + woff, bit);
+		if (t.has_max) {
+			const bool at_max = !t.never && ((add && newc == t.cmax1) || (claimed && t.cmax1 == 1u));
+			lh_or32(at_max, t.s_over + woff, bit);
+			r_max += at_max ? 1u : 0u;
+		}
+	}
+	return act && !empty && !same;
+}
+
+// one drain step: up to 64 deferred probes (two per lane, their chains overlap), each moved on by one slot
+template <int SLOT_BITS, bool SIMPLE>
 __device__ __forceinline__ void lh_drain(const LhRound& t, uint32_t& head, uint32_t& tail, uint32_t lane, uint32_t lt, uint32_t& r_claim, uint32_t& r_max)
 {
 	constexpr uint32_t SM1 = (1u << SLOT_BITS) - 1u;
 	__syncwarp();
-	const uint32_t take = min(tail - head, 32u);
-	const bool act = lane < take;
-	const uint64_t item = act ? t.queue[(head + lane) & (kLhQueue - 1)] : 0ull;
+	const uint32_t take = min(tail - head, 64u);
+	bool act[2];
+	uint64_t rem[2];
+	uint32_t pc[2], slot[2];
+	unsigned long long ent[2], old[2];
+#pragma unroll
+	for (int u = 0; u < 2; ++u) {
+		act[u] = u * 32 + lane < take;
+		const uint64_t item = act[u] ? t.queue[(head + u * 32 + lane) & (kLhQueue - 1)] : 0ull;
+		rem[u] = item & ((1ull << kLhKeyBits) - 1ull);
+		pc[u] = (uint32_t)(item >> kLhKeyBits);
+		slot[u] = ((lh_hash(rem[u]) >> (32 - SLOT_BITS)) + pc[u]) & SM1;
+		ent[u] = (rem[u] << t.cb) | 1ull;
+		old[u] = lh_probe(act[u], t.s_main + slot[u] * 8u, t.s_dummy, ent[u]);
+	}
 	head += take;
-	const uint64_t rem = item & ((1ull << kLhKeyBits) - 1ull);
-	const uint32_t pc = (uint32_t)(item >> kLhKeyBits);
-	const uint32_t slot = ((lh_hash(rem) >> (32 - SLOT_BITS)) + pc) & SM1;
-	unsigned long long old = 0;
-	if (act) old = atomicCAS(reinterpret_cast<unsigned long long*>(&t.main[slot]), (unsigned long long)kLwEmpty, (unsigned long long)((rem << t.cb) | 1ull));
-	const bool miss = lh_settle<SLOT_BITS>(t, act, old, rem, slot, r_claim, r_max);
-	const uint32_t bal = __ballot_sync(0xffffffffu, miss);
-	if (miss) t.queue[(tail + __popc(bal & lt)) & (kLhQueue - 1)] = ((uint64_t)(pc + 1u) << kLhKeyBits) | rem;
-	tail += __popc(bal);
+#pragma unroll
+	for (int u = 0; u < 2; ++u) {
+		const bool miss = lh_settle<SIMPLE>(t, act[u], old[u], ent[u], slot[u], r_claim, r_max);
+		const uint32_t bal = __ballot_sync(0xffffffffu, miss);
+		if (miss) t.queue[(tail + __popc(bal & lt)) & (kLhQueue - 1)] = ((uint64_t)(pc[u] + 1u) << kLhKeyBits) | rem[u];
+		tail += __popc(bal);
+	}
 }
 
-template <int SLOT_BITS>
+// the insertion of one round: 4 k-mers per lane and step, first probes of all four before any result is looked at; returns false when the
+// table fills up (more distinct k-mers than planned).  MULTI: one of several rounds of a leaf - only the k-mers whose next bits are r
+template <int SLOT_BITS, bool SIMPLE, bool MULTI>
+__device__ __forceinline__ bool lh_insert(const LhRound& T, const unsigned long long* __restrict__ g, uint32_t m, uint32_t kb, uint32_t emask, uint32_t r,
+	uint32_t limit, uint32_t lane, uint32_t lt, uint32_t& r_claim, uint32_t& r_max)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	uint32_t head = 0, tail = 0;
+	bool ok = true;
+	uint64_t nx[4];
+#pragma unroll
+	for (int u = 0; u < 4; ++u) { const uint32_t j = u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+	for (uint32_t j0 = 0; j0 < m; j0 += 128) {
+		uint64_t rem[4];
+		uint32_t slot[4];
+		unsigned long long ent[4], old[4];
+		bool act[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const uint64_t cur = nx[u];
+			act[u] = j0 + u * 32 + lane < m;
+			if (MULTI) act[u] = act[u] && (((uint32_t)(cur >> kb) & emask) == r);
+			rem[u] = cur & T.rem_mask;
+			slot[u] = lh_hash(rem[u]) >> (32 - SLOT_BITS);
+			ent[u] = (rem[u] << T.cb) | 1ull;
+			old[u] = lh_probe(act[u], T.s_main + slot[u] * 8u, T.s_dummy, ent[u]);
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + 128 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const bool miss = lh_settle<SIMPLE>(T, act[u], old[u], ent[u], slot[u], r_claim, r_max);
+			const uint32_t bal = __ballot_sync(FULL, miss);
+			if (miss) T.queue[(tail + __popc(bal & lt)) & (kLhQueue - 1)] = (1ull << kLhKeyBits) | rem[u];
+			tail += __popc(bal);
+		}
+		// (a table that fills up must end the round HERE: probes into a full table would circulate in the queue for ever)
+		if (__reduce_add_sync(FULL, r_claim) > limit) ok = false;          // more distinct k-mers than planned: the round is split
+		while (ok && tail - head >= 64u) {
+			lh_drain<SLOT_BITS, SIMPLE>(T, head, tail, lane, lt, r_claim, r_max);
+			if (__reduce_add_sync(FULL, r_claim) > limit) ok = false;
+		}
+		if (!ok) break;
+	}
+	while (ok && tail != head) {
+		lh_drain<SLOT_BITS, SIMPLE>(T, head, tail, lane, lt, r_claim, r_max);
+		if (__reduce_add_sync(FULL, r_claim) > limit) ok = false;
+	}
+	return ok;
+}
+
+template <int SLOT_BITS, bool SIMPLE>
 __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LH_MINBLOCKS) leaf_hash_kernel(const LeafArgs a)
 {
 	using R = Rec<1>;
@@ -111,14 +252,15 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LH_MINBLOCKS) leaf_hash
 	constexpr int SLOTS = SM::kSlots;
 	constexpr int NW = SLOTS / 32;                       // bitmap words (<= 32: one per lane)
 	constexpr uint32_t FULL = 0xffffffffu;
-	constexpr uint32_t SM1 = (uint32_t)SLOTS - 1u;
 	static_assert(NW <= 32 && NW >= 4, "one bitmap word per lane");
 	static_assert(kLhQueue * 8 >= (uint32_t)SLOTS * 2, "the u16 list of survivors lives in the queue");
-	static_assert(kLhQueue >= 192 && (kLhQueue & (kLhQueue - 1)) == 0, "a step adds up to 128 deferred probes to up to 31 left over");
+	static_assert(kLhQueue >= 192 && (kLhQueue & (kLhQueue - 1)) == 0, "a step adds up to 128 deferred probes to up to 63 left over");
 	extern __shared__ __align__(16) uint8_t lh_dsm[];
 	SM& S = reinterpret_cast<SM*>(lh_dsm)[threadIdx.x >> 5];
 	if (*a.flags & kMsdFlagStop) return;
 	const uint32_t lane = threadIdx.x & 31u, lt = lanemask_lt();
+	S.dummy[lane] = 0ull;
+	__syncwarp();
 	const uint32_t CAP = max((uint32_t)SLOTS * a.fill_pct / 100u, 32u);         // distinct k-mers a round is planned for
 	const uint32_t LIMIT = (uint32_t)SLOTS - (uint32_t)SLOTS / 8u;               // ... and where it gives up (the table gets too crowded to probe)
 	const unsigned long long* __restrict__ recs = reinterpret_cast<const unsigned long long*>(a.recs);
@@ -176,50 +318,12 @@ __global__ void __launch_bounds__(32 * kLwWarps, KMCB200_LH_MINBLOCKS) leaf_hash
 					if (lane < 2 * NW / 4) reinterpret_cast<uint4*>(S.surv)[lane] = zv;            // surv, over (contiguous)
 				}
 				__syncwarp();
-				// ---- insertion: 4 k-mers per lane and step; first probes of all four before any result is looked at
-				const LhRound T{S.main, S.queue, S.surv, S.over, cb, cmask, rem_mask, cut};
-				uint32_t r_claim = 0, r_max = 0, head = 0, tail = 0;
-				bool ok = true;
-				{
-					uint64_t nx[4];
-#pragma unroll
-					for (int u = 0; u < 4; ++u) { const uint32_t j = u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
-					for (uint32_t j0 = 0; j0 < m; j0 += 128) {
-						uint64_t rem[4];
-						uint32_t slot[4];
-						unsigned long long old[4];
-						bool act[4];
-#pragma unroll
-						for (int u = 0; u < 4; ++u) {
-							const uint64_t cur = nx[u];
-							act[u] = (j0 + u * 32 + lane < m) && (((uint32_t)(cur >> kb) & emask) == r);
-							rem[u] = cur & rem_mask;
-							slot[u] = lh_hash(rem[u]) >> (32 - SLOT_BITS);
-							old[u] = 0;
-							if (act[u]) old[u] = atomicCAS(reinterpret_cast<unsigned long long*>(&S.main[slot[u]]), (unsigned long long)kLwEmpty, (unsigned long long)((rem[u] << cb) | 1ull));
-						}
-#pragma unroll
-						for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + 128 + u * 32 + lane; nx[u] = j < m ? __ldg(g + j) : 0ull; }
-#pragma unroll
-						for (int u = 0; u < 4; ++u) {
-							const bool miss = lh_settle<SLOT_BITS>(T, act[u], old[u], rem[u], slot[u], r_claim, r_max);
-							const uint32_t bal = __ballot_sync(FULL, miss);
-							if (miss) S.queue[(tail + __popc(bal & lt)) & (kLhQueue - 1)] = (1ull << kLhKeyBits) | rem[u];
-							tail += __popc(bal);
-						}
-						// (a table that fills up must end the round HERE: probes into a full table would circulate in the queue for ever)
-						if (__reduce_add_sync(FULL, r_claim) > LIMIT) ok = false;          // more distinct k-mers than planned: the round is split
-						while (ok && tail - head >= 32u) {
-							lh_drain<SLOT_BITS>(T, head, tail, lane, lt, r_claim, r_max);
-							if (__reduce_add_sync(FULL, r_claim) > LIMIT) ok = false;
-						}
-						if (!ok) break;
-					}
-					while (ok && tail != head) {
-						lh_drain<SLOT_BITS>(T, head, tail, lane, lt, r_claim, r_max);
-						if (__reduce_add_sync(FULL, r_claim) > LIMIT) ok = false;
-					}
-				}
+				// ---- insertion
+				const LhRound T{smem_u32(S.main), smem_u32(S.queue), smem_u32(S.surv), smem_u32(S.over), smem_u32(&S.dummy[lane]), S.queue, cb, cmask, rem_mask, 1ull << cb,
+					cut.cmin, cut.cmax1, cut.never, cut.cmax1 != 0u && cut.cmax1 <= kLwHeavy + 1u};
+				uint32_t r_claim = 0, r_max = 0;
+				const bool ok = e == 0 ? lh_insert<SLOT_BITS, SIMPLE, false>(T, g, m, kb, emask, r, LIMIT, lane, lt, r_claim, r_max)
+				                       : lh_insert<SLOT_BITS, SIMPLE, true>(T, g, m, kb, emask, r, LIMIT, lane, lt, r_claim, r_max);
 				if (!prefetched) {        // the next leaf: towards L2 while this one is counted
 					prefetched = true;
 					const uint32_t nl = __shfl_sync(FULL, next_t, 0);
