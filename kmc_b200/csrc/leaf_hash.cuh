@@ -237,9 +237,25 @@ __device__ __forceinline__ bool lh_insert(const LhRound& T, const unsigned long 
 		}
 		if (!ok) break;
 	}
+	// what is left in the queue at the end of the leaf (< 64 probes): every lane takes one and FOLLOWS it to its slot - a short loop
+	// (a few probes) instead of drain steps that each move a handful of probes by one slot and queue them again (measured: 4.1 such steps
+	// per leaf, 13 % of the kernel's instructions)
 	while (ok && tail != head) {
-		lh_drain<SLOT_BITS, SIMPLE>(T, head, tail, lane, lt, r_claim, r_max);
-		if (__reduce_add_sync(FULL, r_claim) > limit) ok = false;
+		__syncwarp();
+		const uint32_t take = min(tail - head, 32u);
+		bool pend = lane < take;
+		const uint64_t item = pend ? T.queue[(head + lane) & (kLhQueue - 1)] : 0ull;
+		head += take;
+		const uint64_t rem = item & ((1ull << kLhKeyBits) - 1ull);
+		const unsigned long long ent = (rem << T.cb) | 1ull;
+		uint32_t slot = ((lh_hash(rem) >> (32 - SLOT_BITS)) + (uint32_t)(item >> kLhKeyBits)) & ((1u << SLOT_BITS) - 1u);
+		while (true) {
+			const unsigned long long old = lh_probe(pend, T.s_main + slot * 8u, T.s_dummy, ent);
+			pend = lh_settle<SIMPLE>(T, pend, old, ent, slot, r_claim, r_max);
+			slot = (slot + 1u) & ((1u << SLOT_BITS) - 1u);
+			if (__reduce_add_sync(FULL, r_claim) > limit) { ok = false; break; }          // (a full table would keep the loop going for ever)
+			if (!__any_sync(FULL, pend)) break;
+		}
 	}
 	return ok;
 }
