@@ -55,6 +55,8 @@ struct ExpandArgs {
 	uint64_t* pack_kbase;        // [n_packs + 1]
 	uint32_t* pack_tbase;        // [n_packs + 1]
 	uint32_t* tile_pack;         // [tile_pack_cap]
+	uint4* tile_desc;            // [2 * tile_pack_cap] everything expand_kernel needs to know about an output tile, gathered by tile_desc_kernel:
+	                             //   {slot0, nsk, j_lo, off_lo} {tile_start | (cnt - 1), pack_end, obase lo, obase hi}
 	uint64_t tile_pack_cap;      // n_rec / kExpandMinTile + n_packs + 2 (sized from the CALLER's n_rec: writes are clamped to it)
 	uint32_t* status;            // [0] error bits, [1] total tiles (0 when the bin is malformed: nothing is expanded)
 	uint32_t* flags;             // msd_sort.cuh: [0] / [1] get kMsdFlagAbort when the bin is malformed, so that no kernel behind touches the records
@@ -374,6 +376,26 @@ __global__ void __launch_bounds__(1024) scan_packs_kernel(const ExpandArgs a)
 	}
 }
 
+// one thread per output tile: the tile's geometry, gathered from the per-pack tables and the index into ONE 32-byte descriptor, so that
+// expand_kernel starts a tile with one load instead of a chain of four dependent ones (tile -> pack -> pack tables -> first super-k-mer ->
+// its offset: a third of the stall samples of expand_kernel were waits for global loads, round 2) and without a 64-bit division
+__global__ void __launch_bounds__(256) tile_desc_kernel(const ExpandArgs a)
+{
+	const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+	if (g >= a.status[1]) return;
+	const uint32_t p = a.tile_pack[g];
+	const uint32_t t = g - a.pack_tbase[p];
+	const uint64_t pstart = a.pack_start[p];
+	const uint64_t slot0 = pstart / a.min_rec_bytes;
+	const uint32_t nk = a.pack_nk[p];
+	const uint32_t tile_start = t * a.tile;
+	const uint32_t cnt = min(a.tile, nk - tile_start);
+	const uint32_t j_lo = a.tile_first[tile_first_base(pstart, p, a.tile) + t];
+	const uint64_t obase = a.pack_kbase[p] + tile_start;
+	a.tile_desc[2 * (size_t)g] = make_uint4((uint32_t)slot0, a.pack_nsk[p], j_lo, a.sk_off[slot0 + j_lo]);
+	a.tile_desc[2 * (size_t)g + 1] = make_uint4(tile_start | (cnt - 1u), (uint32_t)a.pack_start[p + 1], (uint32_t)obase, (uint32_t)(obase >> 32));
+}
+
 __device__ __forceinline__ uint64_t bswap64(uint64_t x)
 {
 	const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
@@ -503,42 +525,42 @@ __device__ __forceinline__ uint32_t msd_free_bits(const Rec<WORDS>& r, uint32_t 
 // MODE is a template parameter: the bin path (kExpandAll) must not pay registers / shared memory for the oversized-bin modes
 // (measured: with the scatter code in the same instance the kernel went from 32 to more registers and the expansion from 0.75 to 0.90 ms)
 template <int WORDS, uint32_t MODE = kExpandAll>
-__global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(const ExpandArgs a)
+__global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads, WORDS <= 2 ? 2048 / ExpandCfg<WORDS>::kThreads : 6) expand_kernel(const ExpandArgs a)      // (<= 32 registers for one- and two-word records, <= 42 beyond: the occupancy the kernel was tuned at)
 {
 	constexpr int kExpandTile = ExpandCfg<WORDS>::kTile, kExpandThreads = ExpandCfg<WORDS>::kThreads;
 	constexpr int IPT = kExpandTile / kExpandThreads;    // 8 k-mers per thread
 	constexpr int MAXSK = 1024, STAGE = 12288;          // per-tile staging of the super-k-mer index and bytes (typical tile: ~350 super-k-mers, ~4.5 KB)
-	__shared__ uint16_t head[kExpandTile];
-	__shared__ uint32_t warp_max[kExpandThreads / 32];
+	constexpr int HW = kExpandTile / 32;                 // words of the head bitmap
+	__shared__ uint32_t hbits[HW];                       // bit s: a super-k-mer (other than the tile's first) starts at output slot s
+	__shared__ uint32_t hpre[HW];                        // set bits before the word
 	__shared__ uint32_t s_bit[MAXSK];                    // staged tiles: bit position of (k-mer of output slot 0) of every super-k-mer, minus 2 * slot
 	__shared__ __align__(16) uint8_t s_bytes[STAGE + 32];       // the tile's bytes as big-endian 32-bit words (+ slack: a funnel shift looks 2*WORDS words ahead)
 	__shared__ uint32_t s_jmax;
 	__shared__ unsigned long long s_fbase;
+	__shared__ uint32_t warp_max[kExpandThreads / 32];   // (scratch of the filter mode)
 	__shared__ uint32_t htop[256];
+	static_assert(HW <= 128 && HW % 32 == 0, "the head bitmap is scanned by one warp, HW / 32 words per lane");
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid < 256) htop[tid] = 0;
 	const uint32_t total_tiles = a.status[1];
 	Rec<WORDS>* __restrict__ out = reinterpret_cast<Rec<WORDS>*>(a.recs);
 
 	for (uint32_t g = blockIdx.x; g < total_tiles; g += gridDim.x) {
-		const uint32_t p = a.tile_pack[g];
-		const uint32_t t = g - a.pack_tbase[p];
-		const uint64_t pstart = a.pack_start[p];
-		const uint64_t slot0 = pstart / a.min_rec_bytes;
-		const uint32_t nsk = a.pack_nsk[p];
-		const uint32_t nk = a.pack_nk[p];
-		const uint32_t tile_start = t * kExpandTile;
-		const uint32_t cnt = min((uint32_t)kExpandTile, nk - tile_start);
-		const uint32_t j_lo = a.tile_first[tile_first_base(pstart, p, kExpandTile) + t];
+		const uint4 da = __ldg(a.tile_desc + 2 * (size_t)g), db = __ldg(a.tile_desc + 2 * (size_t)g + 1);
+		if (g + gridDim.x < total_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tile_desc + 2 * (size_t)(g + gridDim.x)));
+		const uint64_t slot0 = da.x;
+		const uint32_t nsk = da.y;
+		const uint32_t j_lo = da.z;
+		const uint32_t off_lo = da.w;
+		const uint32_t tile_start = db.x & ~(uint32_t)(kExpandTile - 1);
+		const uint32_t cnt = (db.x & (uint32_t)(kExpandTile - 1)) + 1u;
 		const uint32_t* __restrict__ kpre = a.sk_kpre + slot0;
 		const uint32_t* __restrict__ off = a.sk_off + slot0;
-		const uint32_t off_lo = off[j_lo];
 		const uintptr_t g0a = reinterpret_cast<uintptr_t>(a.bin + off_lo) & ~(uintptr_t)15;          // staging starts on the absolute 16-byte grid
 		const uint32_t base_off = (uint32_t)(reinterpret_cast<uintptr_t>(a.bin + off_lo) - g0a);
 
-		__syncthreads();      // previous tile is done with head[]
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) head[i * kExpandThreads + tid] = 0;
+		__syncthreads();      // previous tile is done with the bitmap
+		if (tid < (uint32_t)HW) hbits[tid] = 0;
 		if (tid == 0) s_jmax = j_lo;
 		__syncthreads();
 		// head flags: super-k-mer j_lo + r starts at output slot kpre - tile_start; its index entry is staged in shared memory
@@ -549,7 +571,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				if (j > j_lo && kp >= tile_start + cnt) break;
 				const uint32_t rel = j - j_lo;
 				if (rel < (uint32_t)MAXSK) s_bit[rel] = 8u * (base_off + (off[j] - off_lo) + 1u) + 2u * tile_start - 2u * kp;      // (mod 2^32; + 2 * slot is the k-mer's bit)
-				if (j > j_lo) head[kp - tile_start] = (uint16_t)rel;
+				if (j > j_lo) atomicOr(&hbits[(kp - tile_start) >> 5], 1u << ((kp - tile_start) & 31u));
 				jm = j;
 			}
 			if (jm > j_lo) atomicMax(&s_jmax, jm);
@@ -557,7 +579,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 		__syncthreads();
 		// stage the tile's bytes of the bin (contiguous: from its first super-k-mer to the end of its last one) when they fit
 		const uint32_t j_hi = s_jmax;
-		const uint64_t b_hi = j_hi + 1 < nsk ? (uint64_t)off[j_hi + 1] : a.pack_start[p + 1];
+		const uint64_t b_hi = j_hi + 1 < nsk ? (uint64_t)off[j_hi + 1] : (uint64_t)db.y;
 		const uint64_t span = reinterpret_cast<uintptr_t>(a.bin + b_hi) - g0a;
 		const bool staged = (j_hi - j_lo) < (uint32_t)MAXSK && span + 16 <= (uint64_t)STAGE;
 		if (staged)
@@ -566,33 +588,28 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads) expand_kernel(cons
 				x.x = __byte_perm(x.x, 0, 0x0123); x.y = __byte_perm(x.y, 0, 0x0123); x.z = __byte_perm(x.z, 0, 0x0123); x.w = __byte_perm(x.w, 0, 0x0123);
 				reinterpret_cast<uint4*>(s_bytes)[v] = x;
 			}
-		// inclusive max-scan (blocked: 8 consecutive slots per thread)
-		uint32_t v[IPT];
-		uint32_t m = 0;
+		// the super-k-mer of output slot s = number of head bits at or before s: prefix popcounts of the bitmap words (one warp)
+		if (warp == 0) {
+			constexpr int WPL = HW / 32;
+			uint32_t c[WPL], tot = 0;
 #pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			m = max(m, (uint32_t)head[tid * IPT + i]);
-			v[i] = m;
+			for (int i = 0; i < WPL; ++i) { c[i] = __popc(hbits[lane * WPL + i]); tot += c[i]; }
+			uint32_t inc = tot;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+				if (lane >= (uint32_t)o) inc += x;
+			}
+			uint32_t ex = inc - tot;
+#pragma unroll
+			for (int i = 0; i < WPL; ++i) { hpre[lane * WPL + i] = ex; ex += c[i]; }
 		}
-		uint32_t inc = m;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= (uint32_t)o) inc = max(inc, x);
-		}
-		if (lane == 31) warp_max[warp] = inc;
-		uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
-		if (lane == 0) excl = 0;
-		__syncthreads();
-		for (uint32_t w = 0; w < warp; ++w) excl = max(excl, warp_max[w]);
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) head[tid * IPT + i] = (uint16_t)max(v[i], excl);
 		__syncthreads();
 
 		// striped extraction: consecutive lanes <-> consecutive output k-mers
-		const uint64_t obase = a.pack_kbase[p] + tile_start;
+		const uint64_t obase = ((uint64_t)db.w << 32) | db.z;
 		auto kmer_of = [&](uint32_t slot) -> Rec<WORDS> {
-			const uint32_t rel = head[slot];
+			const uint32_t rel = hpre[slot >> 5] + __popc(hbits[slot >> 5] & (0xffffffffu >> (31u - (slot & 31u))));
 			if (staged) return extract_kmer_be32<WORDS>(reinterpret_cast<const uint32_t*>(s_bytes), s_bit[rel] + 2u * slot, a.k, a.both_strands != 0);
 			const uint32_t j = j_lo + rel;
 			const uint32_t s = tile_start + slot - kpre[j];

@@ -69,6 +69,7 @@ struct Slot {
 	uint32_t* sk_kpre = nullptr; size_t sk_kpre_cap = 0;
 	uint32_t* tile_first = nullptr; size_t tile_first_cap = 0;
 	uint32_t* tile_pack = nullptr; size_t tile_pack_cap = 0;
+	uint4* tile_desc = nullptr; size_t tile_desc_cap = 0;
 	ZeroBlock* zero = nullptr;
 	uint64_t* desc = nullptr; size_t desc_cap = 0;          // radix look-back descriptors
 	// hybrid MSD sort: bucket boundaries and work-item tables
@@ -642,6 +643,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	if (int rc = ensure(ctx, s.tile_first, s.tile_first_cap, size * 4 / kExpandMinTile + np + 2)) return rc;
 	const uint64_t n_bound = n_rec == kExpandUnknownRecs ? size * 4 : n_rec;        // a record of 1 + ceil((k+a)/4) bytes holds a+1 k-mers: < 4 per byte
 	if (int rc = ensure(ctx, s.tile_pack, s.tile_pack_cap, n_bound / kExpandMinTile + np + 2)) return rc;
+	if (int rc = ensure(ctx, s.tile_desc, s.tile_desc_cap, 2 * (n_bound / kExpandMinTile + np + 2))) return rc;
 
 	ExpandArgs a;
 	a.bin = d_bin; a.size = size; a.pack_start = s.d_pack_start; a.n_packs = np; a.k = k; a.min_rec_bytes = min_rec;
@@ -649,6 +651,7 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 	a.tile = ctx->words == 1 ? ExpandCfg<1>::kTile : ExpandCfg<2>::kTile;
 	a.sk_off = s.sk_off; a.sk_kpre = s.sk_kpre; a.tile_first = s.tile_first; a.pack_nsk = s.pack_nsk; a.pack_nk = s.pack_nk;
 	a.pack_kbase = s.pack_kbase; a.pack_tbase = s.pack_tbase; a.tile_pack = s.tile_pack; a.tile_pack_cap = n_bound / kExpandMinTile + np + 2;
+	a.tile_desc = s.tile_desc;
 	a.status = s.zero->status; a.flags = s.zero->msd_flags;
 	a.recs = d_recs;
 	a.mode = em.mode; a.fshift = em.fshift; a.fprefix = em.fprefix; a.fmask = em.fmask; a.hist12 = em.hist12; a.out_counter = em.out_counter;
@@ -675,7 +678,8 @@ int stage_expand(kmcb200_ctx* ctx, Slot& s, const uint8_t* d_bin, uint64_t size,
 		ctx->launches++;
 	}
 	scan_packs_kernel<<<1, 1024, 0, st>>>(a);
-	ctx->launches++;
+	tile_desc_kernel<<<(uint32_t)((a.tile_pack_cap + 255) / 256), 256, 0, st>>>(a);
+	ctx->launches += 2;
 	CU(cudaGetLastError());
 	if (st_expand != st) {
 		CU(cudaEventRecord(s.ev_walk, st));
@@ -1240,7 +1244,7 @@ void kmcb200_destroy(kmcb200_ctx* ctx)
 	cudaDeviceSynchronize();
 	for (auto& s : ctx->slots) {
 		for (void* p : {(void*)s.recs_a, (void*)s.recs_b, (void*)s.recs_x, (void*)s.d_bin, (void*)s.d_pack_start, (void*)s.pack_nsk, (void*)s.pack_nk, (void*)s.pack_tbase,
-				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.zero, (void*)s.desc,
+				 (void*)s.pack_kbase, (void*)s.pack_done, (void*)s.sk_off, (void*)s.sk_kpre, (void*)s.tile_first, (void*)s.tile_pack, (void*)s.tile_desc, (void*)s.zero, (void*)s.desc,
 				 (void*)s.cdesc, (void*)s.pdesc, (void*)s.d_out, (void*)s.d_lut, (void*)s.d_result, (void*)s.msd_seg1, (void*)s.msd_start2, (void*)s.msd_start3,
 				 (void*)s.msd_item_base1, (void*)s.msd_item_base2, (void*)s.msd_item_seg2, (void*)s.msd_item_lo1, (void*)s.msd_item_cnt1,
 				 (void*)s.msd_cells, (void*)s.msd_cell_scan, (void*)s.msd_block_sums, (void*)s.leaf_tmp, (void*)s.leaf_emit, (void*)s.leaf_off, (void*)s.d_hist12, (void*)s.d_out_counter, (void*)s.tot_lut, (void*)s.tot_res, (void*)s.d_extras, (void*)s.d_pack_rec, (void*)s.d_blk_of_prefix, (void*)s.d_region_start})
