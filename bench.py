@@ -599,18 +599,19 @@ def main_ours(args, rank, world, local_rank):
         share = {nm: x / tot_ms for nm, x in acc.items()}
         dom = max((nm for nm in acc if nm != "other"), key=lambda nm: acc[nm])
         gbs = lambda nm: alg[nm] / (acc[nm] * 1e-3) / 1e9 if acc.get(nm, 0) > 0 else None
-        kernel_names = {"expand": "walk_packs_parallel_kernel + scan_packs_kernel + expand_kernel<1> (index + expansion of a bin)",
+        kernel_names = {"expand": "walk_packs_parallel_kernel + scan_packs_kernel + tile_desc_kernel + expand_kernel<1> (index + expansion of a bin)",
                         "msd_partition_L1": "msd_partition_kernel<1> (level-1 8-bit MSD partition pass)",
-                        "msd_partition_L2": "msd_partition_kernel<1,256|1024> (level-2 MSD partition pass, 8-10 bits)",
+                        "msd_partition_L2": "msd_partition_kernel<1,256|1024> (level-2 MSD partition pass, 8-9 bits)",
                         "msd_count_L2": "msd_count_kernel<1> + cell scan (level-2 digit counts)",
-                        "leaf_count": "leaf_warp_kernel<1,10> + leaf_scan/gather (count the leaves, emit the database records)"}
+                        "leaf_count": "leaf_hash_kernel<10> + leaf_scan/gather (count the leaves, emit the database records)"}
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if tj.get("stage") == dom:
-                    traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+                if dom in tj.get("stages", {}):
+                    traffic = tj["stages"][dom]["dram_bytes_per_launch"]
+                    traffic_src = "%s; kernel %s" % (tj.get("source"), tj["stages"][dom].get("kernel"))
             except Exception:
                 pass
         n_w = sum(weights)

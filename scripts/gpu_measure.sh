@@ -13,5 +13,5 @@ echo "reference rc=$?"; tail -c 900 gpurun_out/bench_${TAG}_reference.json; echo
 # launches each) + the first ~32 bins of the first warm-up step; --kill: the remaining ~10^5 launches of the run are not replayed under ncu
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 840 --kill on --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-secondary > gpurun_out/ncu_launches_${TAG}.log 2>&1
 echo "launch list rc=$?"; tail -2 gpurun_out/ncu_launches_${TAG}.log | cut -c1-300
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"expand_kernel|walk_packs_parallel|msd_partition|msd_count|leaf_warp" -s 6 -c 6 -o gpurun_out/prof_${TAG} python scripts/probe_bin.py 117440512 31 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"expand_kernel|walk_packs_parallel|msd_partition|msd_count|leaf_hash" -s 6 -c 6 -o gpurun_out/prof_${TAG} python scripts/probe_bin.py 117440512 31 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full rc=$?"; ls -la gpurun_out | tail -8

@@ -33,7 +33,11 @@ if os.path.exists(rp):
             ("smsp__inst_executed.sum", "warp insts"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"), ("launch__grid_size", "grid")]
     out.append("## `ncu --set full` (one capture per kernel instance; %s)\n" % os.path.basename(rp))
     out.append("| # | kernel | " + " | ".join(c[1] for c in cols) + " |\n|---|---|" + "---|" * len(cols))
-    traffic = None
+    traffic = {}          # stage of bench.py's roofline -> DRAM bytes of its main kernel (first capture of each)
+    stage_of = [("leaf_hash_kernel", "leaf_count"), ("leaf_warp_kernel", "leaf_count"), ("expand_kernel", "expand")]
+    def tobytes(x, unit):
+        return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    n_part = 0
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
         vals = []
@@ -44,16 +48,20 @@ if os.path.exists(rp):
             except ValueError: pass
             vals.append(v + (" " + u if u and u not in ("%",) else ""))
         out.append("| %s | `%s` | " % (r[0], name) + " | ".join(vals) + " |")
-        if "leaf_warp" in name and traffic is None:          # the dominant stage of the step (bench.py: roofline.stage = leaf_count)
-            def tobytes(x, unit):
-                return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-            traffic = tobytes(r[idx["dram__bytes_read.sum"]], rows[1][idx["dram__bytes_read.sum"]]) + tobytes(r[idx["dram__bytes_write.sum"]], rows[1][idx["dram__bytes_write.sum"]])
+        b = tobytes(r[idx["dram__bytes_read.sum"]], rows[1][idx["dram__bytes_read.sum"]]) + tobytes(r[idx["dram__bytes_write.sum"]], rows[1][idx["dram__bytes_write.sum"]])
+        st = next((s for k, s in stage_of if k in name), None)
+        if "msd_partition" in name:
+            n_part += 1
+            st = "msd_partition_L%d" % n_part if n_part <= 2 else None
+        if "msd_count" in name: st = "msd_count_L2"
+        if st and st not in traffic and float(r[idx["gpu__time_duration.sum"]]) > 20:          # (not the HEAVY instance that returns at once)
+            traffic[st] = {"kernel": name, "dram_bytes_per_launch": b}
     out.append("")
     if traffic:
-        json.dump({"stage": "leaf_count", "dram_bytes_per_launch": traffic,
-                   "source": "ncu --set full --clock-control none, %s: leaf_warp_kernel<1,10> on one bin of 117440512 k-mers (scripts/probe_bin.py), the workload's mean bin" % os.path.basename(rp)},
-                  open(os.path.join(P, "dominant_kernel_traffic.json"), "w"))
-        out.append("dominant-kernel (leaf_warp_kernel) DRAM traffic per launch: %.4g bytes (algorithmic N*W + U*7 = %.4g for N = 117440512)\n" % (traffic, 117440512 * 8.0 + 4858316 * 7.0))
+        src = "ncu --set full --clock-control none, %s: one bin of 117440512 k-mers (scripts/probe_bin.py), the workload's mean bin" % os.path.basename(rp)
+        json.dump({"source": src, "stages": traffic}, open(os.path.join(P, "dominant_kernel_traffic.json"), "w"), indent=1)
+        out.append("DRAM traffic per launch (bench.py reads the dominant stage's into roofline.traffic): " +
+                   ", ".join("%s %.4g B" % (k, v["dram_bytes_per_launch"]) for k, v in traffic.items()) + "\n")
 
 for suffix in ("", "_reference"):
     bp = os.path.join(G, "bench_%s%s.json" % (tag, suffix))
