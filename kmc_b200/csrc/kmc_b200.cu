@@ -10,6 +10,7 @@
 #include "msd_sort.cuh"
 #include "leaf_warp.cuh"
 #include "leaf_hash.cuh"
+#include "leaf_hash_wide.cuh"
 
 #include <cmath>
 #include <cstddef>
@@ -133,6 +134,7 @@ struct kmcb200_ctx {
 	bool use_leaf = true;                                   // KMCB200_LEAF=sort sorts the leaves + count_emit instead of counting them
 	int occ_leaf = 1;
 	int occ_leaf_hash = 1;
+	bool leaf_hash_wide = true;                             // KMCB200_LEAF_WIDE = hash | warp: records of more than one word by leaf_hash_wide_kernel / leaf_warp_kernel
 	bool leaf_hash = true;                                  // KMCB200_LEAF_KERNEL = hash | warp: one-word records are counted by leaf_hash_kernel (round 2) / leaf_warp_kernel
 	uint32_t leaf_max_b2 = 9;                               // KMCB200_LEAF_MAX_B2
 	uint32_t leaf_target = 1024;                            // KMCB200_LEAF_TARGET: mean leaf size the second partition level of a large bin aims at (leaf_hash_kernel)
@@ -721,13 +723,19 @@ __global__ void finish_result_kernel(uint64_t* result, uint64_t n_rec, const uin
 template <int WORDS, int SLOT_BITS>
 int launch_leaves(kmcb200_ctx* ctx, const LeafArgs& la, cudaStream_t st)
 {
-	if (WORDS == 1 && ctx->leaf_hash) {
+	if (ctx->leaf_hash && (WORDS == 1 || ctx->leaf_hash_wide)) {
 		const size_t hsmem = sizeof(LhSmem<SLOT_BITS>) * kLwWarps;
 		const uint32_t hgrid = std::min<uint32_t>((la.n_leaves + kLwWarps - 1) / kLwWarps, (uint32_t)(ctx->sm_count * ctx->occ_leaf_hash));
 		// (the usual cutoffs - cutoff_min >= 2, a cutoff_max no count of a leaf reaches - get the instance without the rarely needed transitions)
-		const bool simple = la.cutoff_min >= 2u && la.cutoff_max >= la.cutoff_min && (la.cutoff_max + 1u == 0u || la.cutoff_max + 1u > kLwHeavy + 1u);
-		if (simple) leaf_hash_kernel<SLOT_BITS, true><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
-		else leaf_hash_kernel<SLOT_BITS, false><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+		const uint32_t max_count = WORDS == 1 ? kLwHeavy : kLwMaxLeaf;
+		const bool simple = la.cutoff_min >= 2u && la.cutoff_max >= la.cutoff_min && (la.cutoff_max + 1u == 0u || la.cutoff_max + 1u > max_count + 1u);
+		if constexpr (WORDS == 1) {
+			if (simple) leaf_hash_kernel<SLOT_BITS, true><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+			else leaf_hash_kernel<SLOT_BITS, false><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+		} else {
+			if (simple) leaf_hash_wide_kernel<WORDS, SLOT_BITS, true><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+			else leaf_hash_wide_kernel<WORDS, SLOT_BITS, false><<<hgrid, 32 * kLwWarps, hsmem, st>>>(la);
+		}
 		ctx->launches++;
 		CU(cudaGetLastError());
 		return 0;
@@ -759,17 +767,25 @@ int setup_leaves(kmcb200_ctx* ctx)
 	CU(cudaFuncSetAttribute(leaf_warp_kernel<WORDS, SLOT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf, leaf_warp_kernel<WORDS, SLOT_BITS>, 32 * kLwWarps, smem));
 	if (ctx->occ_leaf < 1) ctx->occ_leaf = 1;
-	if (WORDS == 1) {
+	{
 		const int hsmem = (int)(sizeof(LhSmem<SLOT_BITS>) * kLwWarps);
-		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
-		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
-		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
-		CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
-		int occ_f = 1;
-		CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_leaf_hash, leaf_hash_kernel<SLOT_BITS, true>, 32 * kLwWarps, hsmem)));
-		CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, leaf_hash_kernel<SLOT_BITS, false>, 32 * kLwWarps, hsmem)));
-		ctx->occ_leaf_hash = std::min(ctx->occ_leaf_hash, occ_f);
-		if (ctx->occ_leaf_hash < 1) ctx->occ_leaf_hash = 1;
+		int occ_t = 1, occ_f = 1;
+		if constexpr (WORDS == 1) {
+			CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
+			CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+			CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
+			CU((cudaFuncSetAttribute(leaf_hash_kernel<SLOT_BITS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+			CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, leaf_hash_kernel<SLOT_BITS, true>, 32 * kLwWarps, hsmem)));
+			CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, leaf_hash_kernel<SLOT_BITS, false>, 32 * kLwWarps, hsmem)));
+		} else {
+			CU((cudaFuncSetAttribute(leaf_hash_wide_kernel<WORDS, SLOT_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
+			CU((cudaFuncSetAttribute(leaf_hash_wide_kernel<WORDS, SLOT_BITS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+			CU((cudaFuncSetAttribute(leaf_hash_wide_kernel<WORDS, SLOT_BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem)));
+			CU((cudaFuncSetAttribute(leaf_hash_wide_kernel<WORDS, SLOT_BITS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+			CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, leaf_hash_wide_kernel<WORDS, SLOT_BITS, true>, 32 * kLwWarps, hsmem)));
+			CU((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, leaf_hash_wide_kernel<WORDS, SLOT_BITS, false>, 32 * kLwWarps, hsmem)));
+		}
+		ctx->occ_leaf_hash = std::max(1, std::min(occ_t, occ_f));
 	}
 	return 0;
 }
@@ -1198,6 +1214,7 @@ int kmcb200_create(const kmcb200_params* prm, kmcb200_ctx** out_ctx)
 	if (const char* e = getenv("KMCB200_L2_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 10) ctx->force_b2 = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_ROUND_PCT")) { const int v = atoi(e); if (v >= 50 && v <= 1000) ctx->leaf_round_pct = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_KERNEL")) ctx->leaf_hash = std::string(e) != "warp";
+	if (const char* e = getenv("KMCB200_LEAF_WIDE")) ctx->leaf_hash_wide = std::string(e) != "warp";
 	if (const char* e = getenv("KMCB200_LEAF_MAX_B2")) { const int v = atoi(e); if (v >= 8 && v <= 10) ctx->leaf_max_b2 = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_TARGET")) { const int v = atoi(e); if (v >= 128 && v <= 8192) ctx->leaf_target = (uint32_t)v; }
 	if (const char* e = getenv("KMCB200_LEAF_FILL_PCT")) { const int v = atoi(e); if (v >= 10 && v <= 85) ctx->leaf_fill_pct = (uint32_t)v; }

@@ -47,7 +47,7 @@ def test_leaf_count_cutoffs_and_prefix_lengths(oracle, p_len, cmin, cmax, cntmax
 
 
 @pytest.mark.parametrize("cmin,cmax,cntmax", [(1, 10 ** 9, 255), (2, 3, 255), (1, 1, 255), (3, 2, 255), (2, 2 ** 32 - 1, 2), (5, 100, 65535)])
-@pytest.mark.parametrize("k,both", [(31, True), (32, False), (17, True)])
+@pytest.mark.parametrize("k,both", [(31, True), (32, False), (17, True), (55, True), (96, False)])
 def test_leaf_hash_cutoff_instances(oracle, k, both, cmin, cmax, cntmax):
     """leaf_hash_kernel: the SIMPLE instance (cutoff_min >= 2, unreachable cutoff_max) and the general one - cutoff_min = 1 (a claim is already a
     survivor), reachable cutoff_max (second bitmap), cutoff_max < cutoff_min (nothing survives, everything counts as n_cutoff_max)."""
@@ -57,16 +57,18 @@ def test_leaf_hash_cutoff_instances(oracle, k, both, cmin, cmax, cntmax):
 
 @pytest.mark.parametrize("env", [{"KMCB200_LEAF_FILL_PCT": "10"}, {"KMCB200_LEAF_RATIO0": "8"}, {"KMCB200_LEAF_RATIO0": "256", "KMCB200_LEAF_FILL_PCT": "85"},
                                  {"KMCB200_L2_BITS": "2"}, {"KMCB200_L2_BITS": "2", "KMCB200_LEAF_RATIO0": "8", "KMCB200_LEAF_SLOT_BITS": "8"},
-                                 {"KMCB200_LEAF_KERNEL": "warp"}])
+                                 {"KMCB200_LEAF_KERNEL": "warp"}, {"KMCB200_LEAF_WIDE": "warp"}])
 @pytest.mark.parametrize("coverage", ["30x", "distinct"])
-def test_leaf_hash_round_planning(oracle, monkeypatch, env, coverage):
+@pytest.mark.parametrize("k", [31, 55])
+def test_leaf_hash_round_planning(oracle, monkeypatch, env, coverage, k):
     """leaf_hash_kernel plans its table rounds from a running estimate of distinct k-mers per record: rounds planned far too small (many
     predicated rounds over the leaf), far too large (the table fills up: the round is split on the next bit, binary descent), leaves of
-    ~10^4 records in 256-slot tables, duplicate-rich and all-distinct k-mers; and the round-1 kernel (leaf_warp_kernel) stays selectable."""
+    ~10^4 records in 256-slot tables, duplicate-rich and all-distinct k-mers, one-word and two-word records (leaf_hash_wide_kernel); and the
+    round-1 kernel (leaf_warp_kernel) stays selectable."""
     for k_, v in env.items():
         monkeypatch.setenv(k_, v)
-    p = Params(k=31, cutoff_min=2 if coverage == "30x" else 1, lut_prefix_len=7)
-    b = synth_bin(5, 31, 26000, genome_len=10000, err=0.01) if coverage == "30x" else synth_bin(6, 31, 16000, genome_len=4000000, err=0.0)
+    p = Params(k=k, cutoff_min=2 if coverage == "30x" else 1, lut_prefix_len=7)
+    b = synth_bin(5, k, 26000, genome_len=10000, err=0.01) if coverage == "30x" else synth_bin(6, k, 16000, genome_len=4000000, err=0.0)
     _check_bin(oracle, b, p)
 
 
