@@ -22,8 +22,11 @@
  *   KMCB200_SORT=lsd               plain 8-bit LSD passes instead of the hybrid MSD sort
  *   KMCB200_LEAF=sort              sort the leaves on chip + count_emit instead of counting them in hash tables
  *   KMCB200_LEAF_SLOT_BITS=8|9|10  slots of a warp's leaf table (default 10)
- *   KMCB200_LEAF_ROUND_PCT=n       records per table round in percent of the slots (default 100)
- *   KMCB200_L2_BITS=1..10          bits of the second partition level (default: from the bin size, <= 10)
+ *   KMCB200_LEAF_KERNEL=warp       round 1's leaf kernel (ordered groups, leaf_warp.cuh) instead of leaf_hash_kernel; KMCB200_LEAF_WIDE=warp: for records of > 1 word only
+ *   KMCB200_LEAF_FILL_PCT=n        leaf_hash_kernel plans a table round for this load (default 62); KMCB200_LEAF_RATIO0=n: first guess of distinct k-mers per record x 256 (default 90)
+ *   KMCB200_LEAF_ROUND_PCT=n       leaf_warp_kernel: records per table round in percent of the slots (default 100)
+ *   KMCB200_L2_BITS=1..10          bits of the second partition level (default: from the bin size: 8, from ~10^8 one-word k-mers on 9; wider records up to 10)
+ *   KMCB200_LEAF_TARGET=n, KMCB200_LEAF_MAX_B2=8..10   mean leaf size / most bits the default rule aims at for one-word records (1024, 9)
  *   KMCB200_MAX_BLOCK_RECORDS=n    a bin with more k-mers is counted key block by key block (default: what 60 % of the free HBM holds, < 2^32)
  *   KMCB200_KEY_BLOCKS=filter     key blocks of an oversized bin re-expand it with a filter (default: one scattering expansion when the records fit in HBM once)
  *   KMCB200_KEY_BLOCK_RECORDS=n    preferred size of a key block in the scattering flow (default 2^28)
