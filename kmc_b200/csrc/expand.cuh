@@ -541,6 +541,8 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads, WORDS <= 2 ? 2048 
 	__shared__ uint32_t htop[256];
 	static_assert(HW <= 128 && HW % 32 == 0, "the head bitmap is scanned by one warp, HW / 32 words per lane");
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t le_mask = 0xffffffffu >> (31u - lane);
+	static_assert(kExpandThreads % 32 == 0, "output slot i * threads + tid belongs to lane tid % 32");
 	if (tid < 256) htop[tid] = 0;
 	const uint32_t total_tiles = a.status[1];
 	Rec<WORDS>* __restrict__ out = reinterpret_cast<Rec<WORDS>*>(a.recs);
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(ExpandCfg<WORDS>::kThreads, WORDS <= 2 ? 2048 
 		// striped extraction: consecutive lanes <-> consecutive output k-mers
 		const uint64_t obase = ((uint64_t)db.w << 32) | db.z;
 		auto kmer_of = [&](uint32_t slot) -> Rec<WORDS> {
-			const uint32_t rel = hpre[slot >> 5] + __popc(hbits[slot >> 5] & (0xffffffffu >> (31u - (slot & 31u))));
+			const uint32_t rel = hpre[slot >> 5] + __popc(hbits[slot >> 5] & le_mask);          // (slot = i * threads + tid: bit (slot & 31) is this lane's)
 			if (staged) return extract_kmer_be32<WORDS>(reinterpret_cast<const uint32_t*>(s_bytes), s_bit[rel] + 2u * slot, a.k, a.both_strands != 0);
 			const uint32_t j = j_lo + rel;
 			const uint32_t s = tile_start + slot - kpre[j];

@@ -607,6 +607,27 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint8_t* tmp, co
 	const uint32_t nbytes = leaf_emit[leaf] * ob;
 	const uint8_t* src = tmp + start[leaf] * pad;
 	uint8_t* dst = out + ((out_base ? *out_base : 0ull) + leaf_off[leaf]) * ob;      // out_base: records of earlier key blocks (oversized bins)
+	if (ob <= 8) {
+		// records of up to 8 bytes (k - p <= 28 with a one-byte counter: the usual case): a lane takes a whole padded record with one 8-byte load
+		// and stores its bytes (per store instruction the warp writes 32 bytes spread over 32 * ob: a few sectors); half the instructions of
+		// the byte-by-byte loop below, and wide loads
+		const uint32_t n = leaf_emit[leaf];
+		const unsigned long long* src8 = reinterpret_cast<const unsigned long long*>(src);
+		for (uint32_t r0 = 0; r0 < n; r0 += 64) {
+			unsigned long long v[2];
+#pragma unroll
+			for (int u = 0; u < 2; ++u) { const uint32_t r = r0 + u * 32 + lane; v[u] = r < n ? __ldg(src8 + r) : 0ull; }
+#pragma unroll
+			for (int u = 0; u < 2; ++u) {
+				const uint32_t r = r0 + u * 32 + lane;
+				if (r < n) {
+					uint8_t* d = dst + (size_t)r * ob;
+					for (uint32_t b = 0; b < ob; ++b) d[b] = (uint8_t)(v[u] >> (8 * b));
+				}
+			}
+		}
+		return;
+	}
 	const uint32_t magic = 0xFFFFFFFFu / ob + 1;          // p / ob == umulhi(p, magic) for p < 2^16 ... checked: larger leaves take the division
 	const bool use_magic = nbytes < 65536u && ob > 1;     // (ob == 1: magic wraps to 0, and p / 1 needs no trick)
 	// (4 independent byte loads in flight per lane: the loop is bound by the latency of its loads)

@@ -525,16 +525,22 @@ __global__ void __launch_bounds__(1024) msd_bounds_kernel(const MsdBoundsArgs a)
 		uint32_t bi = carry_i;
 		for (uint32_t w = 0; w < warp; ++w) bi += s_i[w];
 		const uint32_t ei = bi + ii - ni;
-		if (a.tile && m < M) {
-			a.item_base[m] = ei;
-			for (uint32_t t = 0; t < ni; ++t) a.item_seg[ei + t] = m;
-		}
+		if (a.tile && m < M) a.item_base[m] = ei;
 		__syncthreads();
 		if (tid == 1023) carry_i = ei + ni;
 		__syncthreads();
 	}
 	if (tid == 0 && a.tile) { a.item_base[M] = carry_i; *a.n_items = carry_i; }
 	if (over) atomicOr(a.flags, kMsdFlagFallback);
+	// the segment of every item: one WARP per bucket (after level 1 there are 256 buckets of ~100 items each: a thread per bucket writing
+	// its items one after the other took 35 us of this kernel's 36)
+	if (a.tile) {
+		__syncthreads();          // item_base[] of this CTA's threads is visible
+		for (uint32_t m = warp; m < M; m += 32) {
+			const uint32_t e0 = a.item_base[m], e1 = a.item_base[m + 1];
+			for (uint32_t i = e0 + lane; i < e1; i += 32) a.item_seg[i] = m;
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
