@@ -1,6 +1,7 @@
 // kmc_b200 — host side of the C ABI (include/kmc_b200.h): context, HBM workspace, launch sequences.
 // The per-bin sequence mirrors CKmerBinSorter<SIZE>::ProcessBins (kmc_core/kb_sorter.h:210-237):
-//   Expand (index + expand kernels) -> Sort (one radix_pass_kernel per key byte) -> Compact (count_emit_kernel).
+//   Expand (index + expand kernels) -> Sort (two MSD partition levels) + Compact fused in the leaf kernels (leaf_hash.cuh, leaf_hash_wide.cuh);
+//   behind a device flag: Sort (one cooperative lsd_sort_kernel over all key bytes) -> Compact (count_emit_kernel).
 #include "../../include/kmc_b200.h"
 #include "common.cuh"
 #include "expand.cuh"
@@ -794,7 +795,7 @@ int setup_leaves(kmcb200_ctx* ctx)
 
 template <int WORDS> int setup_leaves_w(kmcb200_ctx* ctx) { return DISPATCH_SLOTS(ctx, setup_leaves, WORDS, ctx); }
 
-// Partition (two MSD levels), then COUNT the leaves (leaf_warp.cuh) instead of sorting them; the LSD passes + count_emit_kernel
+// Partition (two MSD levels), then COUNT the leaves (leaf_hash.cuh / leaf_hash_wide.cuh; leaf_warp.cuh as an option) instead of sorting them; the LSD passes + count_emit_kernel
 // stand behind as the device-flagged fallback (they return at once unless a leaf could not be counted).
 template <int WORDS>
 int run_sort_count_leaves(kmcb200_ctx* ctx, Slot& s, uint64_t n_rec, uint32_t np_eff, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_lut, uint64_t* d_result, cudaStream_t st,
